@@ -1,0 +1,254 @@
+"""Bound *specs* and their device serialisation.
+
+A spec is a plain dictionary holding exactly the state the reference keeps on
+a bound object:
+
+    ell  = dict(c=f64[de], B=f64[de,de], B_inv=f64[de,de])
+           (``Ellipsoid.c/B/B_inv``, nautilus/bounds/basic.py:303-309)
+    mix  = dict(dim_cube=bool[d], ell=ell | None)
+           (``UnitCubeEllipsoidMixture``, nautilus/bounds/basic.py:491-563)
+    emu  = dict(mean, scale, coefs=[[W..] per net], intercepts=[[b..] per net])
+           (``NeuralNetworkEmulator``, nautilus/neural.py:74-98)
+    nb   = dict(ell=ell, emulator=emu | None, score_predict_min=float)
+           (``NeuralBound``, nautilus/bounds/neural.py:61-97)
+    spec = dict(kind='nautilus', n_dim, unit, log_v_all=f64[K],
+                mixtures=[mix]*K, neural=[nb]*J)
+           (``NautilusBound`` + its outer ``Union``,
+            nautilus/bounds/nautilus.py:88-144, nautilus/bounds/union.py:117-151)
+    spec = dict(kind='cube', n_dim)          (``UnitCube``, basic.py:9)
+
+``pack_stack`` turns a list of specs (a bound and the later bounds that carve
+its shell, nautilus/sampler.py:796-801) into the two flat arrays the CUDA
+kernels read: ``meta`` (int32) and ``data`` (float64).  The layout is
+documented in ``include/nautilus_b200.h`` and mirrored by ``nb200_blob.cuh``.
+"""
+
+import numpy as np
+
+HDR = 16        # ints in a bound record header
+MIX_REC = 8     # ints per mixture record
+NB_REC = 12     # ints per neural-bound record
+D_MAX = 128     # largest supported dimensionality
+W_MAX = 256     # largest supported hidden width
+
+
+# --------------------------------------------------------------------------
+# flat <-> nested (for .npz fixtures and checkpoints)
+# --------------------------------------------------------------------------
+
+def spec_to_flat(spec, prefix=''):
+    """Flatten a spec into ``{str: ndarray}`` suitable for ``np.savez``."""
+    out = {prefix + 'kind': np.array(spec['kind']),
+           prefix + 'n_dim': np.array(spec['n_dim'])}
+    if spec['kind'] == 'cube':
+        return out
+    out[prefix + 'unit'] = np.array(bool(spec['unit']))
+    out[prefix + 'log_v_all'] = np.asarray(spec['log_v_all'], dtype=float)
+    out[prefix + 'K'] = np.array(len(spec['mixtures']))
+    out[prefix + 'J'] = np.array(len(spec['neural']))
+    for k, mix in enumerate(spec['mixtures']):
+        p = '{}mix{}_'.format(prefix, k)
+        out[p + 'dim_cube'] = np.asarray(mix['dim_cube'], dtype=bool)
+        if mix['ell'] is not None:
+            for key in ('c', 'B', 'B_inv'):
+                out[p + key] = np.asarray(mix['ell'][key], dtype=float)
+    for j, nb in enumerate(spec['neural']):
+        p = '{}nb{}_'.format(prefix, j)
+        for key in ('c', 'B', 'B_inv'):
+            out[p + key] = np.asarray(nb['ell'][key], dtype=float)
+        out[p + 'score_predict_min'] = np.array(float(
+            nb['score_predict_min']))
+        emu = nb['emulator']
+        if emu is not None:
+            out[p + 'mean'] = np.asarray(emu['mean'], dtype=float)
+            out[p + 'scale'] = np.asarray(emu['scale'], dtype=float)
+            out[p + 'n_net'] = np.array(len(emu['coefs']))
+            out[p + 'n_lay'] = np.array(len(emu['coefs'][0]))
+            for n, (ws, bs) in enumerate(zip(emu['coefs'],
+                                             emu['intercepts'])):
+                for i, (w, b) in enumerate(zip(ws, bs)):
+                    out['{}W{}_{}'.format(p, n, i)] = np.asarray(w, float)
+                    out['{}b{}_{}'.format(p, n, i)] = np.asarray(b, float)
+    return out
+
+
+def flat_to_spec(flat, prefix=''):
+    """Inverse of :func:`spec_to_flat`."""
+    kind = str(flat[prefix + 'kind'])
+    spec = dict(kind=kind, n_dim=int(flat[prefix + 'n_dim']))
+    if kind == 'cube':
+        return spec
+    spec['unit'] = bool(flat[prefix + 'unit'])
+    spec['log_v_all'] = np.array(flat[prefix + 'log_v_all'], dtype=float)
+    spec['mixtures'] = []
+    for k in range(int(flat[prefix + 'K'])):
+        p = '{}mix{}_'.format(prefix, k)
+        ell = None
+        if p + 'c' in flat:
+            ell = {key: np.array(flat[p + key], dtype=float)
+                   for key in ('c', 'B', 'B_inv')}
+        spec['mixtures'].append(dict(
+            dim_cube=np.array(flat[p + 'dim_cube'], dtype=bool), ell=ell))
+    spec['neural'] = []
+    for j in range(int(flat[prefix + 'J'])):
+        p = '{}nb{}_'.format(prefix, j)
+        ell = {key: np.array(flat[p + key], dtype=float)
+               for key in ('c', 'B', 'B_inv')}
+        emu = None
+        if p + 'mean' in flat:
+            n_net, n_lay = int(flat[p + 'n_net']), int(flat[p + 'n_lay'])
+            emu = dict(
+                mean=np.array(flat[p + 'mean'], dtype=float),
+                scale=np.array(flat[p + 'scale'], dtype=float),
+                coefs=[[np.array(flat['{}W{}_{}'.format(p, n, i)])
+                        for i in range(n_lay)] for n in range(n_net)],
+                intercepts=[[np.array(flat['{}b{}_{}'.format(p, n, i)])
+                             for i in range(n_lay)] for n in range(n_net)])
+        spec['neural'].append(dict(
+            ell=ell, emulator=emu,
+            score_predict_min=float(flat[p + 'score_predict_min'])))
+    return spec
+
+
+# --------------------------------------------------------------------------
+# spec -> (meta, data) device blob
+# --------------------------------------------------------------------------
+
+class _Data:
+    def __init__(self):
+        self.chunks = []
+        self.n = 0
+
+    def add(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        off = self.n
+        self.chunks.append(a)
+        self.n += len(a)
+        if self.n % 2:                      # keep every array 16-byte aligned
+            self.chunks.append(np.zeros(1))
+            self.n += 1
+        return off
+
+    def array(self):
+        if not self.chunks:
+            return np.zeros(2)
+        return np.concatenate(self.chunks)
+
+
+def _is_lower(m):
+    return bool(np.all(np.triu(m, 1) == 0))
+
+
+def _pack_ell(data, ell):
+    off_c = data.add(ell['c'])
+    off_b = data.add(ell['B'])
+    off_binv = data.add(ell['B_inv'])
+    return off_c, off_b, off_binv, int(_is_lower(ell['B_inv']))
+
+
+def union_cdf(log_v_all):
+    """CDF of the volume-proportional ellipsoid choice
+    (p from nautilus/bounds/union.py:308); last entry forced to 1."""
+    log_v_all = np.asarray(log_v_all, dtype=float)
+    m = np.max(log_v_all)
+    p = np.exp(log_v_all - (m + np.log(np.sum(np.exp(log_v_all - m)))))
+    cdf = np.cumsum(p)
+    cdf[-1] = 1.0
+    return cdf
+
+
+def pack_record(spec, data, cdf=None):
+    """Serialise one bound; returns its int32 record (offsets into ``data``
+    are absolute, offsets into ``meta`` are relative to the record start)."""
+    d = int(spec['n_dim'])
+    if d > D_MAX:
+        raise ValueError('n_dim={} exceeds the supported maximum {}.'.format(
+            d, D_MAX))
+    if spec['kind'] == 'cube':
+        rec = np.zeros(HDR, dtype=np.int32)
+        rec[0], rec[1], rec[2] = HDR, 0, d
+        return rec
+    K, J = len(spec['mixtures']), len(spec['neural'])
+    hdr = np.zeros(HDR, dtype=np.int32)
+    hdr[1:6] = (1, d, K, J, int(bool(spec['unit'])))
+    if cdf is None:
+        cdf = union_cdf(spec['log_v_all'])
+    hdr[6] = data.add(cdf)
+    tail = []          # variable-length int tables appended after records
+    base_tail = HDR + K * MIX_REC + J * NB_REC
+    mix_recs = np.zeros((K, MIX_REC), dtype=np.int32)
+    for k, mix in enumerate(spec['mixtures']):
+        dim_cube = np.asarray(mix['dim_cube'], dtype=bool)
+        idx_ell = np.flatnonzero(~dim_cube)
+        idx_cube = np.flatnonzero(dim_cube)
+        if mix['ell'] is None and len(idx_ell) > 0:
+            raise ValueError('mixture without ellipsoid must be all-cube')
+        off_idx = base_tail + sum(len(t) for t in tail)
+        tail.append(np.concatenate([idx_ell, idx_cube]).astype(np.int32))
+        if mix['ell'] is not None:
+            off_c, off_b, off_binv, tri = _pack_ell(data, mix['ell'])
+        else:
+            off_c = off_b = off_binv = -1
+            tri = 1
+        mix_recs[k] = (len(idx_ell), len(idx_cube), off_idx, off_c, off_b,
+                       off_binv, tri, 0)
+    nb_recs = np.zeros((J, NB_REC), dtype=np.int32)
+    max_width = 1
+    for j, nb in enumerate(spec['neural']):
+        off_c, _, off_binv, tri = _pack_ell(data, nb['ell'])
+        emu = nb['emulator']
+        if emu is None:
+            nb_recs[j] = (off_c, off_binv, tri, 0, 0, -1, -1, -1, -1, -1, 0, 0)
+            continue
+        n_net, n_lay = len(emu['coefs']), len(emu['coefs'][0])
+        sizes = [emu['coefs'][0][0].shape[0]] + [
+            w.shape[1] for w in emu['coefs'][0]]
+        if sizes[0] != d or sizes[-1] != 1:
+            raise ValueError('emulator layer sizes {} do not map {} -> 1'
+                             .format(sizes, d))
+        if max(sizes) > W_MAX:
+            raise ValueError('hidden width above {}'.format(W_MAX))
+        max_width = max(max_width, max(sizes))
+        off_mean = data.add(emu['mean'])
+        off_scale = data.add(emu['scale'])
+        off_thr = data.add([float(nb['score_predict_min']) - 1e-9,
+                            float(nb['score_predict_min'])])
+        off_sizes = base_tail + sum(len(t) for t in tail)
+        tail.append(np.asarray(sizes, dtype=np.int32))
+        wtab = []
+        for ws, bs in zip(emu['coefs'], emu['intercepts']):
+            if [w.shape for w in ws] != [
+                    (sizes[i], sizes[i + 1]) for i in range(n_lay)]:
+                raise ValueError('all networks must share one architecture')
+            for w, b in zip(ws, bs):
+                wtab += [data.add(w), data.add(b)]
+        off_wtab = base_tail + sum(len(t) for t in tail)
+        tail.append(np.asarray(wtab, dtype=np.int32))
+        nb_recs[j] = (off_c, off_binv, tri, n_net, n_lay, off_mean, off_scale,
+                      off_thr, off_sizes, off_wtab, 0, 0)
+    hdr[7] = HDR
+    hdr[8] = HDR + K * MIX_REC
+    hdr[9] = max_width
+    rec = np.concatenate([hdr, mix_recs.ravel(), nb_recs.ravel()] + tail)
+    rec = rec.astype(np.int32)
+    rec[0] = len(rec)
+    return rec
+
+
+def pack_stack(specs):
+    """Serialise a list of bounds.
+
+    Returns ``(meta int32[], data float64[])``; ``meta[0]`` = number of
+    bounds L, ``meta[1 + i]`` = start of record i.
+    """
+    data = _Data()
+    recs = [pack_record(s, data) for s in specs]
+    L = len(recs)
+    table = np.zeros(1 + L, dtype=np.int32)
+    table[0] = L
+    off = 1 + L
+    for i, r in enumerate(recs):
+        table[1 + i] = off
+        off += len(r)
+    meta = np.concatenate([table] + recs).astype(np.int32)
+    return meta, data.array()
