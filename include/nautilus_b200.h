@@ -1,0 +1,213 @@
+/*
+ * nautilus_b200 -- C ABI of the B200-native importance-nested-sampling cycle.
+ *
+ * The reference (johannesulf/nautilus v1.0.6) is pure Python and has no FFI;
+ * its seam is Python duck typing.  This header is the boundary
+ * a maintainer would bind (ctypes): every entry point is
+ * `extern "C"`, takes plain pointers / sizes / scalars, and names the reference
+ * method it replaces.  All `file:line` citations are relative to
+ * /root/reference/nautilus/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     nb200_last_error() returns a thread-local message for the last failure.
+ *   - `*_d` pointers are DEVICE pointers on the current CUDA device, `*_h`
+ *     pointers are HOST pointers.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Device-pointer entry points only
+ *     enqueue work; they do not synchronise.
+ *   - points are row-major float64 [n, d]; masks / flags are uint8; counters
+ *     are int64.  d <= NB200_D_MAX.
+ *   - bounds are passed as a serialised *stack* (meta int32[], data float64[])
+ *     produced by nautilus_b200/_pack.py:pack_stack; `bound` selects a record.
+ *     The host copy of `meta` is needed because launch shapes depend on it.
+ *
+ * Blob layout (mirrored by nautilus_b200/csrc/nb200_blob.cuh)
+ *   meta[0] = L (#bounds); meta[1+i] = start of record i.
+ *   record header (16 ints): len, kind(0 cube,1 nautilus), d, K, J, unit,
+ *       off_cdf(data), off_mix(rel), off_neural(rel), max_width, 0...
+ *   mixture record (8 ints): de, nc, off_idx(rel; d ints: ellipsoid dims then
+ *       cube dims), off_c, off_B, off_Binv (data; -1 if de==0), binv_is_lower, 0
+ *   neural record (12 ints): off_c, off_Binv, binv_is_lower, n_net, n_lay,
+ *       off_mean, off_scale, off_thr(data: {score_predict_min-1e-9, raw}),
+ *       off_sizes(rel; n_lay+1 ints), off_wtab(rel; n_net*n_lay*{off_W,off_b}),
+ *       0, 0
+ */
+#ifndef NAUTILUS_B200_H
+#define NAUTILUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_VERSION 100
+#define NB200_D_MAX 128
+#define NB200_W_MAX 256
+
+/* disposition of a raw proposal (one byte per proposal) */
+#define NB200_CODE_CUBE_REJECT 0     /* bounds/union.py:313-314            */
+#define NB200_CODE_OVERLAP_REJECT 1  /* bounds/union.py:316-319            */
+#define NB200_CODE_NN_REJECT 2       /* bounds/nautilus.py:217-219         */
+#define NB200_CODE_EXCLUDED 3        /* sampler.py:796-801                 */
+#define NB200_CODE_IN_SHELL 4        /* likelihood evaluated               */
+
+/* emulator arithmetic */
+#define NB200_MLP_F64 0   /* fp64 CUDA cores, canonical summation order     */
+#define NB200_MLP_TF32 1  /* tcgen05 kind::tf32, fp32 accumulate in TMEM    */
+
+/* built-in synthetic likelihoods; params are float64        */
+#define NB200_LIKE_GAUSSIAN 0    /* {inv_sigma2, norm, mu[d]}                */
+#define NB200_LIKE_ROSENBROCK 1  /* {lo, width}  theta = lo + width * u      */
+#define NB200_LIKE_MIXTURE 2     /* {M, inv_sigma2, norm, mu[M*d]}           */
+#define NB200_LIKE_EQUICORR 3    /* {a, b, norm, mu[d]}: -0.5(a*S2 - b*S1^2) */
+
+/* indices into the int64 counters written by nb200_cycle / nb200_stats      */
+#define NB200_CNT_RAW 0
+#define NB200_CNT_CUBE_REJECT 1
+#define NB200_CNT_OVERLAP_REJECT 2
+#define NB200_CNT_NN_REJECT 3
+#define NB200_CNT_EXCLUDED 4
+#define NB200_CNT_IN_SHELL 5
+#define NB200_CNT_UPDATE 6 /* #(log_l >= log_l_min), sampler.py:1144        */
+#define NB200_N_CNT 8
+/* float64 sums: {max, sum exp(l-max), sum exp(2(l-max)), 0}                 */
+#define NB200_N_LSE 4
+
+const char* nb200_last_error(void);
+int nb200_version(void);
+/* sm_count, compute capability of the current device */
+int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in this process (for
+ * bench.py's gpu_launches) */
+int64_t nb200_launch_count(void);
+
+/* ---- Ellipsoid (bounds/basic.py:244-449) ------------------------------ */
+
+/* Ellipsoid.transform, basic.py:339-342.  inverse==0: out = M (x - c) with
+ * M = B_inv; inverse!=0: out = M x + c with M = B.  M is dense d*d row-major. */
+int nb200_ell_transform(const double* points_d, int64_t n, int d,
+                        const double* c_d, const double* M_d, int inverse,
+                        double* out_d, void* stream);
+/* Ellipsoid.contains, basic.py:360: sum((B_inv (x-c))^2) < 1 (strict).
+ * r2_d may be NULL; otherwise receives the squared Mahalanobis radius. */
+int nb200_ell_contains(const double* points_d, int64_t n, int d,
+                       const double* c_d, const double* Binv_d,
+                       uint8_t* out_d, double* r2_d, void* stream);
+/* Ellipsoid.sample with explicit base randoms, basic.py:376-381:
+ * z f64[n,d] normals, u f64[n] uniforms. */
+int nb200_ell_sample_from(const double* z_d, const double* u_d, int64_t n,
+                          int d, const double* c_d, const double* B_d,
+                          double* out_d, void* stream);
+
+/* ---- Union / UnitCubeEllipsoidMixture (bounds/union.py, basic.py:452) -- */
+
+/* Union.contains (union.py:285-289) and the overlap count
+ * n_bound = sum_k contains_k (union.py:316-317).  in_mask_d may be NULL (all
+ * points).  count_d / contains_d may each be NULL. */
+int nb200_union_count(const int32_t* meta_h, const int32_t* meta_d,
+                      const double* data_d, int bound,
+                      const double* points_d, const uint8_t* in_mask_d,
+                      int64_t n, int32_t* count_d, uint8_t* contains_d,
+                      void* stream);
+
+/* Raw draws of one Union.sample pass (union.py:305-319) for proposals
+ * offset .. offset+n-1: choose ellipsoid k ~ p_k, draw inside mixture k,
+ * unit-cube filter, overlap count, accept iff r > 1 - 1/n_bound.
+ * Philox mode: k_d == NULL; randoms come from Philox4x32-10 keyed by `seed`
+ * with counter (proposal index, block, stream_id).
+ * Test mode: k_d i32[n], z_d f64[n,d] (first de columns used), cube_u_d
+ * f64[n,d] (first nc columns), u_d f64[n], r_d f64[n] supplied by the host
+ * exactly as the reference drew them.
+ * Outputs: points f64[n,d], code u8[n] (0, 1 or 4), n_bound i32[n] (may be
+ * NULL).  For a UnitCube record (sampler shell 0, basic.py:85) points are
+ * uniform and code is 4. */
+int nb200_union_propose(const int32_t* meta_h, const int32_t* meta_d,
+                        const double* data_d, int bound, int64_t n,
+                        uint64_t seed, uint64_t offset, uint32_t stream_id,
+                        const int32_t* k_d, const double* z_d,
+                        const double* cube_u_d, const double* u_d,
+                        const double* r_d, double* points_d, uint8_t* code_d,
+                        int32_t* n_bound_d, void* stream);
+
+/* ---- NeuralNetworkEmulator (neural.py:100-116) ------------------------- */
+
+/* emulator.predict of neural bound j of `bound` on whitened coordinates
+ * x f64[n,d] (the standardisation (x-mean)/scale is applied inside). */
+int nb200_mlp_predict(const int32_t* meta_h, const int32_t* meta_d,
+                      const double* data_d, int bound, int j,
+                      const double* x_d, int64_t n, double* out_d,
+                      int mlp_mode, void* workspace_d, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- NautilusBound.contains (bounds/nautilus.py:146-169) --------------- */
+
+/* which: 0 = full bound (union & any neural), 1 = union only,
+ * 2 = any NeuralBound only (the filter of NautilusBound.sample,
+ * nautilus.py:217-218).  in_mask_d may be NULL. */
+int nb200_bound_contains(const int32_t* meta_h, const int32_t* meta_d,
+                         const double* data_d, int bound, int which,
+                         const double* points_d, const uint8_t* in_mask_d,
+                         int64_t n, uint8_t* out_d, int mlp_mode,
+                         void* workspace_d, size_t workspace_bytes,
+                         void* stream);
+
+/* bytes of scratch the bound-level entry points need for n points in d dims */
+size_t nb200_workspace_bytes(int64_t n, int d);
+
+/* ---- shell reductions (sampler.py:925-943, 1144) ----------------------- */
+
+/* One-pass (max, sum e^{l-m}, sum e^{2(l-m)}) over log_l[i] with code[i]==4
+ * (code_d NULL = all), plus the disposition histogram and
+ * #(log_l >= log_l_min).  lse_d f64[4], counters_d i64[8].  Deterministic:
+ * fixed-shape tree, no atomics. */
+int nb200_stats(const double* log_l_d, const uint8_t* code_d, int64_t n,
+                double log_l_min, double* lse_d, int64_t* counters_d,
+                void* workspace_d, size_t workspace_bytes, void* stream);
+
+/* built-in likelihood on points with code==4 (code_d NULL = all) */
+int nb200_loglike(const double* points_d, const uint8_t* code_d, int64_t n,
+                  int d, int like_id, const double* params_d, int n_params,
+                  double* log_l_d, void* stream);
+
+/* stable compaction of the rows with code==4 into out_points / out_log_l
+ * (either may be NULL); *n_out_d receives the count. */
+int nb200_compact(const double* points_d, const double* log_l_d,
+                  const uint8_t* code_d, int64_t n, int d,
+                  double* out_points_d, double* out_log_l_d, int64_t* n_out_d,
+                  void* workspace_d, size_t workspace_bytes, void* stream);
+
+/* ---- the full cycle (sampler.py:1093-1144 over one raw batch) ---------- */
+
+/* n raw proposals from stack record `bound`, filtered by its neural bounds,
+ * excluded by records first_later .. first_later+n_later-1, likelihood
+ * `like_id` (or none if like_id < 0), reductions.  Outputs: points f64[n,d],
+ * log_l f64[n] (NaN unless code 4), code u8[n], lse f64[4], counters i64[8].
+ */
+int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
+                const double* data_d, int bound, int first_later, int n_later,
+                int64_t n, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                int like_id, const double* like_params_d, int n_like_params,
+                double log_l_min, int mlp_mode, double* points_d,
+                double* log_l_d, uint8_t* code_d, double* lse_d,
+                int64_t* counters_d, void* workspace_d, size_t workspace_bytes,
+                void* stream);
+
+/* Host-buffer form of the cycle (what a ctypes/NumPy caller binds): uploads
+ * the blob, runs nb200_cycle, compacts, and copies the in-shell points and
+ * log_l back.  points_out_h f64[cap,d], log_l_out_h f64[cap]; *n_out_h <= cap
+ * rows are written (error if more would be needed). */
+int nb200_cycle_host(const int32_t* meta_h, int64_t n_meta,
+                     const double* data_h, int64_t n_data, int bound,
+                     int first_later, int n_later, int64_t n, uint64_t seed,
+                     uint64_t offset, uint32_t stream_id, int like_id,
+                     const double* like_params_h, int n_like_params,
+                     double log_l_min, int mlp_mode, int64_t cap,
+                     double* points_out_h, double* log_l_out_h,
+                     int64_t* n_out_h, double* lse_h, int64_t* counters_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAUTILUS_B200_H */

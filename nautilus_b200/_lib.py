@@ -1,0 +1,115 @@
+"""Loader of ``libnautilus_b200.so`` (the C ABI in include/nautilus_b200.h).
+
+There is no CPU fallback: if the library is missing or fails to load, every
+operation raises.  ``build()`` compiles the CUDA sources in-tree for sm_100a
+(nvcc cross-compiles without a GPU).
+"""
+
+import ctypes
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'libnautilus_b200.so')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+              '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
+
+_lib = None
+
+
+class NautilusB200Error(RuntimeError):
+    """Raised when a library call fails (mirrors RuntimeError semantics)."""
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(_CSRC, '*.cu')))
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(_CSRC, '*.cuh')) + [
+        os.path.join(_HERE, '..', 'include', 'nautilus_b200.h')]
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile the extension in-tree with nvcc for sm_100a."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + sources() + ['-lcuda']
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_i32p = ctypes.c_void_p
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of the public header
+PROTOTYPES = {
+    'nb200_last_error': (ctypes.c_char_p, []),
+    'nb200_version': (_int, []),
+    'nb200_device_info': (_int, [_vp, _vp, _vp]),
+    'nb200_launch_count': (_i64, []),
+    'nb200_workspace_bytes': (_sz, [_i64, _int]),
+    'nb200_ell_transform': (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp]),
+    'nb200_ell_contains': (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
+    'nb200_ell_sample_from': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp,
+                                     _vp]),
+    'nb200_union_count': (_int, [_i32p, _vp, _vp, _int, _vp, _vp, _i64, _vp,
+                                 _vp, _vp]),
+    'nb200_union_propose': (_int, [_i32p, _vp, _vp, _int, _i64, _u64, _u64,
+                                   _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp]),
+    'nb200_mlp_predict': (_int, [_i32p, _vp, _vp, _int, _int, _vp, _i64, _vp,
+                                 _int, _vp, _sz, _vp]),
+    'nb200_bound_contains': (_int, [_i32p, _vp, _vp, _int, _int, _vp, _vp,
+                                    _i64, _vp, _int, _vp, _sz, _vp]),
+    'nb200_stats': (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp, _sz, _vp]),
+    'nb200_loglike': (_int, [_vp, _vp, _i64, _int, _int, _vp, _int, _vp,
+                             _vp]),
+    'nb200_compact': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp,
+                             _sz, _vp]),
+    'nb200_cycle': (_int, [_i32p, _vp, _vp, _int, _int, _int, _i64, _u64,
+                           _u64, _u32, _int, _vp, _int, _dbl, _int, _vp, _vp,
+                           _vp, _vp, _vp, _vp, _sz, _vp]),
+    'nb200_cycle_host': (_int, [_i32p, _i64, _vp, _i64, _int, _int, _int,
+                                _i64, _u64, _u64, _u32, _int, _vp, _int, _dbl,
+                                _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib():
+    """Return the loaded library; raise if it does not exist."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NautilusB200Error(
+                'libnautilus_b200.so is not built; run '
+                '`python -c "import __graft_entry__ as g; g.build()"`. '
+                'nautilus_b200 has no CPU fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)       # AttributeError if missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NautilusB200Error(lib().nb200_last_error().decode())

@@ -1,0 +1,85 @@
+// Shared helpers of the nautilus_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nautilus_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "nautilus_b200 targets sm_100a (B200) only"
+#endif
+
+namespace nb200 {
+
+// ---- error state ---------------------------------------------------------
+extern thread_local char g_err[512];
+extern int64_t g_launches;
+
+inline int fail(const char* fmt, const char* a = "", long long b = 0,
+                long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return 1;
+}
+
+#define NB_CHECK(cond, msg)                                              \
+  do {                                                                   \
+    if (!(cond)) return nb200::fail("nautilus_b200: %s", msg);          \
+  } while (0)
+
+#define NB_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      snprintf(nb200::g_err, sizeof(nb200::g_err),                           \
+               "nautilus_b200: CUDA error '%s' at %s:%d", cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                          \
+      return 2;                                                              \
+    }                                                                        \
+  } while (0)
+
+#define NB_LAUNCH_OK()                 \
+  do {                                 \
+    nb200::g_launches++;               \
+    NB_CUDA(cudaGetLastError());       \
+  } while (0)
+
+// ---- blob accessors (layout: include/nautilus_b200.h) --------------------
+constexpr int HDR = 16;
+constexpr int MIX_REC = 8;
+constexpr int NB_REC = 12;
+
+struct Rec {          // header of one bound record, host or device
+  const int32_t* r;   // record start
+  __host__ __device__ int kind() const { return r[1]; }
+  __host__ __device__ int d() const { return r[2]; }
+  __host__ __device__ int K() const { return r[3]; }
+  __host__ __device__ int J() const { return r[4]; }
+  __host__ __device__ int unit() const { return r[5]; }
+  __host__ __device__ int off_cdf() const { return r[6]; }
+  __host__ __device__ int max_width() const { return r[9]; }
+  __host__ __device__ const int32_t* mix(int k) const {
+    return r + r[7] + k * MIX_REC;
+  }
+  __host__ __device__ const int32_t* nb(int j) const {
+    return r + r[8] + j * NB_REC;
+  }
+};
+
+__host__ __device__ inline Rec record(const int32_t* meta, int bound) {
+  return Rec{meta + meta[1 + bound]};
+}
+
+// ---- small device utilities ----------------------------------------------
+__device__ __forceinline__ int row_stride(int d) { return d | 1; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace nb200

@@ -1,0 +1,59 @@
+// Philox4x32-10 counter RNG (Salmon et al., SC'11) and the conversions the
+// proposal kernels use.  Mirrored bit-for-bit by oracle/philox.py.
+//
+// Replaces the reference's serial PCG64 stream (nautilus/sampler.py:305,
+// shared with every bound at :1002,1031): counter = (global proposal index,
+// block, stream id), key = sampler seed, so a proposal's randoms do not depend
+// on how the batch is sharded over threads, launches or GPUs.
+#pragma once
+#include <stdint.h>
+
+namespace nb200 {
+
+struct Philox {
+  uint32_t c0, c1, c3;  // proposal index (lo, hi) and stream id
+  uint32_t k0, k1;
+
+  __device__ __forceinline__ Philox(uint64_t idx, uint32_t stream,
+                                    uint64_t seed)
+      : c0((uint32_t)idx), c1((uint32_t)(idx >> 32)), c3(stream),
+        k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+
+  __device__ __forceinline__ uint4 block(uint32_t b) const {
+    uint32_t x0 = c0, x1 = c1, x2 = b, x3 = c3, ka = k0, kb = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+      const uint32_t n0 = hi1 ^ x1 ^ ka, n2 = hi0 ^ x3 ^ kb;
+      x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+    }
+    return make_uint4(x0, x1, x2, x3);
+  }
+};
+
+// (w + 0.5) * 2^-32 in fp64: uniform on (0,1), exact.
+__device__ __forceinline__ double u01_32(uint32_t w) {
+  return ((double)w + 0.5) * 2.3283064365386963e-10;
+}
+// 53-bit uniform on [0,1): 27 + 26 bits, exact.
+__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) *
+         1.1102230246251565e-16;
+}
+// Two standard normals by Box-Muller in fp32 (24-bit uniforms, radius <=
+// 5.9 sigma).  The normals only fix a direction on the sphere, so fp32
+// resolution is ample; everything downstream is fp64.
+__device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0,
+                                        float& n1) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;
+  const float rr = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  n0 = rr * c;
+  n1 = rr * s;
+}
+
+}  // namespace nb200

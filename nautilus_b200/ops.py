@@ -1,0 +1,271 @@
+"""Thin tensor-level wrappers over the C ABI (include/nautilus_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every call below
+passes raw device pointers and the current CUDA stream to
+``libnautilus_b200.so``.  All tensors must be CUDA, contiguous, float64 for
+points / uint8 for masks.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._pack import pack_stack
+
+MLP_F64 = 0
+MLP_TF32 = 1
+
+LIKE_GAUSSIAN = 0
+LIKE_ROSENBROCK = 1
+LIKE_MIXTURE = 2
+LIKE_EQUICORR = 3
+
+CODE_CUBE_REJECT, CODE_OVERLAP_REJECT, CODE_NN_REJECT, CODE_EXCLUDED, \
+    CODE_IN_SHELL = range(5)
+CNT_RAW, CNT_CUBE_REJECT, CNT_OVERLAP_REJECT, CNT_NN_REJECT, CNT_EXCLUDED, \
+    CNT_IN_SHELL, CNT_UPDATE = range(7)
+N_CNT = 8
+N_LSE = 4
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_points(points, d=None):
+    if not (points.is_cuda and points.dtype == torch.float64 and
+            points.dim() == 2 and points.is_contiguous()):
+        raise ValueError('points must be a contiguous CUDA float64 [n, d] '
+                         'tensor')
+    if d is not None and points.shape[1] != d:
+        raise ValueError('points have {} dimensions, bound has {}'.format(
+            points.shape[1], d))
+
+
+def _chk_mask(mask, n):
+    if mask is None:
+        return None
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    if not (mask.is_cuda and mask.dtype == torch.uint8 and
+            mask.is_contiguous() and mask.numel() == n):
+        raise ValueError('mask must be a contiguous CUDA uint8/bool [n] tensor')
+    return mask
+
+
+def device_info():
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().nb200_device_info(
+        ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)))
+    return sm.value, major.value, minor.value
+
+
+def launch_count():
+    return int(_lib.lib().nb200_launch_count())
+
+
+class Workspace:
+    """Grow-only scratch buffer handed to the library."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, n, d):
+        need = int(_lib.lib().nb200_workspace_bytes(int(n), int(d)))
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.buf, need
+
+
+class DeviceStack:
+    """A serialised list of bounds resident on one GPU."""
+
+    def __init__(self, specs, device='cuda'):
+        self.device = torch.device(device)
+        self.n_dim = int(specs[0]['n_dim'])
+        meta, data = pack_stack(specs)
+        self.meta_h = np.ascontiguousarray(meta, dtype=np.int32)
+        self.n_bounds = int(self.meta_h[0])
+        self.meta_d = torch.from_numpy(self.meta_h).to(self.device)
+        self.data_d = torch.from_numpy(data).to(self.device)
+        self.ws = Workspace(self.device)
+
+    @property
+    def _meta_h_ptr(self):
+        return self.meta_h.ctypes.data_as(ctypes.c_void_p)
+
+    # -- Union ------------------------------------------------------------
+    def union_count(self, bound, points, mask=None):
+        """(n_bound int32[n], contains bool[n]) -- union.py:285-289,316-317."""
+        _chk_points(points, self.n_dim)
+        n = points.shape[0]
+        mask = _chk_mask(mask, n)
+        count = torch.empty(n, dtype=torch.int32, device=self.device)
+        contains = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib().nb200_union_count(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound,
+            _ptr(points), _ptr(mask), n, _ptr(count), _ptr(contains),
+            _stream()))
+        return count, contains.bool()
+
+    def propose(self, bound, n, seed=0, offset=0, stream_id=0, test=None):
+        """Raw draws + cube filter + overlap acceptance (union.py:305-319).
+
+        ``test`` = dict(k, z, cube_u, u, r) of CUDA tensors switches to the
+        host-supplied randoms of the reference (test mode).
+        Returns (points f64[n,d], code u8[n], n_bound i32[n]).
+        """
+        points = torch.empty((n, self.n_dim), dtype=torch.float64,
+                             device=self.device)
+        code = torch.empty(n, dtype=torch.uint8, device=self.device)
+        n_bound = torch.empty(n, dtype=torch.int32, device=self.device)
+        t = test or {}
+        _lib.check(_lib.lib().nb200_union_propose(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound, n,
+            seed, offset, stream_id, _ptr(t.get('k')), _ptr(t.get('z')),
+            _ptr(t.get('cube_u')), _ptr(t.get('u')), _ptr(t.get('r')),
+            _ptr(points), _ptr(code), _ptr(n_bound), _stream()))
+        return points, code, n_bound
+
+    # -- emulator ---------------------------------------------------------
+    def mlp_predict(self, bound, j, x, mode=MLP_F64):
+        """emulator.predict on whitened coordinates (neural.py:114-116)."""
+        _chk_points(x, self.n_dim)
+        n = x.shape[0]
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        buf, nbytes = self.ws.get(n, self.n_dim)
+        _lib.check(_lib.lib().nb200_mlp_predict(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound, j,
+            _ptr(x), n, _ptr(out), mode, _ptr(buf), nbytes, _stream()))
+        return out
+
+    # -- contains ---------------------------------------------------------
+    def contains(self, bound, points, which=0, mask=None, mode=MLP_F64):
+        """NautilusBound.contains (nautilus.py:146-169); which=1 union only,
+        which=2 the neural filter of NautilusBound.sample (:217-218)."""
+        _chk_points(points, self.n_dim)
+        n = points.shape[0]
+        mask = _chk_mask(mask, n)
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        buf, nbytes = self.ws.get(n, self.n_dim)
+        _lib.check(_lib.lib().nb200_bound_contains(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound,
+            which, _ptr(points), _ptr(mask), n, _ptr(out), mode, _ptr(buf),
+            nbytes, _stream()))
+        return out.bool()
+
+    # -- full cycle ---------------------------------------------------------
+    def cycle(self, bound, n, later=(0, 0), seed=0, offset=0, stream_id=0,
+              like_id=-1, like_params=None, log_l_min=-np.inf, mode=MLP_F64,
+              out=None):
+        """One raw batch through propose -> NN filter -> exclusion ->
+        likelihood -> sums (sampler.py:1093-1144).
+
+        Returns dict(points, log_l, code, lse f64[4], counters i64[8]) of CUDA
+        tensors; nothing is synchronised.
+        """
+        d = self.n_dim
+        if out is None:
+            out = dict(
+                points=torch.empty((n, d), dtype=torch.float64,
+                                   device=self.device),
+                log_l=torch.empty(n, dtype=torch.float64, device=self.device),
+                code=torch.empty(n, dtype=torch.uint8, device=self.device),
+                lse=torch.empty(N_LSE, dtype=torch.float64,
+                                device=self.device),
+                counters=torch.empty(N_CNT, dtype=torch.int64,
+                                     device=self.device))
+        buf, nbytes = self.ws.get(n, d)
+        n_par = 0 if like_params is None else like_params.numel()
+        _lib.check(_lib.lib().nb200_cycle(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound,
+            later[0], later[1], n, seed, offset, stream_id, like_id,
+            _ptr(like_params), n_par, float(log_l_min), mode,
+            _ptr(out['points']), _ptr(out['log_l']), _ptr(out['code']),
+            _ptr(out['lse']), _ptr(out['counters']), _ptr(buf), nbytes,
+            _stream()))
+        return out
+
+    def compact(self, points, log_l, code, out_points=None, out_log_l=None):
+        """Stable gather of the in-shell rows.  Returns (points, log_l, n)
+        with n a CUDA int64 scalar tensor (no sync)."""
+        n, d = points.shape
+        if out_points is None:
+            out_points = torch.empty_like(points)
+        if out_log_l is None and log_l is not None:
+            out_log_l = torch.empty_like(log_l)
+        n_out = torch.empty(1, dtype=torch.int64, device=self.device)
+        buf, nbytes = self.ws.get(n, d)
+        _lib.check(_lib.lib().nb200_compact(
+            _ptr(points), _ptr(log_l), _ptr(code), n, d, _ptr(out_points),
+            _ptr(out_log_l), _ptr(n_out), _ptr(buf), nbytes, _stream()))
+        return out_points, out_log_l, n_out
+
+
+# -- single-ellipsoid primitives -------------------------------------------
+
+def ell_transform(points, c, M, inverse=False):
+    """Ellipsoid.transform (basic.py:339-342)."""
+    _chk_points(points)
+    n, d = points.shape
+    out = torch.empty_like(points)
+    _lib.check(_lib.lib().nb200_ell_transform(
+        _ptr(points), n, d, _ptr(c), _ptr(M), int(inverse), _ptr(out),
+        _stream()))
+    return out
+
+
+def ell_contains(points, c, B_inv, return_r2=False):
+    """Ellipsoid.contains (basic.py:360)."""
+    _chk_points(points)
+    n, d = points.shape
+    out = torch.empty(n, dtype=torch.uint8, device=points.device)
+    r2 = torch.empty(n, dtype=torch.float64, device=points.device) \
+        if return_r2 else None
+    _lib.check(_lib.lib().nb200_ell_contains(
+        _ptr(points), n, d, _ptr(c), _ptr(B_inv), _ptr(out), _ptr(r2),
+        _stream()))
+    return (out.bool(), r2) if return_r2 else out.bool()
+
+
+def ell_sample_from(z, u, c, B):
+    """Ellipsoid.sample with explicit base randoms (basic.py:376-381)."""
+    _chk_points(z)
+    n, d = z.shape
+    out = torch.empty_like(z)
+    _lib.check(_lib.lib().nb200_ell_sample_from(
+        _ptr(z), _ptr(u), n, d, _ptr(c), _ptr(B), _ptr(out), _stream()))
+    return out
+
+
+def stats(log_l, code=None, log_l_min=-np.inf):
+    """(lse f64[4], counters i64[8]) -- sampler.py:934-937, 1144."""
+    n = log_l.numel()
+    dev = log_l.device
+    lse = torch.empty(N_LSE, dtype=torch.float64, device=dev)
+    counters = torch.empty(N_CNT, dtype=torch.int64, device=dev)
+    nbytes = int(_lib.lib().nb200_workspace_bytes(1, 1))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().nb200_stats(
+        _ptr(log_l), _ptr(code), n, float(log_l_min), _ptr(lse),
+        _ptr(counters), _ptr(buf), nbytes, _stream()))
+    return lse, counters
+
+
+def loglike(points, like_id, params, code=None):
+    _chk_points(points)
+    n, d = points.shape
+    out = torch.empty(n, dtype=torch.float64, device=points.device)
+    _lib.check(_lib.lib().nb200_loglike(
+        _ptr(points), _ptr(code), n, d, like_id, _ptr(params),
+        params.numel(), _ptr(out), _stream()))
+    return out

@@ -1,0 +1,55 @@
+"""The C-ABI library builds, loads and exports every symbol the public header
+declares (no compute calls: this runs without a GPU)."""
+
+import os
+import re
+import subprocess
+
+import pytest
+
+from nautilus_b200 import _lib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'nautilus_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(nb200_\w+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    _lib.build()
+    return _lib.LIB_PATH
+
+
+def test_header_and_prototypes_agree():
+    assert header_symbols() == sorted(_lib.PROTOTYPES)
+
+
+def test_library_exports_every_symbol(built):
+    out = subprocess.check_output(['nm', '-D', '--defined-only', built],
+                                  text=True)
+    exported = set(re.findall(r' T (nb200_\w+)', out))
+    assert set(header_symbols()) <= exported
+
+
+def test_library_loads_and_reports_version(built):
+    lib = _lib.lib()
+    assert lib.nb200_version() == 100
+    assert lib.nb200_workspace_bytes(1 << 20, 30) > (1 << 20) * 30 * 8
+
+
+def test_library_is_sm100a_only(built):
+    out = subprocess.check_output(
+        ['/usr/local/cuda/bin/cuobjdump', '-lelf', built], text=True)
+    archs = set(re.findall(r'sm_(\w+)\.', out))
+    assert archs == {'100a'}, archs
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_lib.NautilusB200Error):
+        _lib.lib()
