@@ -1,0 +1,475 @@
+"""Benchmark of the importance-nested-sampling cycle (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one pass of the hot path over one batch of 2^20 raw proposals per
+GPU drawn from the config-2 bound (30-D Gaussian, n_live=2000, 4 networks
+(100, 50, 20); the bound was built by the reference and is shipped as
+tests/golden/cfg2_bound_d30.npz): union proposal -> unit-cube filter ->
+overlap acceptance -> neural filter -> likelihood -> log-sum-exp / ESS /
+counters, and for N > 1 the one NCCL collective that merges the per-rank
+sums.  `value` = raw proposals per second over all ranks.
+
+Prints ONE JSON line on rank 0 (see the contract in the task description).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 30
+ALGO_BYTES_PER_PROPOSAL = 8 * D + 8 + 1      # row + log_l + disposition
+MLP_FLOPS_PER_POINT = 4 * 2 * (30 * 100 + 100 * 50 + 50 * 20 + 20 * 1)
+WORKLOAD = ('cfg2: 30-D isotropic Gaussian (sigma=0.1), n_live=2000, bound '
+            'built by the reference (K=1 ellipsoid, 4 nets 100-50-20), '
+            'batch=2^20 raw proposals per GPU per step')
+
+
+def load_spec():
+    from nautilus_b200._pack import flat_to_spec
+    with np.load(os.path.join(ROOT, 'tests', 'golden',
+                              'cfg2_bound_d30.npz')) as f:
+        return flat_to_spec({k: f[k] for k in f.files})
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p['hbm_gbs']), bf16=float(p['bf16_tflops']),
+                    bf16_sustained=float(p['bf16_tflops_sustained']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+# --------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference loop, on host cores
+# --------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    """NautilusBound.sample + likelihood + update_shell_info for
+    ~n_raw raw proposals, exactly the reference's loop structure (1000 raw
+    draws per iteration, bounds/union.py:305-323, bounds/nautilus.py:213-222,
+    sampler.py:925-943), single-threaded BLAS like the reference
+    (sampler.py:789)."""
+    seed, n_raw = args
+    from threadpoolctl import threadpool_limits
+    from oracle import nautilus_oracle as orc
+    from nautilus_b200 import likelihoods
+    spec = load_spec()
+    like = likelihoods.Gaussian(D)
+    rng = np.random.default_rng(seed)
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        state = None
+        log_l = []
+        n_points = 0
+        while state is None or state['u_n_sample'] < n_raw:
+            pts, state = orc.nautilus_sample(spec, rng, 100, state)
+            log_l.append(like(pts))
+            n_points += len(pts)
+        log_l = np.concatenate(log_l)
+        log_v = orc.bound_log_v(spec, state['u_n_sample'],
+                                state['u_n_reject'], state['n_sample'],
+                                state['n_reject'])
+        orc.shell_info(log_l, log_v, n_points)
+        dt = time.perf_counter() - t0
+    return state['u_n_sample'], dt
+
+
+def cpu_pass(cores, n_raw_per_core, seed=0):
+    """Run the oracle loop on `cores` processes; returns (raw proposals, s)."""
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker((seed, n_raw_per_core))]
+    else:
+        ctx = mp.get_context('fork')
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(seed + i, n_raw_per_core)
+                                         for i in range(cores)])
+    # throughput of the persistent pool the reference would use: slowest
+    # worker's loop time (pool start-up and imports excluded)
+    del t0
+    return sum(r[0] for r in res), max(r[1] for r in res)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on all host cores, bounded samples."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_core = 100000
+    for _ in range(args.warmup):
+        cpu_pass(cores, 5000)
+    total, wall = 0, 0.0
+    for s in range(args.steps):
+        n, dt = cpu_pass(cores, per_core, seed=1000 * (s + 1))
+        total += n
+        wall += dt
+    value = total / wall
+    sample = ('{} steps x {} processes x {} raw proposals through the oracle '
+              'port of Union.sample/NautilusBound.sample/likelihood/'
+              'update_shell_info'.format(args.steps, cores, per_core))
+    line = {
+        'impl': 'reference', 'metric': 'raw_proposals_per_sec',
+        'value': value, 'unit': 'proposals/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * wall / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'impl': 'oracle port (NumPy/SciPy), '
+                   'the reference is pure Python and cannot travel'},
+        'cpu_baseline': {'value': value, 'unit': 'proposals/s',
+                         'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'proposals/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.gpu),
+                     '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                    capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in ln.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [],
+                    'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx),
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+
+def merge_lse(parts):
+    """Combine per-rank (m, s1, s2) triples in rank order (deterministic)."""
+    m = max(p[0] for p in parts)
+    if not np.isfinite(m):
+        return m, 0.0, 0.0
+    s1 = sum(p[1] * np.exp(p[0] - m) for p in parts)
+    s2 = sum(p[2] * np.exp(2 * (p[0] - m)) for p in parts)
+    return m, s1, s2
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from nautilus_b200 import likelihoods, ops
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run for --gpus > 1')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    spec = load_spec()
+    like = likelihoods.Gaussian(D)
+    stack = ops.DeviceStack([spec], device=dev)
+    like_params = like.device_params(dev)
+    n = args.batch
+    mode = ops.MLP_TF32 if args.mlp == 'tf32' else ops.MLP_F64
+    seed = 0
+    log_l_min = float(np.load(os.path.join(
+        ROOT, 'tests', 'golden', 'cfg2_bound_d30.npz'))['log_l_min']) + \
+        like.norm
+
+    out = stack.cycle(0, n, seed=seed, like_id=like.like_id,
+                      like_params=like_params, log_l_min=log_l_min, mode=mode)
+    packed = torch.zeros(ops.N_CNT + ops.N_LSE, dtype=torch.float64,
+                         device=dev)
+    gathered = torch.zeros((world, ops.N_CNT + ops.N_LSE),
+                           dtype=torch.float64, device=dev)
+    state = {'step': 0}
+
+    def step():
+        # every rank draws its own slice of the global proposal index space
+        s = state['step']
+        state['step'] += 1
+        offset = (s * world + rank) * n
+        stack.cycle(0, n, seed=seed, offset=offset, like_id=like.like_id,
+                    like_params=like_params, log_l_min=log_l_min, mode=mode,
+                    out=out)
+        if world > 1:
+            # the one exchange step: per-rank counters + LSE partials
+            packed[:ops.N_CNT] = out['counters'].double()
+            packed[ops.N_CNT:] = out['lse']
+            dist.all_gather_into_tensor(gathered.view(-1), packed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+        time.sleep(0.25)
+
+    # ---- timed region: K steps, device time, max over ranks ---------------
+    launches0 = ops.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if clocks:
+        clocks.stop_flag.set()
+        clocks.join()
+
+    # result of the last step (also a sanity check on the collective)
+    if world > 1:
+        g = gathered.cpu().numpy()
+        cnt = g[:, :ops.N_CNT].sum(axis=0)
+        m, s1, s2 = merge_lse([tuple(r[ops.N_CNT:ops.N_CNT + 3]) for r in g])
+    else:
+        cnt = out['counters'].cpu().numpy().astype(float)
+        m, s1, s2 = out['lse'].cpu().numpy()[:3]
+    n_shell = cnt[ops.CNT_IN_SHELL]
+    result = {
+        'raw': int(cnt[ops.CNT_RAW]), 'in_shell': int(n_shell),
+        'acceptance': float(n_shell / cnt[ops.CNT_RAW]),
+        'shell_log_l': float(m + np.log(s1) - np.log(n_shell)),
+        'shell_n_eff': float(s1 * s1 / s2),
+    }
+
+    # ---- roofline leg: same K steps with per-stage events ------------------
+    barrier()
+    ops.profile_enable(True)
+    for _ in range(args.steps):
+        step()
+    prof = ops.profile_collect()
+    ops.profile_enable(False)
+    barrier()
+
+    # ---- e2e leg: host buffers, H2D of the bound + D2H of the results ------
+    meta_pin = torch.from_numpy(stack.meta_h).pin_memory()
+    data_pin = stack.data_d.cpu().pin_memory()
+    par_pin = like_params.cpu().pin_memory()
+    cap = n
+    pts_pin = torch.empty((cap, D), dtype=torch.float64).pin_memory()
+    ll_pin = torch.empty(cap, dtype=torch.float64).pin_memory()
+    small_pin = torch.empty(ops.N_CNT + ops.N_LSE + 1,
+                            dtype=torch.float64).pin_memory()
+    cp = torch.empty((n, D), dtype=torch.float64, device=dev)
+    cl = torch.empty(n, dtype=torch.float64, device=dev)
+    bytes_io = {'h2d': 0, 'd2h': 0}
+
+    def e2e_step():
+        s = state['step']
+        state['step'] += 1
+        stack.meta_d.copy_(meta_pin, non_blocking=True)
+        stack.data_d.copy_(data_pin, non_blocking=True)
+        like_params.copy_(par_pin, non_blocking=True)
+        h2d = (meta_pin.numel() * 4 + data_pin.numel() * 8 +
+               par_pin.numel() * 8)
+        stack.cycle(0, n, seed=seed, offset=(s * world + rank) * n,
+                    like_id=like.like_id, like_params=like_params,
+                    log_l_min=log_l_min, mode=mode, out=out)
+        _, _, n_out = stack.compact(out['points'], out['log_l'], out['code'],
+                                    out_points=cp, out_log_l=cl)
+        small = torch.cat([out['counters'].double(), out['lse'],
+                           n_out.double()])
+        small_pin.copy_(small, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        k = int(small_pin[-1].item())
+        pts_pin[:k].copy_(cp[:k], non_blocking=True)
+        ll_pin[:k].copy_(cl[:k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        bytes_io['h2d'] = h2d
+        bytes_io['d2h'] = k * (D + 1) * 8 + small_pin.numel() * 8
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    value = world * n * args.steps / (ms * 1e-3)
+    e2e_value = world * n * args.steps / (e2e_ms * 1e-3)
+    stage_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1] > 0}
+    total_stage = sum(stage_ms.values()) or 1.0
+    top = max(stage_ms, key=stage_ms.get)
+    evaluated = result['raw'] / world - 0   # ~all proposals reach the MLP
+    if top in ('mlp_predict', 'fused_cycle'):
+        flops = MLP_FLOPS_PER_POINT * evaluated
+        achieved = flops / (stage_ms[top] * 1e-3) / 1e12
+        roofline = {
+            'kernel': top, 'bound': 'tensor', 'achieved': achieved,
+            'peak': peaks['bf16'], 'unit': 'TFLOP/s',
+            'frac': achieved / peaks['bf16'], 'traffic': None,
+            'peak_source': peaks['source'] + ', dense bf16 burst',
+            'flops_per_launch': flops, 'ms_per_launch': stage_ms[top],
+            'arith': args.mlp}
+    else:
+        nbytes = ALGO_BYTES_PER_PROPOSAL * n
+        achieved = nbytes / (stage_ms[top] * 1e-3) / 1e9
+        roofline = {
+            'kernel': top, 'bound': 'hbm', 'achieved': achieved,
+            'peak': peaks['hbm'], 'unit': 'GB/s',
+            'frac': achieved / peaks['hbm'], 'traffic': None,
+            'peak_source': peaks['source'],
+            'bytes_per_launch': nbytes, 'ms_per_launch': stage_ms[top]}
+    roofline['share_of_step'] = stage_ms[top] / total_stage
+    roofline['stages_ms'] = stage_ms
+    # whole-step figure against the 8d+9 B/proposal HBM roofline
+    roofline['cycle_hbm_frac'] = (value / world * ALGO_BYTES_PER_PROPOSAL /
+                                  1e9) / peaks['hbm']
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        per_core = 200000
+        n_cpu, wall = cpu_pass(cores, per_core)
+        n1, wall1 = cpu_pass(1, per_core)
+        cpu = {'value': n_cpu / wall, 'unit': 'proposals/s', 'cores': cores,
+               'kind': 'port',
+               'sample': '{} processes x {} raw proposals through the oracle '
+                         'port of the reference loop (NumPy/SciPy, BLAS '
+                         'pinned to 1 thread per process as the reference '
+                         'does)'.format(cores, per_core),
+               'single_core_value': n1 / wall1}
+
+    line = {
+        'metric': 'raw_proposals_per_sec', 'value': value,
+        'unit': 'proposals/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': n,
+                   'emulator_arith': args.mlp,
+                   'l2': 'each step writes {:.0f} MB of proposals (> 126 MB '
+                         'L2); bound parameters ({:.0f} KB) are meant to stay '
+                         'cache-resident'.format(
+                             n * ALGO_BYTES_PER_PROPOSAL / 1e6,
+                             stack.data_d.numel() * 8 / 1e3),
+                   'parallelism': 'proposal batch sharded over {} GPU(s), one '
+                                  'all-gather of 12 doubles per step'.format(
+                                      world)},
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': 'proposals/s',
+                'h2d_bytes_per_step': bytes_io['h2d'],
+                'd2h_bytes_per_step': bytes_io['d2h'],
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': launches,
+        'clocks': clocks.summary() if clocks else None,
+        'result': result,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1 << 20)
+    ap.add_argument('--mlp', default='f64', choices=['f64', 'tf32'])
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

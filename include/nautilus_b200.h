@@ -83,6 +83,15 @@ int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * bench.py's gpu_launches) */
 int64_t nb200_launch_count(void);
 
+/* Optional per-stage CUDA-event timing (used by bench.py for the roofline of
+ * the dominant kernel; adds two event records per stage, keep it off when
+ * measuring throughput).  collect() synchronises the device and returns the
+ * accumulated milliseconds and scope counts of NB200_N_STAGES stages. */
+#define NB200_N_STAGES 9
+void nb200_profile_enable(int on);
+int nb200_profile_collect(double* ms_by_stage, int64_t* calls_by_stage);
+const char* nb200_profile_stage_name(int stage);
+
 /* ---- Ellipsoid (bounds/basic.py:244-449) ------------------------------ */
 
 /* Ellipsoid.transform, basic.py:339-342.  inverse==0: out = M (x - c) with

@@ -46,6 +46,21 @@ inline int fail(const char* fmt, const char* a = "", long long b = 0,
     NB_CUDA(cudaGetLastError());       \
   } while (0)
 
+// ---- optional per-stage CUDA-event profiler (bench.py's roofline leg) -----
+enum Stage {
+  ST_PROPOSE = 0, ST_UNION, ST_PREP, ST_MLP, ST_GLUE, ST_LOGLIKE, ST_STATS,
+  ST_COMPACT, ST_FUSED, N_STAGES
+};
+extern bool g_prof_on;
+void prof_push(int stage, cudaStream_t st, bool begin);
+struct ProfScope {     // records an event pair around the launches in scope
+  int stage; cudaStream_t st;
+  ProfScope(int s, cudaStream_t t) : stage(s), st(t) {
+    if (g_prof_on) prof_push(stage, st, true);
+  }
+  ~ProfScope() { if (g_prof_on) prof_push(stage, st, false); }
+};
+
 // ---- blob accessors (layout: include/nautilus_b200.h) --------------------
 constexpr int HDR = 16;
 constexpr int MIX_REC = 8;

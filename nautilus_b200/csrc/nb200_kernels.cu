@@ -7,10 +7,30 @@
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
 
+#include <vector>
+
 namespace nb200 {
 
 thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+
+// ---- profiler ------------------------------------------------------------
+bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int stage; };
+static std::vector<ProfRec> g_prof;
+void prof_push(int stage, cudaStream_t st, bool begin) {
+  if (begin) {
+    ProfRec r;
+    r.stage = stage;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+  } else {
+    for (size_t i = g_prof.size(); i-- > 0;)
+      if (g_prof[i].stage == stage) { cudaEventRecord(g_prof[i].b, st); break; }
+  }
+}
 
 static inline int threads_for(int d) { return d <= 48 ? 128 : 64; }
 static inline size_t smem_rows(int threads, int d, int rows) {
@@ -766,6 +786,7 @@ static int launch_apply(int mode, int64_t n, uint8_t* code, uint8_t* cand,
                         uint8_t* passf, uint8_t* out, const uint8_t* mask,
                         cudaStream_t st) {
   if (n == 0) return 0;
+  ProfScope prof(ST_GLUE, st);
   k_apply<<<blocks_for(n, 256), 256, 0, st>>>(mode, n, code, cand, passf, out,
                                               mask);
   NB_LAUNCH_OK();
@@ -788,6 +809,7 @@ static int launch_mlp(const int32_t* meta_h, const int32_t* meta_d,
   const Rec rec = record(meta_h, bound);
   const int32_t* nb = rec.nb(j);
   NB_CHECK(nb[3] > 0, "neural bound has no emulator");
+  ProfScope prof(ST_MLP, st);
   if (mlp_mode == NB200_MLP_TF32)
     return launch_mlp_tf32(meta_h, meta_d, data_d, bound, j, t_rows, mask, n,
                            score_out, passf, st);
@@ -823,10 +845,13 @@ static int neural_any(const int32_t* meta_h, const int32_t* meta_d,
   if (opt_in_smem(k_neural_prep, smem)) return 2;
   for (int j = 0; j < rec.J(); ++j) {
     const bool has_emu = rec.nb(j)[3] > 0;
+    {
+    ProfScope prof(ST_PREP, st);
     k_neural_prep<<<blocks_for(n, threads), threads, smem, st>>>(
         meta_d, (int)(rec.r - meta_h), data_d, j, points, cand, cand_val, n,
         has_emu ? ws.t_rows : nullptr, ws.maskj, ws.passf);
     NB_LAUNCH_OK();
+    }
     if (has_emu) {
       const int rc = launch_mlp(meta_h, meta_d, data_d, bound, j, ws.t_rows,
                                 ws.maskj, n, nullptr, ws.passf, mlp_mode, st);
@@ -848,6 +873,7 @@ static int union_contains_launch(const int32_t* meta_h, const int32_t* meta_d,
   const int threads = threads_for(d);
   const size_t smem = smem_rows(threads, d, 2);
   if (opt_in_smem(k_union_count, smem)) return 2;
+  ProfScope prof(ST_UNION, st);
   k_union_count<<<blocks_for(n, threads), threads, smem, st>>>(
       meta_d, (int)(rec.r - meta_h), data_d, points, mask, mask_val, n, count,
       contains, passf);
@@ -876,6 +902,35 @@ extern "C" {
 const char* nb200_last_error(void) { return g_err; }
 int nb200_version(void) { return NB200_VERSION; }
 int64_t nb200_launch_count(void) { return g_launches; }
+
+void nb200_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+
+int nb200_profile_collect(double* ms_by_stage, int64_t* calls_by_stage) {
+  NB_CUDA(cudaDeviceSynchronize());
+  for (int s = 0; s < N_STAGES; ++s) { ms_by_stage[s] = 0; calls_by_stage[s] = 0; }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_stage[r.stage] += ms;
+      calls_by_stage[r.stage] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
+
+const char* nb200_profile_stage_name(int stage) {
+  static const char* names[N_STAGES] = {
+      "union_propose", "union_count", "neural_prep", "mlp_predict", "glue",
+      "loglike", "stats", "compact", "fused_cycle"};
+  return (stage >= 0 && stage < N_STAGES) ? names[stage] : "";
+}
 
 int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -966,6 +1021,7 @@ int nb200_union_propose(const int32_t* meta_h, const int32_t* meta_d,
   const size_t smem = smem_rows(threads, d, 2);
   const int rec_off = (int)(rec.r - meta_h);
   const bool test = (rec.kind() == 0) ? (cube_u_d != nullptr) : (k_d != nullptr);
+  ProfScope prof(ST_PROPOSE, (cudaStream_t)stream);
   if (test) {
     if (rec.kind() != 0)
       NB_CHECK(z_d && cube_u_d && u_d && r_d,
@@ -1052,6 +1108,7 @@ int nb200_stats(const double* log_l_d, const uint8_t* code_d, int64_t n,
   int64_t nb = (n + 4 * STAT_THREADS - 1) / (4 * STAT_THREADS);
   if (nb < 1) nb = 1;
   if (nb > STAT_MAX_BLOCKS) nb = STAT_MAX_BLOCKS;
+  ProfScope prof(ST_STATS, st);
   k_stats_partial<<<(unsigned)nb, STAT_THREADS, 0, st>>>(
       log_l_d, code_d, n, log_l_min, partial);
   NB_LAUNCH_OK();
@@ -1076,6 +1133,7 @@ int nb200_loglike(const double* points_d, const uint8_t* code_d, int64_t n,
   const int threads = threads_for(d);
   const size_t smem = smem_rows(threads, d, 1);
   if (opt_in_smem(k_loglike, smem)) return 2;
+  ProfScope prof(ST_LOGLIKE, (cudaStream_t)stream);
   k_loglike<<<blocks_for(n, threads), threads, smem, (cudaStream_t)stream>>>(
       points_d, code_d, n, d, like_id, params_d, log_l_d);
   NB_LAUNCH_OK();
@@ -1097,6 +1155,7 @@ int nb200_compact(const double* points_d, const double* log_l_d,
     NB_CUDA(cudaMemsetAsync(n_out_d, 0, sizeof(int64_t), st));
     return 0;
   }
+  ProfScope prof(ST_COMPACT, st);
   k_compact_count<<<nblocks, CMP_THREADS, 0, st>>>(code_d, n, ws.block_count);
   NB_LAUNCH_OK();
   k_compact_scan<<<1, 1024, 0, st>>>(ws.block_count, nblocks,

@@ -72,6 +72,24 @@ def launch_count():
     return int(_lib.lib().nb200_launch_count())
 
 
+N_STAGES = 9
+
+
+def profile_enable(on=True):
+    _lib.lib().nb200_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """{stage name: (milliseconds, scopes)} accumulated since enable()."""
+    ms = np.zeros(N_STAGES)
+    calls = np.zeros(N_STAGES, dtype=np.int64)
+    _lib.check(_lib.lib().nb200_profile_collect(
+        ms.ctypes.data_as(ctypes.c_void_p),
+        calls.ctypes.data_as(ctypes.c_void_p)))
+    return {_lib.lib().nb200_profile_stage_name(i).decode():
+            (float(ms[i]), int(calls[i])) for i in range(N_STAGES)}
+
+
 class Workspace:
     """Grow-only scratch buffer handed to the library."""
 

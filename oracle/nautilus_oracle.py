@@ -348,9 +348,12 @@ def replay_integer_stream(n, offset, stream, seed, spec):
     """
     idx = np.arange(n, dtype=np.uint64) + np.uint64(offset)
     w0, w1, w2, w3 = philox.philox_block(idx, 0, stream, seed)
-    cdf = categorical_cdf(spec)
-    k = np.minimum(np.searchsorted(cdf, philox.u01_32(w0), side='right'),
-                   len(cdf) - 1)
+    if spec['kind'] == 'cube':
+        k = np.zeros(n, dtype=np.int64)
+    else:
+        cdf = categorical_cdf(spec)
+        k = np.minimum(np.searchsorted(cdf, philox.u01_32(w0), side='right'),
+                       len(cdf) - 1)
     return k, philox.u01_32(w1), philox.u01_53(w2, w3)
 
 
