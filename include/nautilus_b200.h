@@ -21,7 +21,7 @@
  *     produced by nautilus_b200/_pack.py:pack_stack; `bound` selects a record.
  *     The host copy of `meta` is needed because launch shapes depend on it.
  *
- * Blob layout (mirrored by nautilus_b200/csrc/nb200_blob.cuh)
+ * Blob layout (mirrored by nautilus_b200/csrc/nb200_common.cuh)
  *   meta[0] = L (#bounds); meta[1+i] = start of record i.
  *   record header (16 ints): len, kind(0 cube,1 nautilus), d, K, J, unit,
  *       off_cdf(data), off_mix(rel), off_neural(rel), max_width, 0...
@@ -30,7 +30,8 @@
  *   neural record (12 ints): off_c, off_Binv, binv_is_lower, n_net, n_lay,
  *       off_mean, off_scale, off_thr(data: {score_predict_min-1e-9, raw}),
  *       off_sizes(rel; n_lay+1 ints), off_wtab(rel; n_net*n_lay*{off_W,off_b}),
- *       0, 0
+ *       off_tc(data; tf32 weight blob for tcgen05, -1 if none),
+ *       off_tc_hdr(rel; 32 ints, TcHeader in csrc/nb200_mlp_tc.cu)
  */
 #ifndef NAUTILUS_B200_H
 #define NAUTILUS_B200_H

@@ -135,6 +135,95 @@ class _Data:
         return np.concatenate(self.chunks)
 
 
+TC_MAGIC = 0x7F32
+TC_MAX_HID = 4
+TC_HDR_WORDS = 32
+TC_SMEM_LIMIT = 220 * 1024     # bytes of resident weights per CTA
+TC_COLS = 256                  # TMEM columns per tile group
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def tf32_round(a):
+    """Round float32 values to tf32 (10 explicit mantissa bits), nearest with
+    ties away from zero like ``cvt.rna.tf32.f32``."""
+    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(
+        np.float32)
+
+
+def _core_matrix_layout(wt, np_, kp):
+    """K-major, no-swizzle UMMA operand layout of a [n, k] matrix zero-padded
+    to [np_, kp]: 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row
+    groups kp*32 B apart (see smem_desc() in csrc/nb200_mlp_tc.cu)."""
+    full = np.zeros((np_, kp), dtype=np.float32)
+    full[:wt.shape[0], :wt.shape[1]] = wt
+    return full.reshape(np_ // 8, 8, kp // 4, 4).transpose(0, 2, 1, 3).ravel()
+
+
+def pack_tc(emu, score_predict_min):
+    """Tensor-core blob of an emulator for ``k_mlp_tf32``.
+
+    Returns ``(header int32[32], weights float32[])`` or ``None`` if the
+    architecture does not fit the kernel's envelope (<= 4 hidden layers,
+    resident weights <= 220 KB, <= 256 TMEM columns per tile group)."""
+    coefs, intercepts = emu['coefs'], emu['intercepts']
+    n_net, n_lay = len(coefs), len(coefs[0])
+    n_hid = n_lay - 1
+    if not 1 <= n_hid <= TC_MAX_HID:
+        return None
+    sizes = [coefs[0][0].shape[0]] + [w.shape[1] for w in coefs[0]]
+    d = sizes[0]
+    k0p = _round_up(d, 8)
+    np_ = [_round_up(sizes[l + 1], 16) for l in range(n_hid)]
+    kp = [k0p] + [_round_up(sizes[l + 1], 8) for l in range(n_hid - 1)]
+    # TMEM columns: input row, then one region per hidden layer (its
+    # accumulator, rewritten in place as the next layer's A operand)
+    a0_col, col = 0, _round_up(k0p, 32)
+    d_col = []
+    for l in range(n_hid):
+        d_col.append(col)
+        col += _round_up(np_[l], 32)
+    if col > TC_COLS:
+        return None
+    w_off, b_off, off = [], [], 0
+    for l in range(n_hid):
+        w_off.append(off)
+        off += np_[l] * kp[l]
+    for l in range(n_hid):
+        b_off.append(off)
+        off += np_[l]
+    w_out_off = off
+    off += np_[-1]
+    b_out_off = off
+    off += 4
+    net_stride = _round_up(off, 4)
+    total = net_stride * n_net
+    if total * 4 > TC_SMEM_LIMIT:
+        return None
+    blob = np.zeros(total, dtype=np.float32)
+    for n in range(n_net):
+        base = n * net_stride
+        for l in range(n_hid):
+            wt = tf32_round(np.asarray(coefs[n][l], dtype=np.float64).T)
+            blob[base + w_off[l]:base + w_off[l] + np_[l] * kp[l]] = \
+                _core_matrix_layout(wt, np_[l], kp[l])
+            b = np.asarray(intercepts[n][l], dtype=np.float32)
+            blob[base + b_off[l]:base + b_off[l] + len(b)] = b
+        w_out = np.asarray(coefs[n][-1], dtype=np.float32).ravel()
+        blob[base + w_out_off:base + w_out_off + len(w_out)] = w_out
+        blob[base + b_out_off] = np.float32(intercepts[n][-1][0])
+    thr = np.array([float(score_predict_min) - 1e-9]).view(np.int32)
+    pad4 = lambda v: list(v) + [0] * (TC_MAX_HID - len(v))  # noqa: E731
+    hdr = [TC_MAGIC, n_net, n_hid, d, k0p, net_stride, total, a0_col]
+    hdr += pad4(np_) + pad4(kp) + pad4(w_off) + pad4(b_off) + pad4(d_col)
+    hdr += [w_out_off, b_out_off, int(thr[0]), int(thr[1])]
+    assert len(hdr) == TC_HDR_WORDS
+    return np.asarray(hdr, dtype=np.int32), blob
+
+
 def _is_lower(m):
     return bool(np.all(np.triu(m, 1) == 0))
 
@@ -198,7 +287,8 @@ def pack_record(spec, data, cdf=None):
         off_c, _, off_binv, tri = _pack_ell(data, nb['ell'])
         emu = nb['emulator']
         if emu is None:
-            nb_recs[j] = (off_c, off_binv, tri, 0, 0, -1, -1, -1, -1, -1, 0, 0)
+            nb_recs[j] = (off_c, off_binv, tri, 0, 0, -1, -1, -1, -1, -1, -1,
+                          0)
             continue
         n_net, n_lay = len(emu['coefs']), len(emu['coefs'][0])
         sizes = [emu['coefs'][0][0].shape[0]] + [
@@ -224,8 +314,16 @@ def pack_record(spec, data, cdf=None):
                 wtab += [data.add(w), data.add(b)]
         off_wtab = base_tail + sum(len(t) for t in tail)
         tail.append(np.asarray(wtab, dtype=np.int32))
+        off_tc, off_tc_hdr = -1, 0
+        tc = pack_tc(emu, nb['score_predict_min'])
+        if tc is not None:
+            off_tc = data.add(np.concatenate(
+                [tc[1], np.zeros(len(tc[1]) % 2, np.float32)]).view(
+                    np.float64))
+            off_tc_hdr = base_tail + sum(len(t) for t in tail)
+            tail.append(tc[0])
         nb_recs[j] = (off_c, off_binv, tri, n_net, n_lay, off_mean, off_scale,
-                      off_thr, off_sizes, off_wtab, 0, 0)
+                      off_thr, off_sizes, off_wtab, off_tc, off_tc_hdr)
     hdr[7] = HDR
     hdr[8] = HDR + K * MIX_REC
     hdr[9] = max_width

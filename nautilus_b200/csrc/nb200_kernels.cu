@@ -755,6 +755,7 @@ struct Workspace {        // carve-up of the caller-provided scratch
   uint8_t* cand;          // n
   uint8_t* passf;         // n
   uint8_t* maskj;         // n
+  float* xs32;            // n * round8(d): standardised tf32 rows
   StatPartial* partial;   // STAT_MAX_BLOCKS
   long long* block_count; // n / CMP_ITEMS + 2
   long long* total;       // 1
@@ -774,6 +775,7 @@ static size_t workspace_layout(int64_t n, int d, char* base, Workspace* ws) {
   w.cand = (uint8_t*)take((size_t)n);
   w.passf = (uint8_t*)take((size_t)n);
   w.maskj = (uint8_t*)take((size_t)n);
+  w.xs32 = (float*)take((size_t)n * ((d + 7) / 8 * 8) * sizeof(float));
   w.partial = (StatPartial*)take(sizeof(StatPartial) * STAT_MAX_BLOCKS);
   w.block_count =
       (long long*)take(sizeof(long long) * ((size_t)n / CMP_ITEMS + 2));
@@ -793,10 +795,10 @@ static int launch_apply(int mode, int64_t n, uint8_t* code, uint8_t* cand,
   return 0;
 }
 
-int launch_mlp_tf32(const int32_t* meta_h, const int32_t* meta_d,
-                    const double* data_d, int bound, int j,
-                    const double* t_rows, const uint8_t* mask, int64_t n,
-                    double* score_out, uint8_t* passf, cudaStream_t st);
+int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
+                    int j, const double* t_rows, const uint8_t* mask,
+                    int64_t n, double* score_out, uint8_t* passf,
+                    float* xs32_ws, cudaStream_t st);
 
 // emulator of neural bound j on whitened rows; ORs into passf and/or writes
 // the scores.
@@ -804,15 +806,15 @@ static int launch_mlp(const int32_t* meta_h, const int32_t* meta_d,
                       const double* data_d, int bound, int j,
                       const double* t_rows, const uint8_t* mask, int64_t n,
                       double* score_out, uint8_t* passf, int mlp_mode,
-                      cudaStream_t st) {
+                      float* xs32_ws, cudaStream_t st) {
   if (n == 0) return 0;
   const Rec rec = record(meta_h, bound);
   const int32_t* nb = rec.nb(j);
   NB_CHECK(nb[3] > 0, "neural bound has no emulator");
   ProfScope prof(ST_MLP, st);
   if (mlp_mode == NB200_MLP_TF32)
-    return launch_mlp_tf32(meta_h, meta_d, data_d, bound, j, t_rows, mask, n,
-                           score_out, passf, st);
+    return launch_mlp_tf32(meta_h, data_d, bound, j, t_rows, mask, n,
+                           score_out, passf, xs32_ws, st);
   NB_CHECK(mlp_mode == NB200_MLP_F64, "unknown mlp_mode");
   const int d = rec.d();
   const int32_t* sizes = rec.r + nb[8];
@@ -854,7 +856,8 @@ static int neural_any(const int32_t* meta_h, const int32_t* meta_d,
     }
     if (has_emu) {
       const int rc = launch_mlp(meta_h, meta_d, data_d, bound, j, ws.t_rows,
-                                ws.maskj, n, nullptr, ws.passf, mlp_mode, st);
+                                ws.maskj, n, nullptr, ws.passf, mlp_mode,
+                                ws.xs32, st);
       if (rc) return rc;
     }
   }
@@ -1051,9 +1054,12 @@ int nb200_mlp_predict(const int32_t* meta_h, const int32_t* meta_d,
   const Rec rec = record(meta_h, bound);
   NB_CHECK(rec.kind() == 1 && j >= 0 && j < rec.J(), "neural bound index");
   NB_CHECK(n >= 0, "negative n");
-  (void)workspace_d; (void)workspace_bytes;
+  NB_CHECK(workspace_bytes >= nb200_workspace_bytes(n, rec.d()),
+           "workspace too small");
+  Workspace ws;
+  workspace_layout(n < 1 ? 1 : n, rec.d(), (char*)workspace_d, &ws);
   return launch_mlp(meta_h, meta_d, data_d, bound, j, x_d, nullptr, n, out_d,
-                    nullptr, mlp_mode, (cudaStream_t)stream);
+                    nullptr, mlp_mode, ws.xs32, (cudaStream_t)stream);
 }
 
 int nb200_bound_contains(const int32_t* meta_h, const int32_t* meta_d,

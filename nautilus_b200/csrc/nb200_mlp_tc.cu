@@ -1,10 +1,374 @@
-// tcgen05 (kind::tf32) emulator forward pass -- placeholder until the
-// tensor-core kernel lands; fails loudly instead of falling back.
+// Emulator forward pass on the 5th-generation tensor cores (tcgen05, TMEM).
+//
+// Replaces NeuralNetworkEmulator.predict (nautilus/neural.py:114-116), i.e.
+// n_networks x sklearn MLPRegressor._forward_pass_fast
+// (sklearn/neural_network/_multilayer_perceptron.py:189-224), for the one
+// genuinely dense contraction on the hot path.
+//
+// Mapping (DESIGN.md "emulator kernel"):
+//   * one persistent CTA per SM, 2 tile groups x 4 warps; a group owns a tile
+//     of 128 points, thread r of the group == point r == TMEM lane r;
+//   * all weights of all networks (tf32, K-major core-matrix layout, zero
+//     padded) are fetched ONCE per CTA by a TMA bulk copy (cp.async.bulk ->
+//     UBLKCP) and stay resident in shared memory (~193 KB for 4 x 30-100-50-20-1);
+//   * activations never touch shared or global memory: the standardised
+//     input row is written to TMEM with tcgen05.st, every hidden layer is
+//     D[128 x N] = A[128 x K] (TMEM) . W^T (smem) with tcgen05.mma kind::tf32
+//     (fp32 accumulate), the epilogue reads D with tcgen05.ld, adds the bias,
+//     applies ReLU, rounds to tf32 and writes it back IN PLACE as the next
+//     layer's A operand; the last layer (fan_out 1) is a dot product in the
+//     epilogue registers;
+//   * the two groups of a CTA interleave, so one group's MMAs run under the
+//     other group's epilogue.
+// Arithmetic is tf32 x tf32 -> fp32, so scores differ from the fp64 path by
+// ~1e-3; membership near the threshold can flip (rate reported by the tests),
+// which is why the fp64 kernel remains the parity mode.
 #include "nb200_common.cuh"
+
 namespace nb200 {
-int launch_mlp_tf32(const int32_t*, const int32_t*, const double*, int, int,
-                    const double*, const uint8_t*, int64_t, double*, uint8_t*,
-                    cudaStream_t) {
-  return fail("nautilus_b200: %s", "NB200_MLP_TF32 is not built yet");
+
+constexpr int TC_MAX_HID = 4;
+constexpr int TC_HDR_WORDS = 32;
+constexpr int TC_GROUPS = 2;
+constexpr int TC_COLS_PER_GROUP = 256;
+
+struct TcHeader {            // int32[32] in the meta tail (_pack.py:pack_tc)
+  int magic, n_net, n_hid, d;
+  int k0p, net_stride, total_floats, a0_col;
+  int np[TC_MAX_HID];        // padded fan_out of hidden layer l (mult. of 16)
+  int kp[TC_MAX_HID];        // padded fan_in  of hidden layer l (mult. of 8)
+  int w_off[TC_MAX_HID];     // float offsets inside a network block
+  int b_off[TC_MAX_HID];
+  int d_col[TC_MAX_HID];     // TMEM column of layer l's accumulator
+  int w_out_off, b_out_off;
+  int thr_lo, thr_hi;        // bits of the fp64 threshold score_predict_min-1e-9
+};
+static_assert(sizeof(TcHeader) == TC_HDR_WORDS * 4, "header size");
+
+// ---- PTX wrappers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (it > (1u << 22)) __trap();   // never hang the GPU on a lost arrival
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src,
+                                         uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+      "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void group_sync(int g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]^T, kind::tf32, M=128, cta_group::1
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
+                                            uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
+      "[%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]),
+        "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+        "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+        "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+// K-major, no-swizzle shared-memory matrix descriptor (SmemDescriptor of
+// cute/arch/mma_sm100_desc.hpp): core matrix = 8 rows x 16 B, LBO = byte
+// distance between the two 16-B K chunks of one MMA, SBO = byte distance
+// between 8-row groups; version 1 (Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo,
+                                              uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) |
+         ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((128u >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_GROUPS * 128, 1)
+k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
+           const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
+           int64_t n, double* __restrict__ score_out,
+           uint8_t* __restrict__ passf) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t wbar;
+  __shared__ uint64_t mbar[TC_GROUPS];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int g = tid >> 7;            // tile group
+  const int r = tid & 127;           // row in tile == TMEM lane
+
+  const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    for (int q = 0; q < TC_GROUPS; ++q) mbar_init(&mbar[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float* wsm = (float*)smem;
+  if (warp == 0) {
+    asm volatile(
+        "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+        ::"r"(smem_u32(&tmem_slot)), "r"(TC_GROUPS * TC_COLS_PER_GROUP)
+        : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+                 ::: "memory");
+  }
+  if (tid == 32) {   // one thread of warp 1 feeds the weights by TMA bulk copy
+    const uint32_t bytes = (uint32_t)h.total_floats * 4u;
+    mbar_expect_tx(&wbar, bytes);
+    const char* src = (const char*)blob;
+    uint32_t done = 0;
+    while (done < bytes) {       // chunks: keep each copy <= 64 KB
+      const uint32_t c = min(bytes - done, 65536u);
+      bulk_g2s(smem + done, src + done, c, &wbar);
+      done += c;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+  mbar_wait(&wbar, 0);
+
+  uint32_t phase = 0;
+  const int64_t n_tiles = (n + 127) / 128;
+  for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + g; tile < n_tiles;
+       tile += (int64_t)gridDim.x * TC_GROUPS) {
+    const int64_t row = tile * 128 + r;
+    const bool active = row < n && (!mask || mask[row]);
+
+    // ---- standardised input row -> TMEM (A operand of layer 0) ----------
+    {
+      const uint4* src = (const uint4*)(xs32 + row * (int64_t)h.k0p);
+      for (int c = 0; c < h.k0p; c += 8) {
+        uint32_t v[8];
+        if (active) {
+          const uint4 a = __ldg(src + (c >> 2));
+          const uint4 b = __ldg(src + (c >> 2) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = 0u;
+        }
+        tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    group_sync(g);
+
+    float sum = 0.f;
+    for (int net = 0; net < h.n_net; ++net) {
+      const float* wnet = wsm + (size_t)net * h.net_stride;
+      float y = 0.f;
+      for (int l = 0; l < h.n_hid; ++l) {
+        const int np = h.np[l], kp = h.kp[l];
+        if (r == 0) {   // the group's leader issues this layer's MMAs
+          tc_fence_after();
+          const uint32_t a_col = (l == 0) ? (uint32_t)h.a0_col
+                                          : (uint32_t)h.d_col[l - 1];
+          const uint32_t w_addr = smem_u32(wnet + h.w_off[l]);
+          const uint32_t idesc = idesc_tf32(np);
+          for (int s = 0; s < kp / 8; ++s) {
+            mma_tf32_ts(tmem_base + (uint32_t)h.d_col[l],
+                        tmem_base + a_col + (uint32_t)(s * 8),
+                        smem_desc(w_addr + (uint32_t)s * 256u, 128u,
+                                  (uint32_t)kp * 32u),
+                        idesc, s > 0 ? 1u : 0u);
+          }
+          mma_commit(&mbar[g]);
+        }
+        mbar_wait(&mbar[g], phase);
+        phase ^= 1u;
+        tc_fence_after();
+        const float* bias = wnet + h.b_off[l];
+        const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+        if (l + 1 < h.n_hid) {
+          // bias + ReLU + tf32 rounding, written back in place
+          for (int c = 0; c < np; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(d_addr + (uint32_t)c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              v[q] = to_tf32(fmaxf(__uint_as_float(v[q]) + bias[c + q], 0.f));
+            tmem_st16(d_addr + (uint32_t)c, v);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          group_sync(g);
+        } else {
+          // last hidden layer: fold the fan_out-1 output layer in registers
+          const float* wout = wnet + h.w_out_off;
+          float acc = wnet[h.b_out_off];
+          for (int c = 0; c < np; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(d_addr + (uint32_t)c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              acc = fmaf(fmaxf(__uint_as_float(v[q]) + bias[c + q], 0.f),
+                         wout[c + q], acc);
+          }
+          y = acc;
+          // the next network's layer-0 MMA overwrites TMEM columns that this
+          // group's threads may still be reading: order ld before next MMA
+          tc_fence_before();
+          group_sync(g);
+        }
+      }
+      sum += y;
+    }
+    if (active) {
+      const double score = (double)(sum / (float)h.n_net);
+      if (score_out) score_out[row] = score;
+      if (passf && score > thr) passf[row] = 1;
+    } else if (score_out && row < n) {
+      score_out[row] = nan("");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_slot), "r"(TC_GROUPS * TC_COLS_PER_GROUP)
+                 : "memory");
+  }
+}
+
+// whitened fp64 rows -> standardised, tf32-rounded fp32 rows padded to k0p
+__global__ void k_standardise_tf32(const double* __restrict__ t_rows,
+                                   const uint8_t* __restrict__ mask, int64_t n,
+                                   int d, int k0p,
+                                   const double* __restrict__ mean,
+                                   const double* __restrict__ scale,
+                                   float* __restrict__ xs32) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * k0p) return;
+  const int64_t row = e / k0p;
+  const int k = (int)(e - row * k0p);
+  float v = 0.f;
+  if (k < d && (!mask || mask[row]))
+    v = (float)((t_rows[row * d + k] - __ldg(mean + k)) / __ldg(scale + k));
+  uint32_t rr;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
+  xs32[e] = __uint_as_float(rr);
+}
+
+int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
+                    int j, const double* t_rows, const uint8_t* mask,
+                    int64_t n, double* score_out, uint8_t* passf,
+                    float* xs32_ws, cudaStream_t st) {
+  const Rec rec = record(meta_h, bound);
+  const int32_t* nb = rec.nb(j);
+  NB_CHECK(nb[10] >= 0 && nb[11] > 0,
+           "this emulator has no tensor-core blob (architecture outside the "
+           "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
+  TcHeader h;
+  memcpy(&h, rec.r + nb[11], sizeof(h));
+  NB_CHECK(h.magic == 0x7F32, "corrupt tensor-core blob header");
+  const int d = rec.d();
+  const float* blob = (const float*)(data_d + nb[10]);
+  {
+    const int64_t total = n * h.k0p;
+    k_standardise_tf32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        t_rows, mask, n, d, h.k0p, data_d + nb[5], data_d + nb[6], xs32_ws);
+    NB_LAUNCH_OK();
+  }
+  const size_t smem = (size_t)h.total_floats * 4;
+  NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
+  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  int dev = 0, sms = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = (n + 127) / 128;
+  int64_t grid = (n_tiles + TC_GROUPS - 1) / TC_GROUPS;
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * 128, smem, st>>>(
+      h, blob, xs32_ws, mask, n, score_out, passf);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace nb200
