@@ -88,7 +88,7 @@ int64_t nb200_launch_count(void);
  * the dominant kernel; adds two event records per stage, keep it off when
  * measuring throughput).  collect() synchronises the device and returns the
  * accumulated milliseconds and scope counts of NB200_N_STAGES stages. */
-#define NB200_N_STAGES 9
+#define NB200_N_STAGES 10
 void nb200_profile_enable(int on);
 int nb200_profile_collect(double* ms_by_stage, int64_t* calls_by_stage);
 const char* nb200_profile_stage_name(int stage);
@@ -150,6 +150,24 @@ int nb200_mlp_predict(const int32_t* meta_h, const int32_t* meta_d,
                       const double* x_d, int64_t n, double* out_d,
                       int mlp_mode, void* workspace_d, size_t workspace_bytes,
                       void* stream);
+
+/* NeuralNetworkEmulator.train (neural.py:50-98): fit n_net networks with
+ * layer sizes sizes_h[0..n_lay] (sizes_h[0] == d, sizes_h[n_lay] == 1) to the
+ * already standardised inputs x f64[m,d] and targets y f64[m] with sklearn
+ * MLPRegressor's algorithm (Adam, squared loss, ReLU, minibatch, patience
+ * stopping; see csrc/nb200_mlp_fit.cu).  Network i is seeded with (seed, i),
+ * like random_state=i in the reference (neural.py:94).  Outputs per network:
+ * parameters f64[n_params] in the order W_0 (fan_in x fan_out, row-major),
+ * b_0, W_1, b_1, ...; epochs run; final epoch loss. */
+size_t nb200_mlp_fit_workspace_bytes(int64_t m, int d, int n_params,
+                                     int n_net);
+int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
+                  const int32_t* sizes_h, int n_lay, int n_net, uint64_t seed,
+                  double lr, double beta1, double beta2, double eps,
+                  int batch_size, int max_epochs, double tol, int patience,
+                  double* weights_out_d, int32_t* n_iter_out_d,
+                  double* loss_out_d, void* workspace_d,
+                  size_t workspace_bytes, void* stream);
 
 /* ---- NautilusBound.contains (bounds/nautilus.py:146-169) --------------- */
 

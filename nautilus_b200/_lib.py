@@ -79,6 +79,10 @@ PROTOTYPES = {
                                    _vp, _vp]),
     'nb200_mlp_predict': (_int, [_i32p, _vp, _vp, _int, _int, _vp, _i64, _vp,
                                  _int, _vp, _sz, _vp]),
+    'nb200_mlp_fit_workspace_bytes': (_sz, [_i64, _int, _int, _int]),
+    'nb200_mlp_fit': (_int, [_vp, _vp, _i64, _int, _i32p, _int, _int, _u64,
+                             _dbl, _dbl, _dbl, _dbl, _int, _int, _dbl, _int,
+                             _vp, _vp, _vp, _vp, _sz, _vp]),
     'nb200_bound_contains': (_int, [_i32p, _vp, _vp, _int, _int, _vp, _vp,
                                     _i64, _vp, _int, _vp, _sz, _vp]),
     'nb200_stats': (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp, _sz, _vp]),

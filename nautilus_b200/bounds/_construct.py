@@ -1,0 +1,176 @@
+"""Host-side construction helpers: enclosing ellipsoids, 2-cluster mixtures,
+ellipsoid overlap.
+
+Bound *construction* happens between shells (SURVEY.md section 8, row a23 /
+"next" f-1), on a few thousand live points; it is scheduled after the cycle
+kernels and is plain NumPy here.  The algorithms are written from their
+published descriptions, not from the reference's code:
+
+* minimum-volume enclosing ellipsoid: Khachiyan's first-order algorithm in
+  the lifted space (Todd & Yildirim 2007) with Sherman-Morrison rank-one
+  updates of the inverse and O(N d) updates of the Mahalanobis distances;
+  the reference (nautilus/bounds/basic.py:175-241) runs a batched variant
+  with a full re-inversion per update.
+* two-component Gaussian mixture by EM with k-means++ restarts (the reference
+  calls scikit-learn's GaussianMixture(n_components=2, n_init=10),
+  nautilus/bounds/union.py:185-187).
+* ellipsoid overlap: Gilitschenski & Hanebeck 2012 (the test cited at
+  nautilus/bounds/union.py:17), minimised by golden-section search.
+"""
+
+import numpy as np
+
+
+def _khachiyan(points, max_updates, tol):
+    """Weights u of Khachiyan's algorithm on well-conditioned points."""
+    n, d = points.shape
+    q = np.hstack([points, np.ones((n, 1))])
+    u = np.full(n, 1.0 / n)
+    v_inv = np.linalg.inv((q * u[:, None]).T @ q)
+    g = np.einsum('ij,ij->i', q @ v_inv, q)
+    for it in range(max_updates):
+        j = int(np.argmax(g))
+        g_max = g[j]
+        if g_max <= (d + 1) * (1 + tol):
+            break
+        step = (g_max - (d + 1)) / ((d + 1) * (g_max - 1))
+        beta = step / (1 - step)
+        u *= 1 - step
+        u[j] += step
+        if it % 64 == 63:
+            # refresh the inverse from scratch now and then (rounding drift)
+            v_inv = np.linalg.inv((q * u[:, None]).T @ q)
+            g = np.einsum('ij,ij->i', q @ v_inv, q)
+            continue
+        w = v_inv @ q[j]
+        denom = 1 + beta * g_max
+        # inverse and distances after V <- (1 - step) V + step q_j q_j^T
+        v_inv = (v_inv - (beta / denom) * np.outer(w, w)) / (1 - step)
+        g = (g - (beta / denom) * (q @ w)**2) / (1 - step)
+    return u
+
+
+def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
+    """Approximate MVEE of ``points`` [N, d].
+
+    Returns ``(c, A, A_inv)`` with ``max_i (x_i - c)^T A (x_i - c) == 1``
+    (the convention of nautilus/bounds/basic.py:233-241).  The MVEE is affine
+    equivariant, so the iteration runs on points whitened by their sample
+    covariance, which keeps it stable for extremely elongated clouds.
+    """
+    points = np.asarray(points, dtype=float)
+    n, d = points.shape
+    mu = np.mean(points, axis=0)
+    cov = np.atleast_2d(np.cov(points, rowvar=False))
+    cov = cov + np.eye(d) * 1e-14 * max(np.trace(cov) / d, 1e-300)
+    chol = np.linalg.cholesky(cov)
+    white = np.linalg.solve(chol, (points - mu).T).T
+    u = _khachiyan(white, max_updates, tol)
+    c = u @ points
+    diff = points - c
+    a_inv = (diff * u[:, None]).T @ diff
+    a_inv = np.atleast_2d(0.5 * (a_inv + a_inv.T))
+    a = np.linalg.inv(a_inv)
+    a = 0.5 * (a + a.T)
+    scale = np.max(np.einsum('ij,jk,ik->i', diff, a, diff))
+    return np.atleast_1d(c), a / scale, a_inv * scale
+
+
+# --------------------------------------------------------------------------
+
+def _log_gauss(x, mean, cov):
+    d = x.shape[1]
+    chol = np.linalg.cholesky(cov)
+    sol = np.linalg.solve(chol, (x - mean).T)
+    return (-0.5 * np.sum(sol**2, axis=0) - np.sum(np.log(np.diag(chol))) -
+            0.5 * d * np.log(2 * np.pi))
+
+
+def two_gaussians(x, rng, n_init=10, max_iter=100, tol=1e-3, reg=1e-6):
+    """Fit a 2-component full-covariance Gaussian mixture by EM.
+
+    Returns the per-point log joint density ``log(w_k N(x | mu_k, C_k))`` as
+    an array [N, 2] for the best of ``n_init`` restarts.
+    """
+    x = np.asarray(x, dtype=float)
+    n, d = x.shape
+    best, best_ll = None, -np.inf
+    eye = np.eye(d) * reg
+    for _ in range(n_init):
+        # k-means++ seeding followed by a hard assignment
+        first = x[rng.integers(n)]
+        dist = np.sum((x - first)**2, axis=1)
+        second = x[rng.choice(n, p=dist / np.sum(dist))]
+        resp = (np.sum((x - second)**2, axis=1) < dist).astype(float)
+        resp = np.stack([1 - resp, resp], axis=1)
+        ll_old = -np.inf
+        log_p = None
+        for _ in range(max_iter):
+            nk = resp.sum(axis=0) + 1e-12
+            if np.any(nk < d + 1):
+                break
+            weights = nk / n
+            log_p = np.empty((n, 2))
+            try:
+                for k in range(2):
+                    mean = resp[:, k] @ x / nk[k]
+                    diff = x - mean
+                    cov = (diff * resp[:, k][:, None]).T @ diff / nk[k] + eye
+                    log_p[:, k] = _log_gauss(x, mean, cov) + np.log(weights[k])
+            except np.linalg.LinAlgError:
+                log_p = None
+                break
+            m = np.max(log_p, axis=1, keepdims=True)
+            norm = m + np.log(np.sum(np.exp(log_p - m), axis=1, keepdims=True))
+            resp = np.exp(log_p - norm)
+            ll = float(np.mean(norm))
+            if abs(ll - ll_old) < tol:
+                break
+            ll_old = ll
+        if log_p is not None and ll_old > best_ll:
+            best, best_ll = log_p, ll_old
+    if best is None:      # degenerate data: split along the widest direction
+        axis = np.argmax(np.var(x, axis=0))
+        side = x[:, axis] > np.median(x[:, axis])
+        best = np.stack([np.where(side, -1.0, 0.0),
+                         np.where(side, 0.0, -1.0)], axis=1)
+    return best
+
+
+# --------------------------------------------------------------------------
+
+def ellipsoids_overlap(ellipsoids):
+    """True if any two ellipsoids intersect (nautilus/bounds/union.py:14-40).
+
+    Two ellipsoids {(x-c_i)^T A_i (x-c_i) <= 1} are disjoint iff
+    K(s) = 1 - d^T (A_1^{-1}/(1-s) + A_2^{-1}/s)^{-1} d  < 0 for some s in
+    (0, 1), with d = c_1 - c_2; K is convex in s, so its minimum is found by
+    golden-section search.
+    """
+    cs = [np.asarray(e.c) for e in ellipsoids]
+    a_invs = [np.linalg.inv(e.A) for e in ellipsoids]
+    inv_phi = (np.sqrt(5.0) - 1) / 2
+
+    def k_of(s, d, m1, m2):
+        return 1 - d @ np.linalg.solve(m1 / (1 - s) + m2 / s, d)
+
+    for i in range(len(cs)):
+        for j in range(i + 1, len(cs)):
+            d = cs[i] - cs[j]
+            lo, hi = 1e-9, 1 - 1e-9
+            x1 = hi - inv_phi * (hi - lo)
+            x2 = lo + inv_phi * (hi - lo)
+            f1, f2 = k_of(x1, d, a_invs[i], a_invs[j]), k_of(
+                x2, d, a_invs[i], a_invs[j])
+            for _ in range(60):
+                if f1 < f2:
+                    hi, x2, f2 = x2, x1, f1
+                    x1 = hi - inv_phi * (hi - lo)
+                    f1 = k_of(x1, d, a_invs[i], a_invs[j])
+                else:
+                    lo, x1, f1 = x1, x2, f2
+                    x2 = lo + inv_phi * (hi - lo)
+                    f2 = k_of(x2, d, a_invs[i], a_invs[j])
+            if min(f1, f2) > 0:
+                return True
+    return False

@@ -1,0 +1,174 @@
+"""The composite nautilus bound: union of cube-ellipsoid mixtures AND any of
+the neural-network bounds.
+
+Host-side mirror of ``nautilus/bounds/nautilus.py``; ``PhaseShift``
+(periodic parameters) is outside the hot-path scope
+and rejected loudly.
+"""
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..neural import NeuralNetworkEmulator
+from ._device import PhiloxStream, default_device, to_device
+from .basic import Ellipsoid, UnitCubeEllipsoidMixture, _DeviceBound
+from .neural import NeuralBound
+from .union import Union
+
+
+class NautilusBound(_DeviceBound):
+    """(nautilus/bounds/nautilus.py:13-397)."""
+
+    raw_batch = 1 << 16
+
+    @classmethod
+    def compute(cls, points, log_l, log_l_min, log_v_target,
+                enlarge_per_dim=1.1, n_points_min=None, split_threshold=100,
+                periodic=None, n_networks=4, neural_network_kwargs={},
+                pool=None, rng=None):
+        if periodic is not None:
+            raise NotImplementedError(
+                'periodic parameters (PhaseShift) are outside the scope of '
+                'nautilus_b200.')
+        points = np.asarray(points, dtype=float)
+        log_l = np.asarray(log_l, dtype=float)
+        bound = cls()
+        bound.n_dim = points.shape[1]
+        bound.shift = None
+        bound.rng = np.random.default_rng() if rng is None else rng
+        live = points[log_l >= log_l_min]
+
+        # one neural bound per non-overlapping live-point ellipsoid
+        clusters = Union.compute(
+            live, enlarge_per_dim=enlarge_per_dim, n_points_min=n_points_min,
+            bound_class=Ellipsoid, rng=rng)
+        while clusters.split(allow_overlap=False):
+            pass
+        bound.neural_bounds = []
+        for ell in clusters.bounds:
+            member = ell.contains(points)
+            bound.neural_bounds.append(NeuralBound.compute(
+                points[member], log_l[member], log_l_min,
+                enlarge_per_dim=enlarge_per_dim, n_networks=n_networks,
+                neural_network_kwargs=neural_network_kwargs, pool=pool,
+                rng=rng))
+
+        # outer sampling bound, refined until close enough to the target volume
+        bound.outer_bound = Union.compute(
+            live, enlarge_per_dim=enlarge_per_dim, n_points_min=n_points_min,
+            bound_class=UnitCubeEllipsoidMixture, rng=rng)
+        slack = np.log(split_threshold * enlarge_per_dim**bound.n_dim)
+        while bound.outer_bound.log_v - log_v_target > slack:
+            if not bound.outer_bound.split():
+                break
+        while bound.outer_bound.log_v - log_v_target > slack:
+            if not bound.outer_bound.trim():
+                break
+
+        bound.stream = PhiloxStream(rng)
+        bound._clear()
+        return bound
+
+    def _clear(self):
+        self.points = np.zeros((0, self.n_dim))
+        self._buffer = None
+        self.n_sample = 0
+        self.n_reject = 0
+        self._invalidate()
+
+    def spec(self):
+        spec = self.outer_bound.spec()
+        spec['neural'] = [nb.nb_spec() for nb in self.neural_bounds]
+        return spec
+
+    def contains(self, points, mode=None):
+        """outer union AND any neural bound (nautilus.py:146-169)."""
+        t, restore = to_device(points, self.n_dim)
+        mode = NeuralNetworkEmulator.mode if mode is None else mode
+        return restore(self._device_stack().contains(0, t, mode=mode))
+
+    # -- sampling ------------------------------------------------------------
+    def draw_raw(self, n_raw, mode=None):
+        """One raw batch through union proposal and neural filter.  Updates
+        all four integer counters exactly as the reference's nested loops do
+        in aggregate (union.py:322-323, nautilus.py:221-222) and returns the
+        accepted points (CUDA)."""
+        mode = NeuralNetworkEmulator.mode if mode is None else mode
+        stack = self._device_stack()
+        offset = self.stream.take(n_raw)
+        out = stack.cycle(0, int(n_raw), seed=self.stream.seed, offset=offset,
+                          stream_id=self.stream.stream_id, mode=mode)
+        keep, _, n_keep = stack.compact(out['points'], None, out['code'])
+        cnt = out['counters'].cpu().numpy()
+        n_union_reject = int(cnt[ops.CNT_CUBE_REJECT] +
+                             cnt[ops.CNT_OVERLAP_REJECT])
+        n_nn_reject = int(cnt[ops.CNT_NN_REJECT])
+        self.outer_bound.n_sample += int(n_raw)
+        self.outer_bound.n_reject += n_union_reject
+        self.n_sample += int(n_raw) - n_union_reject
+        self.n_reject += n_nn_reject
+        return keep[:int(cnt[ops.CNT_IN_SHELL])]
+
+    def _refill(self, n_points):
+        have = 0 if self._buffer is None else self._buffer.shape[0]
+        chunks = [] if self._buffer is None else [self._buffer]
+        while have < n_points:
+            if self.outer_bound.n_sample > 0 and self.n_sample > 0:
+                acc = ((1 - self.outer_bound.n_reject /
+                        self.outer_bound.n_sample) *
+                       (1 - self.n_reject / self.n_sample))
+            else:
+                acc = 0.25
+            n_raw = int(min(max(self.raw_batch,
+                                1.2 * (n_points - have) / max(acc, 1e-4)),
+                            1 << 22))
+            keep = self.draw_raw(n_raw)
+            chunks.append(keep)
+            have += keep.shape[0]
+        self._buffer = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
+
+    def sample(self, n_points=100, return_points=True, pool=None,
+               as_numpy=True):
+        """Pop n points from the FIFO of accepted points, refilling it with
+        raw GPU batches (nautilus.py:193-244).  ``pool`` is accepted for API
+        compatibility: the batch is already data-parallel."""
+        self._refill(n_points)
+        if not return_points:
+            return None
+        out = self._buffer[:n_points]
+        self._buffer = self._buffer[n_points:]
+        return out.cpu().numpy() if as_numpy else out.contiguous()
+
+    @property
+    def log_v(self):
+        """outer.log_v + log(1 - n_reject / n_sample) (nautilus.py:246-261)."""
+        if self.n_sample == 0:
+            self.sample(return_points=False)
+        return self.outer_bound.log_v + np.log(
+            1.0 - self.n_reject / self.n_sample)
+
+    @property
+    def n_ell(self):
+        """Number of ellipsoids (nautilus.py:263-274)."""
+        return int(np.sum([np.any(~b.dim_cube)
+                           for b in self.outer_bound.bounds]))
+
+    @property
+    def n_net(self):
+        """Number of networks (nautilus.py:276-290)."""
+        emu = self.neural_bounds[0].emulator
+        if emu is None:
+            return 0
+        return len(self.neural_bounds) * len(emu.neural_networks)
+
+    def reset(self, rng=None):
+        """Forget sampling progress; optionally reseed (nautilus.py:382-397)."""
+        self._buffer = None
+        self.points = np.zeros((0, self.n_dim))
+        self.n_sample = 0
+        self.n_reject = 0
+        self.outer_bound.reset(rng)
+        if rng is not None:
+            self.rng = rng
+            self.stream.reseed(rng)

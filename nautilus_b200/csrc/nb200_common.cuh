@@ -49,7 +49,7 @@ inline int fail(const char* fmt, const char* a = "", long long b = 0,
 // ---- optional per-stage CUDA-event profiler (bench.py's roofline leg) -----
 enum Stage {
   ST_PROPOSE = 0, ST_UNION, ST_PREP, ST_MLP, ST_GLUE, ST_LOGLIKE, ST_STATS,
-  ST_COMPACT, ST_FUSED, N_STAGES
+  ST_COMPACT, ST_FUSED, ST_FIT, N_STAGES
 };
 extern bool g_prof_on;
 void prof_push(int stage, cudaStream_t st, bool begin);

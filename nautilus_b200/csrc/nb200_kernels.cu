@@ -931,7 +931,7 @@ int nb200_profile_collect(double* ms_by_stage, int64_t* calls_by_stage) {
 const char* nb200_profile_stage_name(int stage) {
   static const char* names[N_STAGES] = {
       "union_propose", "union_count", "neural_prep", "mlp_predict", "glue",
-      "loglike", "stats", "compact", "fused_cycle"};
+      "loglike", "stats", "compact", "fused_cycle", "mlp_fit"};
   return (stage >= 0 && stage < N_STAGES) ? names[stage] : "";
 }
 

@@ -1,0 +1,122 @@
+"""Neural-network emulator of the likelihood score.
+
+Host-side mirror of ``nautilus/neural.py``.  ``train`` fits the ensemble with
+the persistent on-chip trainer (csrc/nb200_mlp_fit.cu), ``predict`` runs the
+forward pass on the GPU (fp64 parity kernel or the tcgen05 tf32 kernel).  The
+fitted parameters are kept in the same shape scikit-learn exposes
+(``coefs_``, ``intercepts_``, ``n_layers_``), which is what the reference
+serialises (nautilus/neural.py:139-143) and what ``n_net`` inspects
+(nautilus/bounds/nautilus.py:286-288).
+"""
+
+import warnings
+
+import numpy as np
+import torch
+
+from . import ops
+from .bounds._device import default_device, to_device
+
+DEFAULT_KWARGS = dict(hidden_layer_sizes=(100, 50, 20), alpha=0,
+                      learning_rate_init=1e-2, max_iter=10000, tol=0,
+                      n_iter_no_change=10)
+
+
+class FittedNetwork:
+    """The attributes of a fitted ``MLPRegressor`` the rest of the code reads.
+    """
+
+    def __init__(self, coefs, intercepts, n_iter, loss):
+        self.coefs_ = coefs
+        self.intercepts_ = intercepts
+        self.n_layers_ = len(coefs) + 1
+        self.n_iter_ = int(n_iter)
+        self.loss_ = float(loss)
+
+
+class NeuralNetworkEmulator:
+    """Ensemble of small MLPs on standardised inputs
+    (nautilus/neural.py:35-187)."""
+
+    mode = ops.MLP_F64       # arithmetic of predict(); class-wide default
+
+    @classmethod
+    def train(cls, x, y, n_networks=4, neural_network_kwargs={}, pool=None,
+              seed=0):
+        """Standardise ``x`` and fit ``n_networks`` networks
+        (nautilus/neural.py:50-98).  ``pool`` is accepted for API
+        compatibility; the networks train concurrently, one CTA each."""
+        emulator = cls()
+        x = np.asarray(x, dtype=float)
+        y = np.asarray(y, dtype=float)
+        emulator.mean = np.mean(x, axis=0)
+        emulator.scale = np.std(x, axis=0)
+
+        kwargs = dict(DEFAULT_KWARGS)
+        kwargs.update(neural_network_kwargs)
+        if 'random_state' in kwargs:
+            warnings.warn("The 'random_state' keyword argument passed to the"
+                          " neural network is ignored.", Warning, stacklevel=2)
+            del kwargs['random_state']
+        supported = set(DEFAULT_KWARGS) | {'batch_size', 'beta_1', 'beta_2',
+                                           'epsilon'}
+        unknown = set(kwargs) - supported
+        if unknown:
+            raise ValueError('Unsupported neural network arguments: {}'
+                             .format(sorted(unknown)))
+        if kwargs['alpha'] != 0:
+            raise ValueError("L2 penalty 'alpha' is not supported.")
+
+        hidden = tuple(np.atleast_1d(kwargs['hidden_layer_sizes']))
+        sizes = (x.shape[1], ) + tuple(int(h) for h in hidden) + (1, )
+        batch_size = kwargs.get('batch_size', 'auto')
+        if batch_size == 'auto':
+            batch_size = min(200, len(x))
+        dev = default_device()
+        xs = torch.from_numpy((x - emulator.mean) / emulator.scale).to(dev)
+        params, n_iter, loss = ops.mlp_fit(
+            xs.contiguous(), torch.from_numpy(y).to(dev), sizes, n_networks,
+            seed=seed, lr=kwargs['learning_rate_init'],
+            beta1=kwargs.get('beta_1', 0.9), beta2=kwargs.get('beta_2', 0.999),
+            eps=kwargs.get('epsilon', 1e-8), batch_size=batch_size,
+            max_epochs=kwargs['max_iter'], tol=kwargs['tol'],
+            patience=kwargs['n_iter_no_change'])
+        params = params.cpu().numpy()
+        n_iter = n_iter.cpu().numpy()
+        loss = loss.cpu().numpy()
+        emulator.neural_networks = []
+        for i in range(n_networks):
+            coefs, intercepts, off = [], [], 0
+            for fi, fo in zip(sizes[:-1], sizes[1:]):
+                coefs.append(params[i, off:off + fi * fo].reshape(fi, fo))
+                off += fi * fo
+                intercepts.append(params[i, off:off + fo].copy())
+                off += fo
+            emulator.neural_networks.append(
+                FittedNetwork(coefs, intercepts, n_iter[i], loss[i]))
+        emulator._stack = None
+        return emulator
+
+    def emu_spec(self):
+        return dict(mean=self.mean, scale=self.scale,
+                    coefs=[n.coefs_ for n in self.neural_networks],
+                    intercepts=[n.intercepts_ for n in self.neural_networks])
+
+    def _device_stack(self):
+        if getattr(self, '_stack', None) is None:
+            d = len(self.mean)
+            ident = dict(c=np.zeros(d), B=np.eye(d), B_inv=np.eye(d))
+            spec = dict(kind='nautilus', n_dim=d, unit=False,
+                        log_v_all=np.zeros(1),
+                        mixtures=[dict(dim_cube=np.zeros(d, bool), ell=ident)],
+                        neural=[dict(ell=ident, emulator=self.emu_spec(),
+                                     score_predict_min=0.0)])
+            self._stack = ops.DeviceStack([spec], device=default_device())
+        return self._stack
+
+    def predict(self, x, mode=None):
+        """Mean network output on ``(x - mean) / scale``
+        (nautilus/neural.py:100-116)."""
+        t, restore = to_device(x, len(self.mean))
+        mode = self.mode if mode is None else mode
+        return restore(self._device_stack().mlp_predict(0, 0, t, mode=mode))

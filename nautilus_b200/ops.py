@@ -72,7 +72,7 @@ def launch_count():
     return int(_lib.lib().nb200_launch_count())
 
 
-N_STAGES = 9
+N_STAGES = 10
 
 
 def profile_enable(on=True):
@@ -287,3 +287,32 @@ def loglike(points, like_id, params, code=None):
         _ptr(points), _ptr(code), n, d, like_id, _ptr(params),
         params.numel(), _ptr(out), _stream()))
     return out
+
+
+def mlp_fit(x, y, sizes, n_networks, seed=0, lr=1e-2, beta1=0.9, beta2=0.999,
+            eps=1e-8, batch_size=200, max_epochs=10000, tol=0.0, patience=10):
+    """Train an ensemble on standardised inputs (neural.py:50-98).
+
+    x f64[m,d], y f64[m] CUDA tensors.  Returns (params f64[n_net, n_params]
+    CUDA, n_iter int32[n_net] CUDA, loss f64[n_net] CUDA)."""
+    _chk_points(x)
+    m, d = x.shape
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    n_lay = len(sizes) - 1
+    n_params = int(sum(sizes[i] * sizes[i + 1] + sizes[i + 1]
+                       for i in range(n_lay)))
+    dev = x.device
+    params = torch.empty((n_networks, n_params), dtype=torch.float64,
+                         device=dev)
+    n_iter = torch.empty(n_networks, dtype=torch.int32, device=dev)
+    loss = torch.empty(n_networks, dtype=torch.float64, device=dev)
+    nbytes = int(_lib.lib().nb200_mlp_fit_workspace_bytes(
+        m, d, n_params, n_networks))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().nb200_mlp_fit(
+        _ptr(x), _ptr(y.contiguous()), m, d,
+        sizes.ctypes.data_as(ctypes.c_void_p), n_lay, n_networks, int(seed),
+        lr, beta1, beta2, eps, int(batch_size), int(max_epochs), tol,
+        int(patience), _ptr(params), _ptr(n_iter), _ptr(loss), _ptr(buf),
+        nbytes, _stream()))
+    return params, n_iter, loss

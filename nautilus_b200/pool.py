@@ -1,0 +1,88 @@
+"""Pools: how the proposal batch and the likelihood calls are spread out.
+
+The reference's only "distributed backend" is ``NautilusPool``
+(nautilus/pool.py:36-107): a ``.map/.size`` facade over multiprocessing, dask
+or MPI executors, used for likelihood calls (sampler.py:863-873), for proposal
+sampling (bounds/nautilus.py:223-237) and for network training
+(nautilus/neural.py:93-96).  Here the proposal batch is sharded over GPUs
+instead: ``GpuPool`` names the devices (one CUDA stream each), every device
+draws its slice of the global proposal index range -- Philox counters are
+keyed by that index, so results do not depend on ``size`` -- and the per-rank
+counters / log-sum-exp partials are merged by ONE collective.  Inside one
+process the merge is a host-side sum over devices; across processes
+(``torchrun``, one rank per GPU) it is ``torch.distributed.all_gather`` over
+NCCL (bench.py, tests/test_distributed.py).
+
+``NautilusPool`` is kept for host-side (Python callable) likelihoods with the
+reference's semantics.
+"""
+
+from multiprocessing import Pool
+
+_LIKELIHOOD = None
+
+
+def initialize_worker(likelihood):
+    """Cache the likelihood in the worker (nautilus/pool.py:6-16)."""
+    global _LIKELIHOOD
+    _LIKELIHOOD = likelihood
+
+
+def likelihood_worker(*args):
+    """Evaluate the cached likelihood (nautilus/pool.py:19-33)."""
+    return _LIKELIHOOD(*args)
+
+
+class NautilusPool:
+    """``.map`` / ``.size`` facade over executor-like pools
+    (nautilus/pool.py:36-107)."""
+
+    def __init__(self, pool, likelihood=None):
+        if isinstance(pool, int):
+            pool = Pool(pool, initializer=initialize_worker,
+                        initargs=(likelihood, ))
+        self.pool = pool
+
+    def _is_dask(self):
+        return 'distributed.client.Client' in str(type(self.pool))
+
+    def map(self, func, iterable):
+        if self._is_dask():
+            return list(self.pool.gather(self.pool.map(func, iterable)))
+        return list(self.pool.map(func, iterable))
+
+    @property
+    def size(self):
+        if self._is_dask():
+            return len(self.pool.nthreads())
+        for attr in ('_processes', '_max_workers', 'size', 'nt'):
+            if hasattr(self.pool, attr):
+                return getattr(self.pool, attr)
+        raise ValueError('Cannot determine size of pool.')
+
+
+class GpuPool:
+    """A set of CUDA devices that share one proposal batch."""
+
+    def __init__(self, devices=None):
+        import torch
+        if devices is None:
+            devices = 1
+        if isinstance(devices, int):
+            if devices < 1 or devices > torch.cuda.device_count():
+                raise ValueError('{} GPUs requested, {} visible.'.format(
+                    devices, torch.cuda.device_count()))
+            devices = list(range(devices))
+        self.devices = [torch.device('cuda', int(i)) for i in devices]
+
+    @property
+    def size(self):
+        return len(self.devices)
+
+    def slices(self, n):
+        """Contiguous [lo, hi) slices of n proposals, one per device."""
+        edges = [n * i // self.size for i in range(self.size + 1)]
+        return list(zip(edges[:-1], edges[1:]))
+
+    def map(self, func, iterable):
+        return [func(item) for item in iterable]

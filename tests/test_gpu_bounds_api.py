@@ -1,0 +1,283 @@
+"""The bound classes behave like the reference's (tests/test_bounds.py and
+tests/test_neural.py of johannesulf/nautilus, re-stated for the GPU mirror)."""
+
+import numpy as np
+import pytest
+from scipy.special import gamma
+
+torch = pytest.importorskip('torch')
+
+from nautilus_b200 import bounds, neural  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def points_on_hypersphere_boundary():
+    n_dim = 10
+    points = np.zeros((2 * n_dim, n_dim)) + 0.5
+    for i in range(n_dim * 2):
+        points[i, i // 2] += 1 if i % 2 else -1
+    return points
+
+
+@pytest.fixture
+def random_points_from_hypersphere():
+    np.random.seed(0)
+    n_dim, n_points = 3, 1000
+    points = np.random.normal(size=(n_points, n_dim))
+    points = points / np.sqrt(np.sum(points**2, axis=1))[:, np.newaxis]
+    points *= np.random.uniform(size=n_points)[:, np.newaxis]**(1.0 / n_dim)
+    return points
+
+
+@pytest.fixture
+def random_points_from_hypercube():
+    np.random.seed(0)
+    return np.random.random(size=(500, 4))
+
+
+def test_unit_cube():
+    cube = bounds.UnitCube.compute(3)
+    points = cube.sample(200)
+    assert points.shape == (200, 3)
+    assert np.all((points >= 0) & (points < 1))
+    assert np.all(cube.contains(points))
+    assert cube.log_v == 0
+
+
+def test_unit_cube_rng():
+    n_dim, n_points = 7, 1000
+    cube = bounds.UnitCube.compute(n_dim, rng=np.random.default_rng(0))
+    same = bounds.UnitCube.compute(n_dim, rng=np.random.default_rng(0))
+    diff = bounds.UnitCube.compute(n_dim, rng=np.random.default_rng(1))
+    points = cube.sample(n_points)
+    assert np.all(points == same.sample(n_points))
+    assert not np.all(points == diff.sample(n_points))
+    assert not np.all(points == cube.sample(n_points))
+    assert np.all(cube.contains(np.random.random((n_points, n_dim))))
+
+
+def test_ellipsoid_construction():
+    with pytest.raises(ValueError):
+        bounds.Ellipsoid.compute(np.random.random(size=(10, 10)))
+    with pytest.raises(ValueError):
+        bounds.Ellipsoid.compute(np.random.random(size=(100, 10)),
+                                 enlarge_per_dim=0.9)
+
+
+def test_mvee_known_answer(points_on_hypersphere_boundary):
+    # tests/test_bounds.py:88-101
+    from nautilus_b200.bounds._construct import enclosing_ellipsoid
+    c_true = np.median(points_on_hypersphere_boundary, axis=0)
+    np.random.seed(0)
+    points = np.concatenate([points_on_hypersphere_boundary, np.atleast_2d(
+        c_true + np.random.random() - 0.5)])
+    c, A = enclosing_ellipsoid(points)[:2]
+    assert np.allclose(c, c_true, rtol=0, atol=1e-3)
+    assert np.allclose(A, np.eye(len(c_true)), rtol=0, atol=1e-2)
+
+
+def test_ellipsoid_sample_and_contains(points_on_hypersphere_boundary):
+    ell = bounds.Ellipsoid.compute(points_on_hypersphere_boundary,
+                                   enlarge_per_dim=1.0,
+                                   rng=np.random.default_rng(0))
+    c = np.mean(points_on_hypersphere_boundary)
+    points = ell.sample(100)
+    assert points.shape == (100, 10)
+    assert np.all(np.linalg.norm(points - c, axis=1) < 1 + 1e-9)
+    assert np.all(ell.contains(points))
+    ell = bounds.Ellipsoid.compute(points, enlarge_per_dim=1.1,
+                                   rng=np.random.default_rng(0))
+    points = ell.sample(100)
+    assert np.all(ell.contains(points))
+
+
+def test_ellipsoid_volume(points_on_hypersphere_boundary):
+    n_dim = points_on_hypersphere_boundary.shape[1]
+    for f in [1.0, 1.1, np.pi / 2.0]:
+        ell = bounds.Ellipsoid.compute(points_on_hypersphere_boundary,
+                                       enlarge_per_dim=f)
+        assert np.isclose(ell.log_v, np.log(
+            f**n_dim * np.pi**(n_dim / 2) / gamma(n_dim / 2 + 1)), atol=1e-3)
+
+
+def test_ellipsoid_transform(random_points_from_hypersphere):
+    ell = bounds.Ellipsoid.compute(random_points_from_hypersphere,
+                                   rng=np.random.default_rng(0))
+    points = ell.sample(100)
+    points_t = ell.transform(points)
+    assert np.all(np.abs(points_t) < 1 + 1e-9)
+    assert np.allclose(points, ell.transform(points_t, inverse=True))
+    # single point in, scalar out
+    assert ell.contains(points[0]) in (True, np.True_)
+
+
+def test_ellipsoid_rng(random_points_from_hypersphere):
+    mk = lambda s: bounds.Ellipsoid.compute(  # noqa: E731
+        random_points_from_hypersphere, rng=np.random.default_rng(s))
+    ell, same, diff = mk(0), mk(0), mk(1)
+    points = ell.sample(1000)
+    assert np.all(points == same.sample(1000))
+    assert not np.all(points == diff.sample(1000))
+    assert not np.all(points == ell.sample(1000))
+
+
+def test_mixture_uses_cube_dimensions():
+    rng = np.random.default_rng(7)
+    pts = rng.random((600, 6))
+    pts[:, [1, 3, 4]] = 0.5 + 0.02 * rng.normal(size=(600, 3))
+    mix = bounds.UnitCubeEllipsoidMixture.compute(
+        pts, rng=np.random.default_rng(0))
+    assert list(np.flatnonzero(~mix.dim_cube)) == [1, 3, 4]
+    assert np.all(mix.contains(pts))
+    smp = mix.sample(500)
+    assert np.all(mix.contains(smp))
+    assert np.all((smp[:, mix.dim_cube] >= 0) & (smp[:, mix.dim_cube] < 1))
+    t = mix.transform(smp)
+    assert np.all(np.abs(t[:, mix.dim_cube]) <= 1)
+    assert np.all(np.sum(t[:, ~mix.dim_cube]**2, axis=1) < 1)
+
+
+def test_union_construction():
+    with pytest.raises(ValueError):
+        bounds.Union.compute(np.random.random(size=(100, 10)),
+                             n_points_min=5)
+
+
+def test_union_split(random_points_from_hypersphere):
+    points = np.concatenate([random_points_from_hypersphere,
+                             random_points_from_hypersphere + 100,
+                             random_points_from_hypersphere + 101])
+    union = bounds.Union.compute(points, enlarge_per_dim=1.0 + 1e-9,
+                                 unit=False, rng=np.random.default_rng(0))
+    while union.split(allow_overlap=False):
+        pass
+    assert len(union.bounds) == 2
+    assert np.all(union.contains(points))
+    assert union.split()
+    assert len(union.bounds) == 3
+    assert np.all(union.contains(points))
+
+
+def test_union_sample_and_contains(random_points_from_hypersphere):
+    union = bounds.Union.compute(random_points_from_hypersphere + 50,
+                                 enlarge_per_dim=1.0, unit=False,
+                                 rng=np.random.default_rng(0))
+    for _ in range(4):
+        union.split()
+    points = union.sample(100)
+    assert points.shape == (100, 3)
+    assert np.all(union.contains(points))
+    # volume from the reject counters vs the analytic unit ball
+    assert abs(union.log_v - np.log(4 / 3 * np.pi)) < 0.1
+
+
+def test_union_rng(random_points_from_hypersphere):
+    def mk(seed):
+        u = bounds.Union.compute(random_points_from_hypersphere, unit=False,
+                                 rng=np.random.default_rng(seed))
+        u.split()
+        return u
+    union, same, diff = mk(0), mk(0), mk(1)
+    points = union.sample(100)
+    assert np.all(points == same.sample(100))
+    assert not np.all(points == diff.sample(100))
+    assert not np.all(points == union.sample(100))
+
+
+def test_neural_network_emulator():
+    # tests/test_neural.py:6-15
+    np.random.seed(0)
+    x = np.random.random((1000, 5))
+    y = np.linalg.norm(x - 0.5, axis=1)
+    y = np.argsort(np.argsort(y)) / float(len(y))
+    emu = neural.NeuralNetworkEmulator.train(x, y, n_networks=1, pool=None)
+    rmse = np.sqrt(np.mean((y - emu.predict(x))**2))
+    print('emulator rmse / std = {:.3f}, epochs = {}'.format(
+        rmse / np.std(y), emu.neural_networks[0].n_iter_))
+    assert rmse < 0.3 * np.std(y)
+    assert emu.neural_networks[0].n_layers_ == 5
+    assert emu.neural_networks[0].coefs_[0].shape == (5, 100)
+
+
+def test_neural_bound_contains(random_points_from_hypercube):
+    points = random_points_from_hypercube
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    log_l_min = np.median(log_l)
+    nbound = bounds.NeuralBound.compute(points, log_l, log_l_min,
+                                        n_networks=1)
+    points = np.random.random(size=(1000, 4))
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    in_bound = nbound.contains(points)
+    assert np.mean(log_l[in_bound] > log_l_min) >= 0.9
+
+
+def test_nautilus_bound_sample_and_contains(random_points_from_hypercube):
+    points = random_points_from_hypercube
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    log_l_min = np.median(log_l)
+    nbound = bounds.NautilusBound.compute(points, log_l, log_l_min,
+                                          np.log(0.5), n_networks=1)
+    points = np.random.random(size=(1000, 4))
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    assert np.mean(log_l[nbound.contains(points)] > log_l_min) >= 0.9
+    points = nbound.sample(100)
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    assert np.mean(log_l > log_l_min) >= 0.9
+    assert np.all(nbound.contains(points))
+
+
+def test_nautilus_bound_gaussian_shell():
+    radius, width = 0.45, 0.01
+    np.random.seed(0)
+    points = np.random.random((10000, 2))
+    log_l = -((np.linalg.norm(points - 0.5, axis=1) - radius) / width)**2
+    log_l_min = -1
+    points, log_l = points[log_l > -100], log_l[log_l > -100]
+    log_v_target = np.log(2 * np.pi * radius * width * 2)
+    nbound = bounds.NautilusBound.compute(
+        points, log_l, log_l_min, log_v_target, split_threshold=1,
+        n_networks=1, rng=np.random.default_rng(0))
+    points = nbound.sample(10000)
+    log_l = -((np.linalg.norm(points - 0.5, axis=1) - radius) / width)**2
+    assert np.isclose(nbound.log_v, log_v_target, rtol=0, atol=np.log(2))
+    assert np.mean(log_l > log_l_min) > 0.5
+    assert nbound.n_net == 1
+
+
+def test_nautilus_bound_two_peaks():
+    np.random.seed(0)
+    radius = 1e-5
+    points = np.vstack([np.random.normal(size=(1000, 2)) * radius + 0.1,
+                        np.random.normal(size=(1000, 2)) * radius + 0.9])
+
+    def likelihood(x):
+        return -np.minimum(np.linalg.norm(x - 0.1, axis=-1),
+                           np.linalg.norm(x - 0.9, axis=-1)) / radius
+
+    log_l = likelihood(points)
+    log_l_min = -1
+    log_v_target = np.log(2 * np.pi * radius**2)
+    nbound = bounds.NautilusBound.compute(
+        points, log_l, log_l_min, log_v_target, n_networks=1,
+        rng=np.random.default_rng(0))
+    points = nbound.sample(10000)
+    log_l = likelihood(points)
+    assert np.isclose(nbound.log_v, log_v_target, rtol=0, atol=0.1)
+    assert np.mean(log_l > log_l_min) > 0.9
+    assert nbound.n_net == 2
+
+
+def test_nautilus_bound_reset_and_sample(random_points_from_hypercube):
+    points = random_points_from_hypercube
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    nbound = bounds.NautilusBound.compute(
+        points, log_l, np.median(log_l), np.log(0.5), n_networks=1,
+        rng=np.random.default_rng(0))
+    nbound.reset(np.random.default_rng(0))
+    points_1, volume_1 = nbound.sample(10000), nbound.log_v
+    nbound.reset(np.random.default_rng(0))
+    points_2, volume_2 = nbound.sample(10000), nbound.log_v
+    assert np.all(points_1 == points_2)
+    assert volume_1 == volume_2

@@ -1,0 +1,123 @@
+"""End-to-end behaviour of the drop-in Sampler (tests/test_sampler.py of the
+reference, re-stated; tolerances are the reference's own)."""
+
+import numpy as np
+import pytest
+from scipy.stats import multivariate_normal
+
+torch = pytest.importorskip('torch')
+
+from nautilus_b200 import Prior, Sampler, likelihoods  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sampler_accuracy():
+    # tests/test_sampler.py:167-215: 2-D Gaussian, sigma 0.1
+    n_dim = 2
+    mean, cov = np.repeat(0.5, n_dim), np.eye(n_dim) * 0.01
+
+    def likelihood(x):
+        return multivariate_normal.logpdf(x, mean=mean, cov=cov)
+
+    sampler = Sampler(lambda x: x, likelihood, n_dim=n_dim, n_live=500,
+                      vectorized=True, seed=0)
+    assert sampler.run(f_live=0.45, n_eff=0, verbose=False)
+    assert sampler.run(n_eff=10000, verbose=False)
+    assert np.abs(sampler.log_z) < 0.05
+    points, log_w, log_l = sampler.posterior()
+    w = np.exp(log_w)
+    assert np.isclose(np.sum(w), 1)
+    assert np.allclose(np.average(points, weights=w, axis=0), mean, atol=0.01)
+    assert np.allclose(np.cov(points, aweights=w, rowvar=False), cov,
+                       atol=0.001)
+    points, log_w, log_l = sampler.posterior(equal_weight=True)
+    assert np.all(log_w == log_w[0]) and 0 < len(points) <= sampler.n_like
+    # strictly nested bounds
+    occ = sampler.shell_bound_occupation()
+    for i in range(len(occ)):
+        assert np.all(occ[i, :i + 1] == 1)
+        assert np.all(occ[i, i + 1:] < 1)
+    assert sampler.n_eff >= 10000
+    assert 0 < sampler.eta <= 1
+
+
+def test_sampler_device_likelihood_matches_host_likelihood():
+    like = likelihoods.Gaussian(3, mu=[0.4, 0.5, 0.6], sigma=0.1)
+    s_dev = Sampler(lambda x: x, like, n_dim=3, n_live=500, seed=1)
+    s_dev.run(n_eff=3000)
+    assert abs(s_dev.log_z - like.log_z_true) < 0.05
+    s_host = Sampler(lambda x: x, like.__call__, n_dim=3, n_live=500,
+                     vectorized=True, seed=1)
+    s_host.run(n_eff=3000)
+    # same seed, same arithmetic for log L up to summation order
+    assert abs(s_host.log_z - s_dev.log_z) < 1e-9
+    assert s_host.n_like == s_dev.n_like
+
+
+def test_sampler_flat_likelihood():
+    # tests/test_sampler.py:218-241: one bound, analytic log Z
+    def likelihood(x):
+        return -np.linalg.norm(x - 0.5, axis=-1) * 0.001
+
+    sampler = Sampler(lambda x: x, likelihood, n_dim=2, n_live=500,
+                      vectorized=True, enlarge_per_dim=100, seed=0)
+    sampler.run(f_live=0.45, n_eff=0)
+    sampler.run(n_eff=10000)
+    assert len(sampler.bounds) == 1
+    assert np.isclose(sampler.log_z, -4 * 0.5**3 / 3 * 0.001 * 3.07 / 3.07,
+                      atol=1e-3)
+    assert np.isclose(sampler.n_eff, sampler.n_like, rtol=1e-2)
+
+
+def test_sampler_constant_likelihood():
+    sampler = Sampler(lambda x: x, lambda x: np.zeros(len(x)), n_dim=2,
+                      n_live=500, vectorized=True, seed=0)
+    sampler.run(n_eff=2000)
+    assert np.isclose(sampler.log_z, 0, atol=1e-9)
+    assert len(sampler.bounds) == 1
+
+
+def test_sampler_n_like_max_and_resume():
+    like = likelihoods.Gaussian(2, sigma=0.1)
+
+    def make():
+        return Sampler(lambda x: x, like, n_dim=2, n_live=500, seed=0)
+
+    a = make()
+    assert a.run(n_eff=3000)
+    b = make()
+    assert not b.run(n_like_max=700, n_eff=3000)
+    assert b.n_like >= 700
+    assert b.run(n_eff=3000)
+    assert a.log_z == b.log_z and a.n_eff == b.n_eff
+
+
+def test_sampler_prior_object_and_dict():
+    prior = Prior()
+    prior.add_parameter('a', (-1, 1))
+    prior.add_parameter('b', 0.3)
+    prior.add_parameter('c', (0, 2))
+
+    def likelihood(p):
+        return -0.5 * ((p['a'] / 0.2)**2 + ((p['c'] - 1) / 0.2)**2) + \
+            0 * p['b']
+
+    sampler = Sampler(prior, likelihood, n_live=400, vectorized=True, seed=2)
+    sampler.run(n_eff=2000)
+    pts, log_w, log_l = sampler.posterior(return_as_dict=True)
+    assert set(pts) == {'a', 'b', 'c'} and np.all(pts['b'] == 0.3)
+    truth = np.log(2 * np.pi * 0.04 / 4)
+    assert abs(sampler.log_z - truth) < 0.1
+
+
+def test_sampler_errors():
+    with pytest.raises(ValueError):
+        Sampler(lambda x: x, lambda x: 0.0)                  # n_dim missing
+    with pytest.raises(ValueError):
+        Sampler(lambda x: x, lambda x: 0.0, n_dim=1)
+    with pytest.raises(NotImplementedError):
+        Sampler(lambda x: x, lambda x: 0.0, n_dim=2, filepath='x.hdf5')
+    s = Sampler(lambda x: x, lambda x: 0.0, n_dim=2)
+    with pytest.raises(ValueError):
+        s.discard_exploration = 1
