@@ -55,26 +55,70 @@ def test_sampler_device_likelihood_matches_host_likelihood():
     assert s_host.n_like == s_dev.n_like
 
 
-def test_sampler_flat_likelihood():
-    # tests/test_sampler.py:218-241: one bound, analytic log Z
+def test_sampler_enlarge_per_dim():
+    # tests/test_sampler.py:218-241: bounds so enlarged that every new bound
+    # equals the cube and is rejected; analytic log Z of a flat likelihood
     def likelihood(x):
-        return -np.linalg.norm(x - 0.5, axis=-1) * 0.001
+        return -np.linalg.norm(x - 0.5)**2 * 0.001
 
-    sampler = Sampler(lambda x: x, likelihood, n_dim=2, n_live=500,
-                      vectorized=True, enlarge_per_dim=100, seed=0)
-    sampler.run(f_live=0.45, n_eff=0)
-    sampler.run(n_eff=10000)
+    sampler = Sampler(lambda x: x, likelihood, n_dim=2, enlarge_per_dim=100,
+                      n_networks=0, seed=0)
+    sampler.run(f_live=0.1, n_eff=0)
+    assert np.isclose(sampler.n_like, sampler.n_eff, rtol=0, atol=1)
     assert len(sampler.bounds) == 1
-    assert np.isclose(sampler.log_z, -4 * 0.5**3 / 3 * 0.001 * 3.07 / 3.07,
-                      atol=1e-3)
-    assert np.isclose(sampler.n_eff, sampler.n_like, rtol=1e-2)
+    assert np.isclose(sampler.log_z, -4 * 0.5**3 / 3 * 0.001, rtol=0,
+                      atol=1e-4)
+
+
+def test_sampler_empty_shells():
+    # tests/test_sampler.py:244-258
+    def likelihood(x):
+        return -np.linalg.norm(x - 0.5)**2 * 0.001
+
+    sampler = Sampler(lambda x: x, likelihood, n_dim=2, n_networks=0, seed=0,
+                      n_update=1, n_live=10, n_batch=1)
+    sampler.run(f_live=1e-3, n_eff=0)
+    assert np.all(sampler.shell_n > 0)
+
+
+def test_sampler_funnel():
+    # tests/test_sampler.py:302-331
+    from scipy.stats import norm
+
+    def likelihood(x):
+        return (norm.logpdf(x[0], loc=0.5, scale=0.1) +
+                norm.logpdf(x[1], loc=0.5, scale=np.exp(20 * (x[0] - 0.5)) /
+                            100))
+
+    np.random.seed(0)
+    x_0 = np.random.normal(loc=0.5, scale=0.1, size=1000000)
+    x_1 = np.random.normal(loc=0.5, scale=np.exp(20 * (x_0 - 0.5)) / 100)
+    log_z_true = np.log(np.mean((x_0 > 0) & (x_0 < 1) & (x_1 > 0) & (x_1 < 1)))
+    sampler = Sampler(lambda x: x, likelihood, n_dim=2, n_networks=1, seed=0)
+    sampler.run()
+    assert np.isclose(log_z_true, sampler.log_z, rtol=0, atol=0.1)
+
+
+def test_sampler_plateau():
+    # tests/test_sampler.py:351-369
+    def likelihood(x):
+        if x[0] < 0.9:
+            return -np.inf
+        return np.log(x[0] - 0.9)
+
+    log_z_true = np.log(0.5 * 0.1**2)
+    for seed in range(3):
+        sampler = Sampler(lambda x: x, likelihood, 2, n_live=1000,
+                          n_networks=1, seed=seed)
+        sampler.run(f_live=0.1)
+        assert np.isclose(sampler.log_z, log_z_true, rtol=0, atol=0.1)
 
 
 def test_sampler_constant_likelihood():
-    sampler = Sampler(lambda x: x, lambda x: np.zeros(len(x)), n_dim=2,
-                      n_live=500, vectorized=True, seed=0)
-    sampler.run(n_eff=2000)
-    assert np.isclose(sampler.log_z, 0, atol=1e-9)
+    # tests/test_sampler.py:334-348
+    sampler = Sampler(lambda x: x, lambda x: 0, 2, n_live=500, seed=0)
+    sampler.run(f_live=0.1, n_eff=0)
+    assert np.isclose(sampler.log_z, 0)
     assert len(sampler.bounds) == 1
 
 
