@@ -203,20 +203,11 @@ class ClockSampler(threading.Thread):
 # GPU arm
 # --------------------------------------------------------------------------
 
-def merge_lse(parts):
-    """Combine per-rank (m, s1, s2) triples in rank order (deterministic)."""
-    m = max(p[0] for p in parts)
-    if not np.isfinite(m):
-        return m, 0.0, 0.0
-    s1 = sum(p[1] * np.exp(p[0] - m) for p in parts)
-    s2 = sum(p[2] * np.exp(2 * (p[0] - m)) for p in parts)
-    return m, s1, s2
-
-
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nautilus_b200 import likelihoods, ops
+    from nautilus_b200.pool import exchange_stats
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -242,11 +233,10 @@ def run_gpu(args):
 
     out = stack.cycle(0, n, seed=seed, like_id=like.like_id,
                       like_params=like_params, log_l_min=log_l_min, mode=mode)
-    packed = torch.zeros(ops.N_CNT + ops.N_LSE, dtype=torch.float64,
-                         device=dev)
-    gathered = torch.zeros((world, ops.N_CNT + ops.N_LSE),
-                           dtype=torch.float64, device=dev)
-    state = {'step': 0}
+    packed = torch.zeros(ops.N_CNT + 4, dtype=torch.float64, device=dev)
+    gathered = torch.zeros((world, ops.N_CNT + 4), dtype=torch.float64,
+                           device=dev)
+    state = {'step': 0, 'merged': None}
 
     def step():
         # every rank draws its own slice of the global proposal index space
@@ -257,10 +247,10 @@ def run_gpu(args):
                     like_params=like_params, log_l_min=log_l_min, mode=mode,
                     out=out)
         if world > 1:
-            # the one exchange step: per-rank counters + LSE partials
-            packed[:ops.N_CNT] = out['counters'].double()
-            packed[ops.N_CNT:] = out['lse']
-            dist.all_gather_into_tensor(gathered.view(-1), packed)
+            # the one exchange step: per-rank counters + LSE partials, merged
+            # on every rank (update_shell_info needs the global sums)
+            state['merged'] = exchange_stats(out['counters'], out['lse'],
+                                             gathered=gathered, packed=packed)
 
     def barrier():
         if world > 1:
@@ -298,9 +288,8 @@ def run_gpu(args):
 
     # result of the last step (also a sanity check on the collective)
     if world > 1:
-        g = gathered.cpu().numpy()
-        cnt = g[:, :ops.N_CNT].sum(axis=0)
-        m, s1, s2 = merge_lse([tuple(r[ops.N_CNT:ops.N_CNT + 3]) for r in g])
+        cnt, (m, s1, s2) = state['merged']
+        cnt = cnt.astype(float)
     else:
         cnt = out['counters'].cpu().numpy().astype(float)
         m, s1, s2 = out['lse'].cpu().numpy()[:3]

@@ -86,3 +86,48 @@ class GpuPool:
 
     def map(self, func, iterable):
         return [func(item) for item in iterable]
+
+
+# --------------------------------------------------------------------------
+# the one exchange step of the sharded cycle
+# --------------------------------------------------------------------------
+
+def merge_lse(parts):
+    """Combine per-rank (max, sum e^{l-m}, sum e^{2(l-m)}) triples, in rank
+    order so the result is deterministic."""
+    import numpy as np
+    m = max(float(p[0]) for p in parts)
+    if not np.isfinite(m):
+        return m, 0.0, 0.0
+    s1 = sum(float(p[1]) * np.exp(float(p[0]) - m) for p in parts
+             if np.isfinite(p[0]))
+    s2 = sum(float(p[2]) * np.exp(2 * (float(p[0]) - m)) for p in parts
+             if np.isfinite(p[0]))
+    return m, s1, s2
+
+
+def exchange_stats(counters, lse, gathered=None, packed=None, group=None):
+    """All-gather every rank's int64 counters and fp64 LSE partials with ONE
+    collective (NCCL on GPUs, gloo in the CPU tests) and merge them.
+
+    counters i64[n_cnt], lse f64[>=3] are tensors on this rank's device.
+    Counters (< 2^53) travel as float64 in the same buffer as the partials so
+    that a single collective suffices.  Returns (counters int64 ndarray,
+    (m, s1, s2)); every rank gets the same answer."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_cnt = counters.numel()
+    if packed is None:
+        packed = torch.empty(n_cnt + 4, dtype=torch.float64,
+                             device=counters.device)
+    packed[:n_cnt] = counters.double()
+    packed[n_cnt:n_cnt + 3] = lse[:3]
+    packed[n_cnt + 3] = 0
+    if gathered is None:
+        gathered = torch.empty((world, n_cnt + 4), dtype=torch.float64,
+                               device=counters.device)
+    dist.all_gather_into_tensor(gathered.view(-1), packed, group=group)
+    g = gathered.cpu().numpy()
+    total = g[:, :n_cnt].sum(axis=0).round().astype('int64')
+    return total, merge_lse([tuple(r[n_cnt:n_cnt + 3]) for r in g])

@@ -1,0 +1,58 @@
+"""End-to-end runs of the BASELINE.json configurations through the drop-in
+Sampler; prints one JSON line per run (wall time, n_like, bounds, log Z vs the
+analytic truth, N_eff).  Usage: python tools/run_config.py --config 2"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
+
+from nautilus_b200 import Sampler, likelihoods  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', type=int, default=2)
+    ap.add_argument('--n-eff', type=float, default=10000)
+    ap.add_argument('--n-batch', type=int, default=None)
+    ap.add_argument('--arith', default='tf32')
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--keep-exploration', action='store_true')
+    ap.add_argument('--timeout', type=float, default=1500)
+    args = ap.parse_args()
+    if args.config == 1:
+        like, n_live = likelihoods.Gaussian(3, mu=[0.4, 0.5, 0.6],
+                                            sigma=0.1), 1000
+    elif args.config == 2:
+        like, n_live = likelihoods.Gaussian(30, sigma=0.1), 2000
+    elif args.config == 4:
+        mus = np.full((4, 30), 0.5)
+        mus[:, 0] = [0.25, 0.25, 0.75, 0.75]
+        mus[:, 1] = [0.25, 0.75, 0.25, 0.75]
+        like, n_live = likelihoods.GaussianMixture(mus, sigma=0.03), 2000
+    else:
+        raise SystemExit('config not wired')
+    sampler = Sampler(lambda x: x, like, n_dim=like.n_dim, n_live=n_live,
+                      seed=args.seed, n_batch=args.n_batch,
+                      emulator_arith=args.arith)
+    t0 = time.time()
+    ok = sampler.run(n_eff=args.n_eff, timeout=args.timeout,
+                     discard_exploration=not args.keep_exploration)
+    wall = time.time() - t0
+    raw = sum(b.outer_bound.n_sample for b in sampler.bounds[1:])
+    print(json.dumps({
+        'config': args.config, 'success': bool(ok), 'wall_s': wall,
+        'n_like': int(sampler.n_like), 'n_bounds': len(sampler.bounds),
+        'log_z': float(sampler.log_z), 'log_z_true': like.log_z_true,
+        'delta_log_z': abs(float(sampler.log_z) - like.log_z_true),
+        'n_eff': float(sampler.n_eff), 'raw_proposals': int(raw),
+        'emulator_arith': args.arith, 'n_batch': sampler.n_batch,
+        'discard_exploration': not args.keep_exploration}), flush=True)
+
+
+if __name__ == '__main__':
+    main()
