@@ -20,9 +20,13 @@ __device__ __forceinline__ void load_rows(const double* __restrict__ src,
                                           int stride, double* sm) {
   const double* g = src + base * (int64_t)d;
   const int total = nrows * d;
+  // (row, col) advance incrementally: no integer division per element
+  const int step_r = (int)blockDim.x / d, step_c = (int)blockDim.x % d;
+  int r = (int)threadIdx.x / d, c = (int)threadIdx.x % d;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int r = e / d;
-    sm[r * stride + (e - r * d)] = g[e];
+    sm[r * stride + c] = g[e];
+    r += step_r; c += step_c;
+    if (c >= d) { c -= d; r += 1; }
   }
 }
 __device__ __forceinline__ void store_rows(double* __restrict__ dst,
@@ -30,9 +34,12 @@ __device__ __forceinline__ void store_rows(double* __restrict__ dst,
                                            int stride, const double* sm) {
   double* g = dst + base * (int64_t)d;
   const int total = nrows * d;
+  const int step_r = (int)blockDim.x / d, step_c = (int)blockDim.x % d;
+  int r = (int)threadIdx.x / d, c = (int)threadIdx.x % d;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int r = e / d;
-    g[e] = sm[r * stride + (e - r * d)];
+    g[e] = sm[r * stride + c];
+    r += step_r; c += step_c;
+    if (c >= d) { c -= d; r += 1; }
   }
 }
 

@@ -800,6 +800,17 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
                     int64_t n, double* score_out, uint8_t* passf,
                     float* xs32_ws, cudaStream_t st);
 
+int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
+                         int bound, int j, const float* xs32,
+                         const uint8_t* mask, int64_t n, uint8_t* code,
+                         cudaStream_t st);
+bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
+                      struct FrontArgs* args);
+int launch_front(const int32_t* meta_h, const int32_t* meta_d,
+                 const double* data_d, int bound, int64_t n, uint64_t seed,
+                 uint64_t offset, uint32_t stream_id, double* points,
+                 uint8_t* code, uint8_t* maskj, float* xs32, cudaStream_t st);
+
 // emulator of neural bound j on whitened rows; ORs into passf and/or writes
 // the scores.
 static int launch_mlp(const int32_t* meta_h, const int32_t* meta_d,
@@ -1196,14 +1207,31 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
   Workspace ws;
   workspace_layout(n < 1 ? 1 : n, d, (char*)workspace_d, &ws);
   int rc;
-  // 1. raw draws, cube filter, overlap acceptance
-  rc = nb200_union_propose(meta_h, meta_d, data_d, bound, n, seed, offset,
-                           stream_id, nullptr, nullptr, nullptr, nullptr,
-                           nullptr, points_d, code_d, nullptr, stream);
-  if (rc) return rc;
+  const bool fused = mlp_mode == NB200_MLP_TF32 && n > 0 &&
+                     front_applicable(meta_h, bound, nullptr, nullptr);
+  if (fused) {
+    // 1+2 fused: proposal, cube cut, overlap acceptance, neural-ellipsoid
+    // whitening and standardisation in one fp64 kernel, then the emulator on
+    // tensor cores writes NN rejects straight into the disposition bytes
+    rc = launch_front(meta_h, meta_d, data_d, bound, n, seed, offset,
+                      stream_id, points_d, code_d, ws.maskj, ws.xs32, st);
+    if (rc) return rc;
+    {
+      ProfScope prof(ST_MLP, st);
+      rc = launch_mlp_tf32_rows(meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n,
+                                code_d, st);
+    }
+    if (rc) return rc;
+  } else {
+    // 1. raw draws, cube filter, overlap acceptance
+    rc = nb200_union_propose(meta_h, meta_d, data_d, bound, n, seed, offset,
+                             stream_id, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, points_d, code_d, nullptr, stream);
+    if (rc) return rc;
+  }
   if (n > 0) {
     // 2. neural filter of NautilusBound.sample
-    if (rec.kind() == 1 && rec.J() > 0) {
+    if (!fused && rec.kind() == 1 && rec.J() > 0) {
       rc = launch_apply(0, n, code_d, ws.cand, ws.passf, nullptr, nullptr, st);
       if (rc) return rc;
       rc = neural_any(meta_h, meta_d, data_d, bound, points_d, ws.cand, 1, n,

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1)
 k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
            int64_t n, double* __restrict__ score_out,
-           uint8_t* __restrict__ passf) {
+           uint8_t* __restrict__ passf, uint8_t* __restrict__ code) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t wbar;
   __shared__ uint64_t mbar[TC_GROUPS];
@@ -300,6 +300,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       const double score = (double)(sum / (float)h.n_net);
       if (score_out) score_out[row] = score;
       if (passf && score > thr) passf[row] = 1;
+      if (code && !(score > thr)) code[row] = NB200_CODE_NN_REJECT;
     } else if (score_out && row < n) {
       score_out[row] = nan("");
     }
@@ -327,32 +328,17 @@ __global__ void k_standardise_tf32(const double* __restrict__ t_rows,
   const int k = (int)(e - row * k0p);
   float v = 0.f;
   if (k < d && (!mask || mask[row]))
-    v = (float)((t_rows[row * d + k] - __ldg(mean + k)) / __ldg(scale + k));
+    v = (float)((t_rows[row * d + k] - __ldg(mean + k)) *
+                (1.0 / __ldg(scale + k)));
   uint32_t rr;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
   xs32[e] = __uint_as_float(rr);
 }
 
-int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
-                    int j, const double* t_rows, const uint8_t* mask,
-                    int64_t n, double* score_out, uint8_t* passf,
-                    float* xs32_ws, cudaStream_t st) {
-  const Rec rec = record(meta_h, bound);
-  const int32_t* nb = rec.nb(j);
-  NB_CHECK(nb[10] >= 0 && nb[11] > 0,
-           "this emulator has no tensor-core blob (architecture outside the "
-           "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
-  TcHeader h;
-  memcpy(&h, rec.r + nb[11], sizeof(h));
-  NB_CHECK(h.magic == 0x7F32, "corrupt tensor-core blob header");
-  const int d = rec.d();
-  const float* blob = (const float*)(data_d + nb[10]);
-  {
-    const int64_t total = n * h.k0p;
-    k_standardise_tf32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        t_rows, mask, n, d, h.k0p, data_d + nb[5], data_d + nb[6], xs32_ws);
-    NB_LAUNCH_OK();
-  }
+static int run_mlp_tf32(const TcHeader& h, const float* blob,
+                        const float* xs32, const uint8_t* mask, int64_t n,
+                        double* score_out, uint8_t* passf, uint8_t* code,
+                        cudaStream_t st) {
   const size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
   NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32,
@@ -366,9 +352,50 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
   k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * 128, smem, st>>>(
-      h, blob, xs32_ws, mask, n, score_out, passf);
+      h, blob, xs32, mask, n, score_out, passf, code);
   NB_LAUNCH_OK();
   return 0;
+}
+
+static int tc_header(const int32_t* meta_h, int bound, int j, TcHeader* h) {
+  const Rec rec = record(meta_h, bound);
+  const int32_t* nb = rec.nb(j);
+  NB_CHECK(nb[10] >= 0 && nb[11] > 0,
+           "this emulator has no tensor-core blob (architecture outside the "
+           "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
+  memcpy(h, rec.r + nb[11], sizeof(*h));
+  NB_CHECK(h->magic == 0x7F32, "corrupt tensor-core blob header");
+  return 0;
+}
+
+// whitened fp64 rows in, scores / pass flags out
+int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
+                    int j, const double* t_rows, const uint8_t* mask,
+                    int64_t n, double* score_out, uint8_t* passf,
+                    float* xs32_ws, cudaStream_t st) {
+  TcHeader h;
+  if (tc_header(meta_h, bound, j, &h)) return 1;
+  const Rec rec = record(meta_h, bound);
+  const int32_t* nb = rec.nb(j);
+  const int64_t total = n * h.k0p;
+  k_standardise_tf32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      t_rows, mask, n, rec.d(), h.k0p, data_d + nb[5], data_d + nb[6],
+      xs32_ws);
+  NB_LAUNCH_OK();
+  return run_mlp_tf32(h, (const float*)(data_d + nb[10]), xs32_ws, mask, n,
+                      score_out, passf, nullptr, st);
+}
+
+// standardised tf32 rows in (from k_front); rejects are written into `code`
+int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
+                         int bound, int j, const float* xs32,
+                         const uint8_t* mask, int64_t n, uint8_t* code,
+                         cudaStream_t st) {
+  TcHeader h;
+  if (tc_header(meta_h, bound, j, &h)) return 1;
+  const Rec rec = record(meta_h, bound);
+  return run_mlp_tf32(h, (const float*)(data_d + rec.nb(j)[10]), xs32, mask,
+                      n, nullptr, nullptr, code, st);
 }
 
 }  // namespace nb200

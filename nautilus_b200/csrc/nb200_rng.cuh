@@ -43,17 +43,17 @@ __device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
          1.1102230246251565e-16;
 }
 // Two standard normals by Box-Muller in fp32 (24-bit uniforms, radius <=
-// 5.9 sigma).  The normals only fix a direction on the sphere, so fp32
-// resolution is ample; everything downstream is fp64.
+// 5.9 sigma) on the special-function unit (MUFU lg2 / sqrt / sin / cos).  The
+// normals only fix a direction on the sphere, so ~1e-6 absolute accuracy is
+// ample; everything downstream is fp64.
 __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0,
                                         float& n1) {
   const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;
-  const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;
-  const float rr = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  n0 = rr * c;
-  n1 = rr * s;
+  const float ang =
+      ((float)(b >> 8) * 5.9604644775390625e-8f - 0.5f) * 6.283185307179586f;
+  const float rr = sqrtf(-2.0f * __logf(u1));
+  n0 = rr * __cosf(ang);
+  n1 = rr * __sinf(ang);
 }
 
 }  // namespace nb200
