@@ -176,9 +176,14 @@ def pack_tc(emu, score_predict_min):
         return None
     sizes = [coefs[0][0].shape[0]] + [w.shape[1] for w in coefs[0]]
     d = sizes[0]
-    k0p = _round_up(d, 8)
-    np_ = [_round_up(sizes[l + 1], 16) for l in range(n_hid)]
-    kp = [k0p] + [_round_up(sizes[l + 1], 8) for l in range(n_hid - 1)]
+    # Biases ride on the tensor cores: the input row carries a constant 1 in
+    # its first padding column, every hidden layer regenerates that 1 in ITS
+    # first padding column (a weight of exactly 1 from the previous constant
+    # column; ReLU(1) = 1), and the bias vector is the weight row of that
+    # column.  Hence fan_in is padded to hold one extra column.
+    k0p = _round_up(d + 1, 8)
+    np_ = [_round_up(sizes[l + 1] + 1, 16) for l in range(n_hid)]
+    kp = [k0p] + [_round_up(sizes[l + 1] + 1, 8) for l in range(n_hid - 1)]
     # TMEM columns: input row, then one region per hidden layer (its
     # accumulator, rewritten in place as the next layer's A operand)
     a0_col, col = 0, _round_up(k0p, 32)
@@ -193,8 +198,8 @@ def pack_tc(emu, score_predict_min):
         w_off.append(off)
         off += np_[l] * kp[l]
     for l in range(n_hid):
-        b_off.append(off)
-        off += np_[l]
+        b_off.append(off)          # kept for layout stability; unused
+        off += 0
     w_out_off = off
     off += np_[-1]
     b_out_off = off
@@ -207,11 +212,14 @@ def pack_tc(emu, score_predict_min):
     for n in range(n_net):
         base = n * net_stride
         for l in range(n_hid):
-            wt = tf32_round(np.asarray(coefs[n][l], dtype=np.float64).T)
+            fi, fo = sizes[l], sizes[l + 1]
+            wt = np.zeros((fo + 1, fi + 1))
+            wt[:fo, :fi] = np.asarray(coefs[n][l], dtype=np.float64).T
+            wt[:fo, fi] = np.asarray(intercepts[n][l], dtype=np.float64)
+            if l + 1 < n_hid:
+                wt[fo, fi] = 1.0   # regenerate the constant-one column
             blob[base + w_off[l]:base + w_off[l] + np_[l] * kp[l]] = \
-                _core_matrix_layout(wt, np_[l], kp[l])
-            b = np.asarray(intercepts[n][l], dtype=np.float32)
-            blob[base + b_off[l]:base + b_off[l] + len(b)] = b
+                _core_matrix_layout(tf32_round(wt), np_[l], kp[l])
         w_out = np.asarray(coefs[n][-1], dtype=np.float32).ravel()
         blob[base + w_out_off:base + w_out_off + len(w_out)] = w_out
         blob[base + b_out_off] = np.float32(intercepts[n][-1][0])

@@ -178,23 +178,27 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
         // NeuralBound: ellipsoid test + whitened, standardised input row
         double r2 = 0.0;
         float* xrow = xs32 + i * (long long)A.k0p;
-        for (int i0 = 0; i0 < d8; i0 += 8) {
-          double acc[8];
-          mv8<true>(nbT, d8, i0, A.lower_n ? min(i0 + 8, d) : d, x, cN, acc);
+        for (int i0 = 0; i0 < A.k0p; i0 += 8) {
           uint32_t pk[8];
+          if (i0 < d8) {
+            double acc[8];
+            mv8<true>(nbT, d8, i0, A.lower_n ? min(i0 + 8, d) : d, x, cN, acc);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            r2 = fma(acc[q], acc[q], r2);
-            const float v =
-                (float)((acc[q] - meanN[i0 + q]) * iscaleN[i0 + q]);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[q]) : "f"(v));
+            for (int q = 0; q < 8; ++q) {
+              r2 = fma(acc[q], acc[q], r2);
+              float v = (float)((acc[q] - meanN[i0 + q]) * iscaleN[i0 + q]);
+              if (i0 + q == d) v = 1.0f;   // constant-one (bias) column
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[q]) : "f"(v));
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              pk[q] = (i0 + q == d) ? 0x3F800000u : 0u;
           }
-          if (i0 < A.k0p) {
-            *reinterpret_cast<uint4*>(xrow + i0) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(xrow + i0 + 4) =
-                make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
+          *reinterpret_cast<uint4*>(xrow + i0) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(xrow + i0 + 4) =
+              make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         in_ell = r2 < 1.0;
         if (!in_ell) cd = NB200_CODE_NN_REJECT;       // neural.py:117
@@ -230,7 +234,7 @@ bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   if (args) {
     args->rec_off = (int)(rec.r - meta_h);
     args->d = d; args->d8 = d8; args->K = K; args->unit = rec.unit();
-    args->k0p = d8; args->stride = d | 1;
+    args->k0p = (d + 1 + 7) / 8 * 8; args->stride = d | 1;
     args->smem_doubles = (int)doubles;
     args->lower_k = lower_k; args->lower_n = nb[2];
   }

@@ -775,7 +775,7 @@ static size_t workspace_layout(int64_t n, int d, char* base, Workspace* ws) {
   w.cand = (uint8_t*)take((size_t)n);
   w.passf = (uint8_t*)take((size_t)n);
   w.maskj = (uint8_t*)take((size_t)n);
-  w.xs32 = (float*)take((size_t)n * ((d + 7) / 8 * 8) * sizeof(float));
+  w.xs32 = (float*)take((size_t)n * ((d + 8) / 8 * 8) * sizeof(float));
   w.partial = (StatPartial*)take(sizeof(StatPartial) * STAT_MAX_BLOCKS);
   w.block_count =
       (long long*)take(sizeof(long long) * ((size_t)n / CMP_ITEMS + 2));

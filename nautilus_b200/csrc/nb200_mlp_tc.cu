@@ -164,7 +164,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            uint8_t* __restrict__ passf, uint8_t* __restrict__ code) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t wbar;
-  __shared__ uint64_t mbar[TC_GROUPS];
+  __shared__ uint64_t mbar[TC_GROUPS * 3];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
@@ -175,7 +175,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
   if (tid == 0) {
     mbar_init(&wbar, 1);
-    for (int q = 0; q < TC_GROUPS; ++q) mbar_init(&mbar[q], 1);
+    for (int q = 0; q < TC_GROUPS * 3; ++q) mbar_init(&mbar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -206,15 +206,48 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   mbar_wait(&wbar, 0);
 
-  uint32_t phase = 0;
+  uint32_t phA = 0, phB = 0, phC = 0;
   const int64_t n_tiles = (n + 127) / 128;
+  const int64_t tile_step = (int64_t)gridDim.x * TC_GROUPS;
+  // the input row of the NEXT tile is fetched into registers while the
+  // current tile runs (k0p <= 32: 8 x 16 B per thread)
+  const bool prefetch = h.k0p <= 32;
+  uint4 pre[8];
+  auto fetch = [&](int64_t t, bool& act) {
+    const int64_t rw = t * 128 + r;
+    act = t < n_tiles && rw < n && (!mask || mask[rw]);
+    if (act) {
+      const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q * 4 < h.k0p) pre[q] = __ldg(src + q);
+    }
+  };
+  bool next_active = false;
+  if (prefetch) fetch((int64_t)blockIdx.x * TC_GROUPS + g, next_active);
   for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + g; tile < n_tiles;
-       tile += (int64_t)gridDim.x * TC_GROUPS) {
+       tile += tile_step) {
     const int64_t row = tile * 128 + r;
-    const bool active = row < n && (!mask || mask[row]);
+    bool active;
 
     // ---- standardised input row -> TMEM (A operand of layer 0) ----------
-    {
+    if (prefetch) {
+      active = next_active;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q * 8 < h.k0p) {
+          uint32_t v[8];
+          const uint4 a = active ? pre[2 * q] : make_uint4(0, 0, 0, 0);
+          const uint4 b = active ? pre[2 * q + 1] : make_uint4(0, 0, 0, 0);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + q * 8), v);
+        }
+      }
+      tmem_wait_st();
+      fetch(tile + tile_step, next_active);
+    } else {
+      active = row < n && (!mask || mask[row]);
       const uint4* src = (const uint4*)(xs32 + row * (int64_t)h.k0p);
       for (int c = 0; c < h.k0p; c += 8) {
         uint32_t v[8];
@@ -234,67 +267,104 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     tc_fence_before();
     group_sync(g);
 
-    float sum = 0.f;
-    for (int net = 0; net < h.n_net; ++net) {
-      const float* wnet = wsm + (size_t)net * h.net_stride;
-      float y = 0.f;
-      for (int l = 0; l < h.n_hid; ++l) {
-        const int np = h.np[l], kp = h.kp[l];
-        if (r == 0) {   // the group's leader issues this layer's MMAs
-          tc_fence_after();
-          const uint32_t a_col = (l == 0) ? (uint32_t)h.a0_col
-                                          : (uint32_t)h.d_col[l - 1];
-          const uint32_t w_addr = smem_u32(wnet + h.w_off[l]);
-          const uint32_t idesc = idesc_tf32(np);
-          for (int s = 0; s < kp / 8; ++s) {
-            mma_tf32_ts(tmem_base + (uint32_t)h.d_col[l],
-                        tmem_base + a_col + (uint32_t)(s * 8),
-                        smem_desc(w_addr + (uint32_t)s * 256u, 128u,
-                                  (uint32_t)kp * 32u),
-                        idesc, s > 0 ? 1u : 0u);
-          }
-          mma_commit(&mbar[g]);
-        }
-        mbar_wait(&mbar[g], phase);
-        phase ^= 1u;
+    // ---- helpers --------------------------------------------------------
+    // leader: issue layer l of network `net`, completion arrives on `bar`
+    auto issue = [&](int net, int l, uint64_t* bar) {
+      if (r == 0) {
         tc_fence_after();
-        const float* bias = wnet + h.b_off[l];
-        const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-        if (l + 1 < h.n_hid) {
-          // bias + ReLU + tf32 rounding, written back in place
-          for (int c = 0; c < np; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(d_addr + (uint32_t)c, v);
-            tmem_wait_ld();
+        const float* wnet = wsm + (size_t)net * h.net_stride;
+        const int np = h.np[l], kp = h.kp[l];
+        const uint32_t a_col = (l == 0) ? (uint32_t)h.a0_col
+                                        : (uint32_t)h.d_col[l - 1];
+        const uint32_t w_addr = smem_u32(wnet + h.w_off[l]);
+        const uint32_t idesc = idesc_tf32(np);
+        for (int s = 0; s < kp / 8; ++s) {
+          mma_tf32_ts(tmem_base + (uint32_t)h.d_col[l],
+                      tmem_base + a_col + (uint32_t)(s * 8),
+                      smem_desc(w_addr + (uint32_t)s * 256u, 128u,
+                                (uint32_t)kp * 32u),
+                      idesc, s > 0 ? 1u : 0u);
+        }
+        mma_commit(bar);
+      }
+    };
+    // all: ReLU + tf32 rounding of layer l's accumulator, written back in
+    // place as the next layer's A operand (the bias was added by the MMA
+    // through the constant-one column, see _pack.py:pack_tc)
+    auto epi_hidden = [&](int l) {
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+      for (int c = 0; c < h.np[l]; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(d_addr + (uint32_t)c, v);
+        tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              v[q] = to_tf32(fmaxf(__uint_as_float(v[q]) + bias[c + q], 0.f));
-            tmem_st16(d_addr + (uint32_t)c, v);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          group_sync(g);
-        } else {
-          // last hidden layer: fold the fan_out-1 output layer in registers
-          const float* wout = wnet + h.w_out_off;
-          float acc = wnet[h.b_out_off];
-          for (int c = 0; c < np; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(d_addr + (uint32_t)c, v);
-            tmem_wait_ld();
+        for (int q = 0; q < 16; ++q)
+          v[q] = to_tf32(fmaxf(__uint_as_float(v[q]), 0.f));
+        tmem_st16(d_addr + (uint32_t)c, v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      group_sync(g);
+    };
+    // all: last hidden layer, the fan_out-1 output layer folded in registers
+    auto epi_last = [&](int net, int l) -> float {
+      tc_fence_after();
+      const float* wnet = wsm + (size_t)net * h.net_stride;
+      const float* wout = wnet + h.w_out_off;
+      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+      float acc = wnet[h.b_out_off];
+      for (int c = 0; c < h.np[l]; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(d_addr + (uint32_t)c, v);
+        tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              acc = fmaf(fmaxf(__uint_as_float(v[q]) + bias[c + q], 0.f),
-                         wout[c + q], acc);
-          }
-          y = acc;
-          // the next network's layer-0 MMA overwrites TMEM columns that this
-          // group's threads may still be reading: order ld before next MMA
-          tc_fence_before();
-          group_sync(g);
+        for (int q = 0; q < 16; ++q)
+          acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), wout[c + q], acc);
+      }
+      // a later MMA overwrites these columns: order the loads before it
+      tc_fence_before();
+      group_sync(g);
+      return acc;
+    };
+
+    float sum = 0.f;
+    if (h.n_hid == 3) {
+      // Two networks in flight per group: while the CUDA cores run one
+      // network's epilogue, the tensor pipe runs the other's next layer.
+      //   L0(n+1) || epilogue1(n),  L2(n) || epilogue0(n+1),
+      //   L1(n+1) || epilogue2(n)
+      uint64_t* bA = &mbar[g * 3 + 0];
+      uint64_t* bB = &mbar[g * 3 + 1];
+      uint64_t* bC = &mbar[g * 3 + 2];
+      issue(0, 0, bA);
+      mbar_wait(bA, phA); phA ^= 1u;
+      epi_hidden(0);
+      issue(0, 1, bB);
+      for (int net = 0; net < h.n_net; ++net) {
+        const bool more = net + 1 < h.n_net;
+        mbar_wait(bB, phB); phB ^= 1u;       // D1(net) ready, region 0 free
+        if (more) issue(net + 1, 0, bA);
+        epi_hidden(1);
+        issue(net, 2, bC);
+        if (more) {
+          mbar_wait(bA, phA); phA ^= 1u;
+          epi_hidden(0);
+        }
+        mbar_wait(bC, phC); phC ^= 1u;       // D2(net) ready, region 1 free
+        if (more) issue(net + 1, 1, bB);
+        sum += epi_last(net, 2);
+      }
+    } else {
+      uint64_t* bA = &mbar[g * 3 + 0];
+      for (int net = 0; net < h.n_net; ++net) {
+        for (int l = 0; l < h.n_hid; ++l) {
+          issue(net, l, bA);
+          mbar_wait(bA, phA); phA ^= 1u;
+          if (l + 1 < h.n_hid) epi_hidden(l);
+          else sum += epi_last(net, l);
         }
       }
-      sum += y;
     }
     if (active) {
       const double score = (double)(sum / (float)h.n_net);
@@ -327,9 +397,13 @@ __global__ void k_standardise_tf32(const double* __restrict__ t_rows,
   const int64_t row = e / k0p;
   const int k = (int)(e - row * k0p);
   float v = 0.f;
-  if (k < d && (!mask || mask[row]))
-    v = (float)((t_rows[row * d + k] - __ldg(mean + k)) *
-                (1.0 / __ldg(scale + k)));
+  if (!mask || mask[row]) {
+    if (k < d)
+      v = (float)((t_rows[row * d + k] - __ldg(mean + k)) *
+                  (1.0 / __ldg(scale + k)));
+    else if (k == d)
+      v = 1.0f;            // constant-one column that carries the biases
+  }
   uint32_t rr;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
   xs32[e] = __uint_as_float(rr);
