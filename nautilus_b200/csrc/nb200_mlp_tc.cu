@@ -29,7 +29,8 @@ namespace nb200 {
 
 constexpr int TC_MAX_HID = 4;
 constexpr int TC_HDR_WORDS = 32;
-constexpr int TC_GROUPS = 2;
+constexpr int TC_GROUPS = 2;            // tiles in flight per CTA
+constexpr int TC_GROUP_THREADS = 256;   // two threads per row of a tile
 constexpr int TC_COLS_PER_GROUP = 256;
 
 struct TcHeader {            // int32[32] in the meta tail (_pack.py:pack_tc)
@@ -83,7 +84,7 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void group_sync(int g) {
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem desc]^T, kind::tf32, M=128, cta_group::1
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
@@ -157,7 +158,7 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
 }
 
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_GROUPS * 128, 1)
+__global__ void __launch_bounds__(TC_GROUPS * TC_GROUP_THREADS, 1)
 k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
            int64_t n, double* __restrict__ score_out,
@@ -166,11 +167,14 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   __shared__ uint64_t wbar;
   __shared__ uint64_t mbar[TC_GROUPS * 3];
   __shared__ uint32_t tmem_slot;
+  __shared__ float part[TC_GROUPS][128];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int g = tid >> 7;            // tile group
+  const int g = tid >> 8;            // tile group (8 warps)
   const int r = tid & 127;           // row in tile == TMEM lane
+  const int hf = (tid >> 7) & 1;     // which half of the columns this thread
+                                     // handles (warps w and w+4 share lanes)
 
   const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
   if (tid == 0) {
@@ -212,15 +216,16 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   // the input row of the NEXT tile is fetched into registers while the
   // current tile runs (k0p <= 32: 8 x 16 B per thread)
   const bool prefetch = h.k0p <= 32;
-  uint4 pre[8];
+  uint4 pre[4];                        // this half's 16 columns
   auto fetch = [&](int64_t t, bool& act) {
     const int64_t rw = t * 128 + r;
     act = t < n_tiles && rw < n && (!mask || mask[rw]);
     if (act) {
-      const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
+      const uint4* src =
+          (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q * 4 < h.k0p) pre[q] = __ldg(src + q);
+      for (int q = 0; q < 4; ++q)
+        if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
     }
   };
   bool next_active = false;
@@ -234,14 +239,15 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     if (prefetch) {
       active = next_active;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < h.k0p) {
+      for (int q = 0; q < 2; ++q) {
+        const int c = hf * 16 + q * 8;
+        if (c < h.k0p) {
           uint32_t v[8];
           const uint4 a = active ? pre[2 * q] : make_uint4(0, 0, 0, 0);
           const uint4 b = active ? pre[2 * q + 1] : make_uint4(0, 0, 0, 0);
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
           v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + q * 8), v);
+          tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
         }
       }
       tmem_wait_st();
@@ -249,7 +255,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     } else {
       active = row < n && (!mask || mask[row]);
       const uint4* src = (const uint4*)(xs32 + row * (int64_t)h.k0p);
-      for (int c = 0; c < h.k0p; c += 8) {
+      for (int c = hf * 8; c < h.k0p; c += 16) {
         uint32_t v[8];
         if (active) {
           const uint4 a = __ldg(src + (c >> 2));
@@ -270,7 +276,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     // ---- helpers --------------------------------------------------------
     // leader: issue layer l of network `net`, completion arrives on `bar`
     auto issue = [&](int net, int l, uint64_t* bar) {
-      if (r == 0) {
+      if (r == 0 && hf == 0) {
         tc_fence_after();
         const float* wnet = wsm + (size_t)net * h.net_stride;
         const int np = h.np[l], kp = h.kp[l];
@@ -294,13 +300,15 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     auto epi_hidden = [&](int l) {
       tc_fence_after();
       const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-      for (int c = 0; c < h.np[l]; c += 16) {
+      for (int c = hf * 16; c < h.np[l]; c += 32) {
         uint32_t v[16];
         tmem_ld16(d_addr + (uint32_t)c, v);
         tmem_wait_ld();
+        // ReLU, then round-half-up to tf32: the MMA reads only the top 19
+        // bits, so adding half an ulp of tf32 is the whole rounding
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          v[q] = to_tf32(fmaxf(__uint_as_float(v[q]), 0.f));
+          v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
         tmem_st16(d_addr + (uint32_t)c, v);
       }
       tmem_wait_st();
@@ -313,8 +321,8 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       const float* wnet = wsm + (size_t)net * h.net_stride;
       const float* wout = wnet + h.w_out_off;
       const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-      float acc = wnet[h.b_out_off];
-      for (int c = 0; c < h.np[l]; c += 16) {
+      float acc = hf ? 0.f : wnet[h.b_out_off];
+      for (int c = hf * 16; c < h.np[l]; c += 32) {
         uint32_t v[16];
         tmem_ld16(d_addr + (uint32_t)c, v);
         tmem_wait_ld();
@@ -322,10 +330,11 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
         for (int q = 0; q < 16; ++q)
           acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), wout[c + q], acc);
       }
+      if (hf) part[g][r] = acc;
       // a later MMA overwrites these columns: order the loads before it
       tc_fence_before();
       group_sync(g);
-      return acc;
+      return hf ? 0.f : acc + part[g][r];
     };
 
     float sum = 0.f;
@@ -366,6 +375,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
         }
       }
     }
+    if (hf) continue;                 // results are written by half 0
     if (active) {
       const double score = (double)(sum / (float)h.n_net);
       if (score_out) score_out[row] = score;
@@ -425,7 +435,7 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   int64_t grid = (n_tiles + TC_GROUPS - 1) / TC_GROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * 128, smem, st>>>(
+  k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * TC_GROUP_THREADS, smem, st>>>(
       h, blob, xs32, mask, n, score_out, passf, code);
   NB_LAUNCH_OK();
   return 0;
