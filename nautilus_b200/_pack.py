@@ -335,6 +335,17 @@ def pack_record(spec, data, cdf=None):
     hdr[7] = HDR
     hdr[8] = HDR + K * MIX_REC
     hdr[9] = max_width
+    # the usual unimodal bound: the neural bound's ellipsoid IS mixture k's
+    # (both are the MVEE of the same live points) -> one whitening serves both
+    if J == 1:
+        nbe = spec['neural'][0]['ell']
+        for k, mix in enumerate(spec['mixtures']):
+            e = mix['ell']
+            if (e is not None and not np.any(mix['dim_cube']) and
+                    np.array_equal(e['c'], nbe['c']) and
+                    np.array_equal(e['B_inv'], nbe['B_inv'])):
+                hdr[10] = k + 1
+                break
     rec = np.concatenate([hdr, mix_recs.ravel(), nb_recs.ravel()] + tail)
     rec = rec.astype(np.int32)
     rec[0] = len(rec)

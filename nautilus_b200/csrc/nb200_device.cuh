@@ -186,4 +186,112 @@ struct Lse {
   }
 };
 
+
+// ---- built-in likelihoods; x may live in any memory space --
+__device__ __forceinline__ double loglike_eval(int like_id,
+                                               const double* __restrict__ p,
+                                               const double* x, int d) {
+  double out;
+  if (like_id == NB200_LIKE_GAUSSIAN) {
+    const double* mu = p + 2;
+    double s2 = 0.0;
+    for (int j = 0; j < d; ++j) {
+      const double v = x[j] - __ldg(mu + j);
+      s2 = fma(v, v, s2);
+    }
+    out = -0.5 * __ldg(p) * s2 + __ldg(p + 1);
+  } else if (like_id == NB200_LIKE_ROSENBROCK) {
+    const double lo = __ldg(p), w = __ldg(p + 1);
+    double acc = 0.0;
+    double cur = lo + w * x[0];
+    for (int j = 0; j + 1 < d; ++j) {
+      const double nxt = lo + w * x[j + 1];
+      const double a = nxt - cur * cur;
+      const double b = 1.0 - cur;
+      acc += 100.0 * a * a + b * b;
+      cur = nxt;
+    }
+    out = -acc;
+  } else if (like_id == NB200_LIKE_MIXTURE) {
+    const int M = (int)__ldg(p);
+    const double is2 = __ldg(p + 1), norm = __ldg(p + 2);
+    const double* mu = p + 3;
+    Lse acc;
+    acc.init();
+    for (int mth = 0; mth < M; ++mth) {
+      double s2 = 0.0;
+      for (int j = 0; j < d; ++j) {
+        const double v = x[j] - __ldg(mu + mth * d + j);
+        s2 = fma(v, v, s2);
+      }
+      acc.add(-0.5 * is2 * s2);
+    }
+    out = acc.m + log(acc.s1) - log((double)M) + norm;
+  } else {  // NB200_LIKE_EQUICORR
+    const double a = __ldg(p), b = __ldg(p + 1), norm = __ldg(p + 2);
+    const double* mu = p + 3;
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < d; ++j) {
+      const double v = x[j] - __ldg(mu + j);
+      s1 += v;
+      s2 = fma(v, v, s2);
+    }
+    out = -0.5 * (a * s2 - b * s1 * s1) + norm;
+  }
+  return out;
+}
+
+// ---- shell sums: per-block partials -----------------------------------------
+constexpr int STAT_THREADS = 256;
+constexpr int STAT_MAX_BLOCKS = 1184;  // 148 SMs x 8 resident CTAs
+
+struct StatPartial {
+  double m, s1, s2, pad;
+  long long cnt[NB200_N_CNT];
+};
+
+// Deterministic block reduction (warp shuffles, then warp leaders in order).
+template <int THREADS>
+__device__ __forceinline__ void stat_block_reduce(Lse& acc, long long* cnt,
+                                                  StatPartial* dst) {
+  __shared__ double sm_m[THREADS / 32], sm_s1[THREADS / 32],
+      sm_s2[THREADS / 32];
+  __shared__ long long sm_c[THREADS / 32][NB200_N_CNT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Lse other;
+    other.m = __shfl_down_sync(0xffffffffu, acc.m, o);
+    other.s1 = __shfl_down_sync(0xffffffffu, acc.s1, o);
+    other.s2 = __shfl_down_sync(0xffffffffu, acc.s2, o);
+    acc.merge(other);
+#pragma unroll
+    for (int q = 0; q < NB200_N_CNT; ++q)
+      cnt[q] += __shfl_down_sync(0xffffffffu, cnt[q], o);
+  }
+  if (lane == 0) {
+    sm_m[warp] = acc.m; sm_s1[warp] = acc.s1; sm_s2[warp] = acc.s2;
+#pragma unroll
+    for (int q = 0; q < NB200_N_CNT; ++q) sm_c[warp][q] = cnt[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Lse tot;
+    tot.m = sm_m[0]; tot.s1 = sm_s1[0]; tot.s2 = sm_s2[0];
+    long long c[NB200_N_CNT];
+#pragma unroll
+    for (int q = 0; q < NB200_N_CNT; ++q) c[q] = sm_c[0][q];
+    for (int w = 1; w < THREADS / 32; ++w) {
+      Lse o;
+      o.m = sm_m[w]; o.s1 = sm_s1[w]; o.s2 = sm_s2[w];
+      tot.merge(o);
+#pragma unroll
+      for (int q = 0; q < NB200_N_CNT; ++q) c[q] += sm_c[w][q];
+    }
+    dst->m = tot.m; dst->s1 = tot.s1; dst->s2 = tot.s2; dst->pad = 0.0;
+#pragma unroll
+    for (int q = 0; q < NB200_N_CNT; ++q) dst->cnt[q] = c[q];
+  }
+}
+
 }  // namespace nb200

@@ -29,6 +29,8 @@ struct FrontArgs {
   int smem_doubles;
   unsigned int lower_k;   // bit k: B_inv of mixture k is exactly lower-tri
   int lower_n;            // same for the neural bound's B_inv
+  int same_k;             // mixture whose ellipsoid equals the neural bound's
+                          // (-1: none)
   unsigned long long seed, offset;
   unsigned int stream_id;
   long long n;
@@ -163,21 +165,12 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
       }
       uint8_t cd = NB200_CODE_IN_SHELL;
       bool in_ell = false;
-      if (A.unit && !cube_ok(x, nullptr, d)) {
-        cd = NB200_CODE_CUBE_REJECT;                  // union.py:313-314
-      } else {
-        int nbnd = 0;                                 // union.py:316-317
-        for (int kk = 0; kk < K; ++kk)
-          nbnd += r2_staged(BinvT + (size_t)kk * mat, d, d8,
-                            (A.lower_k >> kk) & 1, x, cK + kk * d8) < 1.0
-                      ? 1 : 0;
-        if (!(r > 1.0 - 1.0 / (double)nbnd))          // union.py:318-319
-          cd = NB200_CODE_OVERLAP_REJECT;
-      }
-      if (cd == NB200_CODE_IN_SHELL) {
-        // NeuralBound: ellipsoid test + whitened, standardised input row
+      float* xrow = xs32 + i * (long long)A.k0p;
+      // whitening w.r.t. the neural bound's ellipsoid: r2 and the
+      // standardised, tf32-rounded emulator input row (with the constant-one
+      // bias column at index d)
+      auto whiten_store = [&]() -> double {
         double r2 = 0.0;
-        float* xrow = xs32 + i * (long long)A.k0p;
         for (int i0 = 0; i0 < A.k0p; i0 += 8) {
           uint32_t pk[8];
           if (i0 < d8) {
@@ -187,7 +180,7 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
             for (int q = 0; q < 8; ++q) {
               r2 = fma(acc[q], acc[q], r2);
               float v = (float)((acc[q] - meanN[i0 + q]) * iscaleN[i0 + q]);
-              if (i0 + q == d) v = 1.0f;   // constant-one (bias) column
+              if (i0 + q == d) v = 1.0f;
               asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[q]) : "f"(v));
             }
           } else {
@@ -200,8 +193,32 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
           *reinterpret_cast<uint4*>(xrow + i0 + 4) =
               make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        in_ell = r2 < 1.0;
-        if (!in_ell) cd = NB200_CODE_NN_REJECT;       // neural.py:117
+        return r2;
+      };
+      double r2_nb = -1.0;
+      if (A.unit && !cube_ok(x, nullptr, d)) {
+        cd = NB200_CODE_CUBE_REJECT;                  // union.py:313-314
+      } else {
+        int nbnd = 0;                                 // union.py:316-317
+        for (int kk = 0; kk < K; ++kk) {
+          double r2;
+          if (kk == A.same_k) {
+            r2 = whiten_store();      // same ellipsoid: one pass serves both
+            r2_nb = r2;
+          } else {
+            r2 = r2_staged(BinvT + (size_t)kk * mat, d, d8,
+                           (A.lower_k >> kk) & 1, x, cK + kk * d8);
+          }
+          nbnd += r2 < 1.0 ? 1 : 0;
+        }
+        if (!(r > 1.0 - 1.0 / (double)nbnd))          // union.py:318-319
+          cd = NB200_CODE_OVERLAP_REJECT;
+      }
+      if (cd == NB200_CODE_IN_SHELL) {
+        // NeuralBound: ellipsoid test (neural.py:117)
+        if (A.same_k < 0) r2_nb = whiten_store();
+        in_ell = r2_nb < 1.0;
+        if (!in_ell) cd = NB200_CODE_NN_REJECT;
       }
       code[i] = cd;
       maskj[i] = in_ell ? 1 : 0;
@@ -237,6 +254,7 @@ bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
     args->k0p = (d + 1 + 7) / 8 * 8; args->stride = d | 1;
     args->smem_doubles = (int)doubles;
     args->lower_k = lower_k; args->lower_n = nb[2];
+    args->same_k = rec.r[10] - 1;
   }
   return true;
 }

@@ -490,110 +490,12 @@ __global__ void k_loglike(const double* __restrict__ points,
     log_l[i] = nan("");
     return;
   }
-  const double* x = sm + threadIdx.x * stride;
-  double out;
-  if (like_id == NB200_LIKE_GAUSSIAN) {
-    const double* mu = p + 2;
-    double s2 = 0.0;
-    for (int j = 0; j < d; ++j) {
-      const double v = x[j] - __ldg(mu + j);
-      s2 = fma(v, v, s2);
-    }
-    out = -0.5 * __ldg(p) * s2 + __ldg(p + 1);
-  } else if (like_id == NB200_LIKE_ROSENBROCK) {
-    const double lo = __ldg(p), w = __ldg(p + 1);
-    double acc = 0.0;
-    double cur = lo + w * x[0];
-    for (int j = 0; j + 1 < d; ++j) {
-      const double nxt = lo + w * x[j + 1];
-      const double a = nxt - cur * cur;
-      const double b = 1.0 - cur;
-      acc += 100.0 * a * a + b * b;
-      cur = nxt;
-    }
-    out = -acc;
-  } else if (like_id == NB200_LIKE_MIXTURE) {
-    const int M = (int)__ldg(p);
-    const double is2 = __ldg(p + 1), norm = __ldg(p + 2);
-    const double* mu = p + 3;
-    Lse acc;
-    acc.init();
-    for (int mth = 0; mth < M; ++mth) {
-      double s2 = 0.0;
-      for (int j = 0; j < d; ++j) {
-        const double v = x[j] - __ldg(mu + mth * d + j);
-        s2 = fma(v, v, s2);
-      }
-      acc.add(-0.5 * is2 * s2);
-    }
-    out = acc.m + log(acc.s1) - log((double)M) + norm;
-  } else {  // NB200_LIKE_EQUICORR
-    const double a = __ldg(p), b = __ldg(p + 1), norm = __ldg(p + 2);
-    const double* mu = p + 3;
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < d; ++j) {
-      const double v = x[j] - __ldg(mu + j);
-      s1 += v;
-      s2 = fma(v, v, s2);
-    }
-    out = -0.5 * (a * s2 - b * s1 * s1) + norm;
-  }
-  log_l[i] = out;
+  log_l[i] = loglike_eval(like_id, p, sm + threadIdx.x * stride, d);
 }
 
 // ==========================================================================
 // Shell reductions (nautilus/sampler.py:925-943, 1144)
 // ==========================================================================
-
-constexpr int STAT_THREADS = 256;
-constexpr int STAT_MAX_BLOCKS = 1184;  // 148 SMs x 8 resident CTAs
-
-struct StatPartial {
-  double m, s1, s2, pad;
-  long long cnt[NB200_N_CNT];
-};
-
-__device__ __forceinline__ void stat_block_reduce(Lse& acc, long long* cnt,
-                                                  StatPartial* dst) {
-  __shared__ double sm_m[STAT_THREADS / 32], sm_s1[STAT_THREADS / 32],
-      sm_s2[STAT_THREADS / 32];
-  __shared__ long long sm_c[STAT_THREADS / 32][NB200_N_CNT];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Lse other;
-    other.m = __shfl_down_sync(0xffffffffu, acc.m, o);
-    other.s1 = __shfl_down_sync(0xffffffffu, acc.s1, o);
-    other.s2 = __shfl_down_sync(0xffffffffu, acc.s2, o);
-    acc.merge(other);
-#pragma unroll
-    for (int q = 0; q < NB200_N_CNT; ++q)
-      cnt[q] += __shfl_down_sync(0xffffffffu, cnt[q], o);
-  }
-  if (lane == 0) {
-    sm_m[warp] = acc.m; sm_s1[warp] = acc.s1; sm_s2[warp] = acc.s2;
-#pragma unroll
-    for (int q = 0; q < NB200_N_CNT; ++q) sm_c[warp][q] = cnt[q];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Lse tot;
-    tot.m = sm_m[0]; tot.s1 = sm_s1[0]; tot.s2 = sm_s2[0];
-    long long c[NB200_N_CNT];
-#pragma unroll
-    for (int q = 0; q < NB200_N_CNT; ++q) c[q] = sm_c[0][q];
-    for (int w = 1; w < STAT_THREADS / 32; ++w) {
-      Lse o;
-      o.m = sm_m[w]; o.s1 = sm_s1[w]; o.s2 = sm_s2[w];
-      tot.merge(o);
-#pragma unroll
-      for (int q = 0; q < NB200_N_CNT; ++q) c[q] += sm_c[w][q];
-    }
-    dst->m = tot.m; dst->s1 = tot.s1; dst->s2 = tot.s2; dst->pad = 0.0;
-#pragma unroll
-    for (int q = 0; q < NB200_N_CNT; ++q) dst->cnt[q] = c[q];
-  }
-}
 
 __global__ void __launch_bounds__(STAT_THREADS)
 k_stats_partial(const double* __restrict__ log_l,
@@ -620,7 +522,7 @@ k_stats_partial(const double* __restrict__ log_l,
       cnt[1 + cd] += 1;  // codes 0..3 -> counters 1..4
     }
   }
-  stat_block_reduce(acc, cnt, partial + blockIdx.x);
+  stat_block_reduce<STAT_THREADS>(acc, cnt, partial + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(STAT_THREADS)
@@ -639,7 +541,7 @@ k_stats_final(const StatPartial* __restrict__ partial, int nblocks,
     for (int q = 0; q < NB200_N_CNT; ++q) cnt[q] += partial[b].cnt[q];
   }
   __shared__ StatPartial tot;
-  stat_block_reduce(acc, cnt, &tot);
+  stat_block_reduce<STAT_THREADS>(acc, cnt, &tot);
   __syncthreads();
   if (threadIdx.x == 0) {
     lse[0] = tot.m; lse[1] = tot.s1; lse[2] = tot.s2; lse[3] = 0.0;
@@ -803,6 +705,9 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
 int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
+                         const double* points, int like_id,
+                         const double* like_p, double log_l_min,
+                         double* log_l, void* partial, int* n_partial_out,
                          cudaStream_t st);
 bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
                       struct FrontArgs* args);
@@ -1209,6 +1114,8 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
   int rc;
   const bool fused = mlp_mode == NB200_MLP_TF32 && n > 0 &&
                      front_applicable(meta_h, bound, nullptr, nullptr);
+  bool fused_tail = false;
+  int n_partial = 0;
   if (fused) {
     // 1+2 fused: proposal, cube cut, overlap acceptance, neural-ellipsoid
     // whitening and standardisation in one fp64 kernel, then the emulator on
@@ -1216,12 +1123,23 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
     rc = launch_front(meta_h, meta_d, data_d, bound, n, seed, offset,
                       stream_id, points_d, code_d, ws.maskj, ws.xs32, st);
     if (rc) return rc;
+    // without later bounds the likelihood and the shell sums ride along
+    fused_tail = n_later == 0 && like_id >= 0 && lse_d && counters_d;
     {
       ProfScope prof(ST_MLP, st);
-      rc = launch_mlp_tf32_rows(meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n,
-                                code_d, st);
+      rc = launch_mlp_tf32_rows(
+          meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n, code_d, points_d,
+          like_id, like_params_d, log_l_min, log_l_d,
+          fused_tail ? (void*)ws.partial : nullptr, &n_partial, st);
     }
     if (rc) return rc;
+    if (fused_tail) {
+      ProfScope prof(ST_STATS, st);
+      k_stats_final<<<1, STAT_THREADS, 0, st>>>(ws.partial, n_partial, lse_d,
+                                                (long long*)counters_d);
+      NB_LAUNCH_OK();
+      return 0;
+    }
   } else {
     // 1. raw draws, cube filter, overlap acceptance
     rc = nb200_union_propose(meta_h, meta_d, data_d, bound, n, seed, offset,

@@ -23,7 +23,7 @@
 // Arithmetic is tf32 x tf32 -> fp32, so scores differ from the fp64 path by
 // ~1e-3; membership near the threshold can flip (rate reported by the tests),
 // which is why the fp64 kernel remains the parity mode.
-#include "nb200_common.cuh"
+#include "nb200_device.cuh"
 
 namespace nb200 {
 
@@ -45,6 +45,18 @@ struct TcHeader {            // int32[32] in the meta tail (_pack.py:pack_tc)
   int thr_lo, thr_hi;        // bits of the fp64 threshold score_predict_min-1e-9
 };
 static_assert(sizeof(TcHeader) == TC_HDR_WORDS * 4, "header size");
+
+// Optional fused tail: built-in likelihood of the accepted points and the
+// per-block partials of the shell sums (nb200_stats), so that a cycle without
+// later bounds is front kernel -> this kernel -> one tiny final reduction.
+struct TcTail {
+  const double* points;
+  const double* like_p;
+  double* log_l;
+  StatPartial* partial;     // nullptr: tail disabled
+  double log_l_min;
+  int d, like_id;
+};
 
 // ---- PTX wrappers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -162,7 +174,8 @@ __global__ void __launch_bounds__(TC_GROUPS * TC_GROUP_THREADS, 1)
 k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
            int64_t n, double* __restrict__ score_out,
-           uint8_t* __restrict__ passf, uint8_t* __restrict__ code) {
+           uint8_t* __restrict__ passf, uint8_t* __restrict__ code,
+           const TcTail tail) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t wbar;
   __shared__ uint64_t mbar[TC_GROUPS * 3];
@@ -209,6 +222,12 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   mbar_wait(&wbar, 0);
+
+  Lse lse_acc;
+  lse_acc.init();
+  int cnt32[NB200_N_CNT];
+#pragma unroll
+  for (int q = 0; q < NB200_N_CNT; ++q) cnt32[q] = 0;
 
   uint32_t phA = 0, phB = 0, phC = 0;
   const int64_t n_tiles = (n + 127) / 128;
@@ -376,16 +395,44 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       }
     }
     if (hf) continue;                 // results are written by half 0
+    bool accepted = false;
     if (active) {
       const double score = (double)(sum / (float)h.n_net);
+      accepted = score > thr;
       if (score_out) score_out[row] = score;
-      if (passf && score > thr) passf[row] = 1;
-      if (code && !(score > thr)) code[row] = NB200_CODE_NN_REJECT;
+      if (passf && accepted) passf[row] = 1;
+      if (code && !accepted) code[row] = NB200_CODE_NN_REJECT;
     } else if (score_out && row < n) {
       score_out[row] = nan("");
     }
+    if (tail.partial && row < n) {
+      // disposition histogram, likelihood and log-sum-exp of this row
+      const int cd = active ? (accepted ? NB200_CODE_IN_SHELL
+                                        : NB200_CODE_NN_REJECT)
+                            : (int)code[row];
+      cnt32[NB200_CNT_RAW] += 1;
+      if (cd == NB200_CODE_IN_SHELL) {
+        const double ll = loglike_eval(tail.like_id, tail.like_p,
+                                       tail.points + row * (int64_t)tail.d,
+                                       tail.d);
+        tail.log_l[row] = ll;
+        lse_acc.add(ll);
+        cnt32[NB200_CNT_IN_SHELL] += 1;
+        if (ll >= tail.log_l_min) cnt32[NB200_CNT_UPDATE] += 1;
+      } else {
+        tail.log_l[row] = nan("");
+        cnt32[1 + cd] += 1;
+      }
+    }
   }
 
+  if (tail.partial) {
+    long long cnt[NB200_N_CNT];
+#pragma unroll
+    for (int q = 0; q < NB200_N_CNT; ++q) cnt[q] = cnt32[q];
+    stat_block_reduce<TC_GROUPS * TC_GROUP_THREADS>(
+        lse_acc, cnt, tail.partial + blockIdx.x);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -422,7 +469,7 @@ __global__ void k_standardise_tf32(const double* __restrict__ t_rows,
 static int run_mlp_tf32(const TcHeader& h, const float* blob,
                         const float* xs32, const uint8_t* mask, int64_t n,
                         double* score_out, uint8_t* passf, uint8_t* code,
-                        cudaStream_t st) {
+                        const TcTail& tail, int* grid_out, cudaStream_t st) {
   const size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
   NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32,
@@ -435,8 +482,10 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   int64_t grid = (n_tiles + TC_GROUPS - 1) / TC_GROUPS;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
+  if (tail.partial) NB_CHECK(grid <= STAT_MAX_BLOCKS, "too many partials");
+  if (grid_out) *grid_out = (int)grid;
   k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * TC_GROUP_THREADS, smem, st>>>(
-      h, blob, xs32, mask, n, score_out, passf, code);
+      h, blob, xs32, mask, n, score_out, passf, code, tail);
   NB_LAUNCH_OK();
   return 0;
 }
@@ -466,20 +515,32 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
       t_rows, mask, n, rec.d(), h.k0p, data_d + nb[5], data_d + nb[6],
       xs32_ws);
   NB_LAUNCH_OK();
+  TcTail none;
+  memset(&none, 0, sizeof(none));
   return run_mlp_tf32(h, (const float*)(data_d + nb[10]), xs32_ws, mask, n,
-                      score_out, passf, nullptr, st);
+                      score_out, passf, nullptr, none, nullptr, st);
 }
 
 // standardised tf32 rows in (from k_front); rejects are written into `code`
+// With `partial` != nullptr the likelihood and the per-block shell sums are
+// fused in (one StatPartial per CTA, *n_partial_out of them).
 int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
+                         const double* points, int like_id,
+                         const double* like_p, double log_l_min,
+                         double* log_l, void* partial, int* n_partial_out,
                          cudaStream_t st) {
   TcHeader h;
   if (tc_header(meta_h, bound, j, &h)) return 1;
   const Rec rec = record(meta_h, bound);
+  TcTail tail;
+  memset(&tail, 0, sizeof(tail));
+  tail.points = points; tail.like_p = like_p; tail.log_l = log_l;
+  tail.partial = (StatPartial*)partial; tail.log_l_min = log_l_min;
+  tail.d = rec.d(); tail.like_id = like_id;
   return run_mlp_tf32(h, (const float*)(data_d + rec.nb(j)[10]), xs32, mask,
-                      n, nullptr, nullptr, code, st);
+                      n, nullptr, nullptr, code, tail, n_partial_out, st);
 }
 
 }  // namespace nb200

@@ -103,3 +103,73 @@ def test_tf32_cycle_self_consistent(golden):
     diff = (out['code'] != out64['code']).float().mean().item()
     print('cycle disposition mismatch tf32 vs f64: {:.3e}'.format(diff))
     assert diff < 0.02
+
+
+def _fused_vs_staged(spec, n, like, seed):
+    """The fused tf32 cycle (k_front -> k_mlp_tf32 with likelihood and shell
+    sums in its tail) against the same decisions rebuilt from staged ops."""
+    from oracle import nautilus_oracle as orc
+    stack = ops.DeviceStack([spec])
+    out = stack.cycle(0, n, seed=seed, offset=77, stream_id=5,
+                      like_id=like.like_id,
+                      like_params=like.device_params('cuda'), log_l_min=-5.0,
+                      mode=ops.MLP_TF32)
+    pts = out['points']
+    code = out['code'].cpu().numpy()
+    log_l = out['log_l'].cpu().numpy()
+    # union stage decided in fp64: bit-exact against the oracle
+    _, r, _ = orc.replay_integer_stream(n, 77, 5, seed, spec)
+    p = pts.cpu().numpy()
+    in_cube = orc.cube_contains(p)
+    nb = np.zeros(n, dtype=int)
+    nb[in_cube] = orc.union_count(spec, p[in_cube])
+    with np.errstate(divide='ignore'):
+        acc = in_cube & (r > 1 - 1.0 / np.maximum(nb, 0))
+    assert np.array_equal(code == 0, ~in_cube)
+    assert np.array_equal(code == 1, in_cube & ~acc)
+    # neural stage: same arithmetic as contains(which=2, tf32)
+    nn = stack.contains(0, pts, which=2, mode=ops.MLP_TF32).cpu().numpy()
+    assert np.array_equal(code == 4, acc & nn)
+    assert np.array_equal(code == 2, acc & ~nn)
+    sel = code == 4
+    ref_ll = like(p[sel])
+    assert np.all(np.isnan(log_l[~sel]))
+    if sel.any():
+        assert np.max(np.abs(log_l[sel] - ref_ll) /
+                      np.maximum(1, np.abs(ref_ll))) < 1e-12
+    cnt = out['counters'].cpu().numpy()
+    lse = out['lse'].cpu().numpy()
+    assert cnt[ops.CNT_RAW] == n
+    for c in range(4):
+        assert cnt[1 + c] == np.sum(code == c)
+    assert cnt[ops.CNT_IN_SHELL] == np.sum(sel)
+    assert cnt[ops.CNT_UPDATE] == np.sum(log_l[sel] >= -5.0)
+    m, s1, s2 = orc.lse_triple(log_l[sel])
+    assert lse[0] == m
+    if sel.any():
+        assert abs(lse[1] / s1 - 1) < 1e-12 and abs(lse[2] / s2 - 1) < 1e-12
+    return cnt
+
+
+def test_fused_cycle_single_ellipsoid(golden):
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    for n in (1, 200, 1 << 15):
+        _fused_vs_staged(spec, n, likelihoods.Gaussian(30), seed=n)
+
+
+def test_fused_cycle_overlapping_ellipsoids(golden):
+    # K = 2 overlapping ellipsoids, the neural bound shares mixture 0's
+    import copy
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden('nautilus_d4'))
+    second = copy.deepcopy(spec['mixtures'][0])
+    second['ell']['c'] = second['ell']['c'] + 0.15
+    spec['mixtures'].append(second)
+    spec['log_v_all'] = np.repeat(spec['log_v_all'], 2)
+    cnt = _fused_vs_staged(spec, 1 << 15, likelihoods.Gaussian(4, sigma=0.3),
+                           seed=3)
+    assert cnt[ops.CNT_OVERLAP_REJECT] > 0 and cnt[ops.CNT_CUBE_REJECT] > 0
+    # and with the neural ellipsoid different from every mixture
+    spec['neural'][0]['ell']['c'] = spec['neural'][0]['ell']['c'] + 1e-3
+    _fused_vs_staged(spec, 1 << 14, likelihoods.Gaussian(4, sigma=0.3), seed=4)
