@@ -374,13 +374,18 @@ def run_gpu(args):
     total_stage = sum(stage_ms.values()) or 1.0
     top = max(stage_ms, key=stage_ms.get)
     evaluated = result['raw'] / world - 0   # ~all proposals reach the MLP
-    if top in ('mlp_predict', 'fused_cycle'):
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(top)
+    if top == 'mlp_predict':
         flops = MLP_FLOPS_PER_POINT * evaluated
         achieved = flops / (stage_ms[top] * 1e-3) / 1e12
         roofline = {
             'kernel': top, 'bound': 'tensor', 'achieved': achieved,
             'peak': peaks['bf16'], 'unit': 'TFLOP/s',
-            'frac': achieved / peaks['bf16'], 'traffic': None,
+            'frac': achieved / peaks['bf16'], 'traffic': traffic,
             'peak_source': peaks['source'] + ', dense bf16 burst',
             'flops_per_launch': flops, 'ms_per_launch': stage_ms[top],
             'arith': args.mlp}
@@ -390,7 +395,7 @@ def run_gpu(args):
         roofline = {
             'kernel': top, 'bound': 'hbm', 'achieved': achieved,
             'peak': peaks['hbm'], 'unit': 'GB/s',
-            'frac': achieved / peaks['hbm'], 'traffic': None,
+            'frac': achieved / peaks['hbm'], 'traffic': traffic,
             'peak_source': peaks['source'],
             'bytes_per_launch': nbytes, 'ms_per_launch': stage_ms[top]}
     roofline['share_of_step'] = stage_ms[top] / total_stage
@@ -447,11 +452,11 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1 << 20)
-    ap.add_argument('--mlp', default='f64', choices=['f64', 'tf32'])
+    ap.add_argument('--mlp', default='tf32', choices=['f64', 'tf32'])
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
