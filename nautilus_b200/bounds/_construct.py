@@ -18,7 +18,13 @@ published descriptions, not from the reference's code:
   nautilus/bounds/union.py:17), minimised by golden-section search.
 """
 
+import hashlib
+from collections import OrderedDict
+
 import numpy as np
+
+_MVEE_CACHE = OrderedDict()      # the same live set is bounded several times
+_MVEE_CACHE_SIZE = 32            # per new bound (nautilus.py:100-119)
 
 
 def _khachiyan(points, max_updates, tol):
@@ -58,8 +64,14 @@ def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
     equivariant, so the iteration runs on points whitened by their sample
     covariance, which keeps it stable for extremely elongated clouds.
     """
-    points = np.asarray(points, dtype=float)
+    points = np.ascontiguousarray(points, dtype=float)
     n, d = points.shape
+    key = (points.shape, max_updates, tol,
+           hashlib.blake2b(points.tobytes(), digest_size=16).digest())
+    if key in _MVEE_CACHE:
+        _MVEE_CACHE.move_to_end(key)
+        c, a, a_inv = _MVEE_CACHE[key]
+        return c.copy(), a.copy(), a_inv.copy()
     mu = np.mean(points, axis=0)
     cov = np.atleast_2d(np.cov(points, rowvar=False))
     cov = cov + np.eye(d) * 1e-14 * max(np.trace(cov) / d, 1e-300)
@@ -73,7 +85,11 @@ def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
     a = np.linalg.inv(a_inv)
     a = 0.5 * (a + a.T)
     scale = np.max(np.einsum('ij,jk,ik->i', diff, a, diff))
-    return np.atleast_1d(c), a / scale, a_inv * scale
+    result = (np.atleast_1d(c), a / scale, a_inv * scale)
+    _MVEE_CACHE[key] = result
+    if len(_MVEE_CACHE) > _MVEE_CACHE_SIZE:
+        _MVEE_CACHE.popitem(last=False)
+    return tuple(r.copy() for r in result)
 
 
 # --------------------------------------------------------------------------

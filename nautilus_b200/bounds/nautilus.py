@@ -26,7 +26,10 @@ class NautilusBound(_DeviceBound):
     def compute(cls, points, log_l, log_l_min, log_v_target,
                 enlarge_per_dim=1.1, n_points_min=None, split_threshold=100,
                 periodic=None, n_networks=4, neural_network_kwargs={},
-                pool=None, rng=None):
+                pool=None, rng=None, mode=None):
+        """``mode`` selects the emulator arithmetic of this bound
+        (``ops.MLP_F64`` parity mode / ``ops.MLP_TF32`` tensor cores); the
+        same arithmetic is used for sampling and for ``contains``."""
         if periodic is not None:
             raise NotImplementedError(
                 'periodic parameters (PhaseShift) are outside the scope of '
@@ -36,6 +39,7 @@ class NautilusBound(_DeviceBound):
         bound = cls()
         bound.n_dim = points.shape[1]
         bound.shift = None
+        bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
         bound.rng = np.random.default_rng() if rng is None else rng
         live = points[log_l >= log_l_min]
 
@@ -52,7 +56,7 @@ class NautilusBound(_DeviceBound):
                 points[member], log_l[member], log_l_min,
                 enlarge_per_dim=enlarge_per_dim, n_networks=n_networks,
                 neural_network_kwargs=neural_network_kwargs, pool=pool,
-                rng=rng))
+                rng=rng, mode=bound.mode))
 
         # outer sampling bound, refined until close enough to the target volume
         bound.outer_bound = Union.compute(
@@ -85,7 +89,7 @@ class NautilusBound(_DeviceBound):
     def contains(self, points, mode=None):
         """outer union AND any neural bound (nautilus.py:146-169)."""
         t, restore = to_device(points, self.n_dim)
-        mode = NeuralNetworkEmulator.mode if mode is None else mode
+        mode = self.mode if mode is None else mode
         return restore(self._device_stack().contains(0, t, mode=mode))
 
     # -- sampling ------------------------------------------------------------
@@ -94,7 +98,7 @@ class NautilusBound(_DeviceBound):
         all four integer counters exactly as the reference's nested loops do
         in aggregate (union.py:322-323, nautilus.py:221-222) and returns the
         accepted points (CUDA)."""
-        mode = NeuralNetworkEmulator.mode if mode is None else mode
+        mode = self.mode if mode is None else mode
         stack = self._device_stack()
         offset = self.stream.take(n_raw)
         out = stack.cycle(0, int(n_raw), seed=self.stream.seed, offset=offset,

@@ -17,8 +17,10 @@ class NeuralBound(_DeviceBound):
 
     @classmethod
     def compute(cls, points, log_l, log_l_min, enlarge_per_dim=1.1,
-                n_networks=4, neural_network_kwargs={}, pool=None, rng=None):
+                n_networks=4, neural_network_kwargs={}, pool=None, rng=None,
+                mode=None):
         bound = cls()
+        bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
         points = np.asarray(points, dtype=float)
         log_l = np.asarray(log_l, dtype=float)
         bound.n_dim = points.shape[1]
@@ -50,6 +52,7 @@ class NeuralBound(_DeviceBound):
             seed=int(rng.integers(0, 2**63 - 1)))
         # threshold: cubic fit of predicted vs true score, evaluated at the
         # lowest live score (neural.py:93-95)
+        bound.emulator.mode = bound.mode
         predicted = bound.emulator.predict(whitened)
         bound.score_predict_min = float(np.polyval(
             np.polyfit(score, predicted, 3), np.amin(score[live])))
@@ -75,6 +78,7 @@ class NeuralBound(_DeviceBound):
         """Inside the ellipsoid and score above the threshold
         (neural.py:99-126)."""
         t, restore = to_device(points, self.n_dim)
-        mode = NeuralNetworkEmulator.mode if mode is None else mode
+        mode = getattr(self, 'mode', NeuralNetworkEmulator.mode) \
+            if mode is None else mode
         return restore(self._device_stack().contains(0, t, which=2,
                                                      mode=mode))

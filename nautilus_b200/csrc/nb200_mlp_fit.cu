@@ -22,21 +22,31 @@
 // are deliberate: Philox instead of MT19937 for init and shuffling, and the
 // per-epoch permutation is an affine map i -> (a*i + b) mod M with gcd(a, M)
 // = 1 instead of a Fisher-Yates shuffle.
+#include <cooperative_groups.h>
+
 #include "nb200_common.cuh"
 #include "nb200_rng.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace nb200 {
 
 constexpr int FIT_THREADS = 512;
 constexpr int FIT_ROWS = 64;        // rows of a minibatch resident at once
 constexpr int FIT_MAX_LAYERS = 6;   // weight matrices
+// Every network is trained by a thread-block CLUSTER of FIT_CLUSTER CTAs: the
+// minibatch is split over the CTAs (data parallel), each CTA holds the full
+// parameter set, and the minibatch gradient is all-reduced through
+// distributed shared memory, in rank order, so that all CTAs apply the same
+// Adam step to bit-identical weights.
+constexpr int FIT_CLUSTER = 4;
 
 struct FitArgs {
   int n_lay, d, batch, max_epochs, patience;
   int sizes[FIT_MAX_LAYERS + 1];
   int w_off[FIT_MAX_LAYERS], b_off[FIT_MAX_LAYERS];   // float offsets in W
   int a_off[FIT_MAX_LAYERS + 1], a_stride[FIT_MAX_LAYERS + 1];
-  int n_params, delta_off, delta_stride, smem_floats;
+  int n_params, delta_off, delta_stride, smem_floats, gsum_off;
   float lr, beta1, beta2, eps, tol;
   unsigned long long seed;
   long long m;
@@ -47,7 +57,8 @@ __device__ __forceinline__ long long gcd_ll(long long a, long long b) {
   return a;
 }
 
-__global__ void __launch_bounds__(FIT_THREADS, 1)
+__global__ void __cluster_dims__(FIT_CLUSTER, 1, 1)
+__launch_bounds__(FIT_THREADS, 1)
 k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           const float* __restrict__ y, float* __restrict__ moments,
           double* __restrict__ weights_out, int* __restrict__ n_iter_out,
@@ -58,14 +69,18 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   float* act = G + A.n_params;         // activations a_0..a_L of one chunk
   float* dl0 = fs + A.delta_off;       // delta ping-pong
   float* dl1 = dl0 + FIT_ROWS * A.delta_stride;
+  float* Gsum = fs + A.gsum_off;       // all-reduced gradient
   __shared__ float red[FIT_THREADS / 32];
   __shared__ float s_loss;
+  __shared__ float s_bsq;              // this CTA's share of sum (y - t)^2
 
-  const int net = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int net = blockIdx.x / FIT_CLUSTER;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = FIT_THREADS / 32;
   const int P = A.n_params;
-  float* mom_m = moments + (size_t)net * 2 * P;
+  float* mom_m = moments + (size_t)blockIdx.x * 2 * P;
   float* mom_v = mom_m + P;
 
   // ---- Glorot-uniform init (weights and biases), zero moments -----------
@@ -110,9 +125,12 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
     for (int bi = 0; bi < n_batches; ++bi) {
       const long long b_lo = (long long)bi * A.batch;
       const int bn = (int)min((long long)A.batch, M - b_lo);
-      float batch_sq = 0.f;            // sum (y - t)^2 over the minibatch
-      for (int c_lo = 0; c_lo < bn; c_lo += FIT_ROWS) {
-        const int R = min(FIT_ROWS, bn - c_lo);
+      float batch_sq = 0.f;            // sum (y - t)^2 over this CTA's rows
+      // this CTA's slice of the minibatch
+      const int per = (bn + FIT_CLUSTER - 1) / FIT_CLUSTER;
+      const int my_lo = min(bn, crank * per), my_hi = min(bn, my_lo + per);
+      for (int c_lo = my_lo; c_lo < my_hi; c_lo += FIT_ROWS) {
+        const int R = min(FIT_ROWS, my_hi - c_lo);
         // ---- gather chunk rows: a_0 = x[perm], targets in dl1 tail --------
         float* a0 = act + A.a_off[0];
         for (int e = tid; e < R * A.d; e += FIT_THREADS) {
@@ -245,13 +263,31 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           float* tmp = dcur; dcur = dnext; dnext = tmp;
         }
       }
+      // ---- all-reduce of the gradient and the loss over the cluster -----------
+      if (tid == 0) s_bsq = batch_sq;
+      cluster.sync();
+      for (int e = tid; e < P; e += FIT_THREADS) {
+        float g = 0.f;
+#pragma unroll
+        for (int q = 0; q < FIT_CLUSTER; ++q)
+          g += cluster.map_shared_rank(G, q)[e];
+        Gsum[e] = g;
+      }
+      {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < FIT_CLUSTER; ++q)
+          t += *cluster.map_shared_rank(&s_bsq, q);
+        batch_sq = t;
+      }
+      cluster.sync();      // nobody may touch G / s_bsq before all have read
       // ---- Adam step on the whole minibatch gradient --------------------------
       t_adam += 1;
       const float b1t = powf(A.beta1, (float)t_adam);
       const float b2t = powf(A.beta2, (float)t_adam);
       const float lr_t = A.lr * sqrtf(1.f - b2t) / (1.f - b1t);
       for (int e = tid; e < P; e += FIT_THREADS) {
-        const float gq = G[e];
+        const float gq = Gsum[e];
         const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
         const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
         mom_m[e] = mq;
@@ -270,8 +306,9 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   }
   // ---- export -------------------------------------------------------------------
   double* wo = weights_out + (size_t)net * P;
-  for (int e = tid; e < P; e += FIT_THREADS) wo[e] = (double)W[e];
-  if (tid == 0) {
+  if (crank == 0)
+    for (int e = tid; e < P; e += FIT_THREADS) wo[e] = (double)W[e];
+  if (tid == 0 && crank == 0) {
     n_iter_out[net] = epoch;
     loss_out[net] = (double)last_loss;
   }
@@ -291,8 +328,8 @@ extern "C" {
 
 size_t nb200_mlp_fit_workspace_bytes(int64_t m, int d, int n_params,
                                      int n_net) {
-  return (size_t)m * d * 4 + (size_t)m * 4 + (size_t)n_net * 2 * n_params * 4 +
-         1024;
+  return (size_t)m * d * 4 + (size_t)m * 4 +
+         (size_t)n_net * FIT_CLUSTER * 2 * n_params * 4 + 1024;
 }
 
 int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
@@ -332,11 +369,12 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
   }
   A.delta_stride = maxw | 1;
   A.delta_off = 2 * A.n_params + aoff;
-  A.smem_floats = A.delta_off + 2 * FIT_ROWS * A.delta_stride;
+  A.gsum_off = A.delta_off + 2 * FIT_ROWS * A.delta_stride;
+  A.smem_floats = A.gsum_off + A.n_params;
   const size_t smem = (size_t)A.smem_floats * 4;
   NB_CHECK(smem <= 220 * 1024,
-           "network too large for the on-chip trainer (weights + gradient + "
-           "one 64-row chunk of activations must fit 220 KB)");
+           "network too large for the on-chip trainer (weights + 2 gradient "
+           "buffers + one 64-row chunk of activations must fit 220 KB)");
   NB_CHECK(workspace_bytes >=
                nb200_mlp_fit_workspace_bytes(m, d, A.n_params, n_net),
            "workspace too small");
@@ -351,7 +389,7 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
   NB_CUDA(cudaFuncSetAttribute(k_mlp_fit,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  k_mlp_fit<<<n_net, FIT_THREADS, smem, st>>>(A, x32, y32, moments,
+  k_mlp_fit<<<n_net * FIT_CLUSTER, FIT_THREADS, smem, st>>>(A, x32, y32, moments,
                                               weights_out_d, n_iter_out_d,
                                               loss_out_d);
   NB_LAUNCH_OK();

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .bounds._device import default_device, to_device
+from ._device import default_device, to_device
 
 DEFAULT_KWARGS = dict(hidden_layer_sizes=(100, 50, 20), alpha=0,
                       learning_rate_init=1e-2, max_iter=10000, tol=0,

@@ -28,7 +28,7 @@ from scipy.special import logsumexp
 
 from . import ops
 from .bounds import NautilusBound, UnitCube
-from .bounds._device import default_device
+from ._device import default_device
 from .likelihoods import DeviceLikelihood
 from .pool import GpuPool, NautilusPool, likelihood_worker
 
@@ -556,7 +556,7 @@ class Sampler:
                     split_threshold=self.split_threshold, periodic=None,
                     n_networks=self.n_networks,
                     neural_network_kwargs=self.neural_network_kwargs,
-                    pool=None, rng=self.rng)
+                    pool=None, rng=self.rng, mode=self.mlp_mode)
                 cand.sample(1000, return_points=False)
                 if cand.log_v < self.bounds[-1].log_v:
                     new_bound = cand

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--keep-exploration', action='store_true')
     ap.add_argument('--timeout', type=float, default=1500)
+    ap.add_argument('--profile', action='store_true')
     args = ap.parse_args()
     if args.config == 1:
         like, n_live = likelihoods.Gaussian(3, mu=[0.4, 0.5, 0.6],
@@ -40,9 +41,17 @@ def main():
                       seed=args.seed, n_batch=args.n_batch,
                       emulator_arith=args.arith)
     t0 = time.time()
+    if args.profile:
+        import cProfile
+        import pstats
+        prof = cProfile.Profile()
+        prof.enable()
     ok = sampler.run(n_eff=args.n_eff, timeout=args.timeout,
                      discard_exploration=not args.keep_exploration)
     wall = time.time() - t0
+    if args.profile:
+        prof.disable()
+        pstats.Stats(prof).sort_stats('cumulative').print_stats(28)
     raw = sum(b.outer_bound.n_sample for b in sampler.bounds[1:])
     print(json.dumps({
         'config': args.config, 'success': bool(ok), 'wall_s': wall,
