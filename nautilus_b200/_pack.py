@@ -139,7 +139,8 @@ TC_MAGIC = 0x7F32
 TC_MAX_HID = 4
 TC_HDR_WORDS = 32
 TC_SMEM_LIMIT = 220 * 1024     # bytes of resident weights per CTA
-TC_COLS = 256                  # TMEM columns per tile group
+TC_COLS = 256                  # TMEM columns per tile group (2 groups/CTA)
+TC_COLS_SINGLE = 512           # ... or all of TMEM for a single group
 
 
 def _round_up(v, m):
@@ -191,8 +192,9 @@ def pack_tc(emu, score_predict_min):
     for l in range(n_hid):
         d_col.append(col)
         col += _round_up(np_[l], 32)
-    if col > TC_COLS:
+    if col > TC_COLS_SINGLE:
         return None
+    n_groups = 2 if col <= TC_COLS else 1
     w_off, b_off, off = [], [], 0
     for l in range(n_hid):
         w_off.append(off)
@@ -225,7 +227,8 @@ def pack_tc(emu, score_predict_min):
         blob[base + b_out_off] = np.float32(intercepts[n][-1][0])
     thr = np.array([float(score_predict_min) - 1e-9]).view(np.int32)
     pad4 = lambda v: list(v) + [0] * (TC_MAX_HID - len(v))  # noqa: E731
-    hdr = [TC_MAGIC, n_net, n_hid, d, k0p, net_stride, total, a0_col]
+    hdr = [TC_MAGIC | (n_groups << 16), n_net, n_hid, d, k0p, net_stride,
+           total, a0_col]
     hdr += pad4(np_) + pad4(kp) + pad4(w_off) + pad4(b_off) + pad4(d_col)
     hdr += [w_out_off, b_out_off, int(thr[0]), int(thr[1])]
     assert len(hdr) == TC_HDR_WORDS

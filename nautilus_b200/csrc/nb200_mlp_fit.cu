@@ -32,7 +32,7 @@ namespace cg = cooperative_groups;
 namespace nb200 {
 
 constexpr int FIT_THREADS = 512;
-constexpr int FIT_ROWS = 64;        // rows of a minibatch resident at once
+constexpr int FIT_ROWS_MAX = 64;    // rows of a minibatch resident at once
 constexpr int FIT_MAX_LAYERS = 6;   // weight matrices
 // Every network is trained by a thread-block CLUSTER of FIT_CLUSTER CTAs: the
 // minibatch is split over the CTAs (data parallel), each CTA holds the full
@@ -47,6 +47,8 @@ struct FitArgs {
   int w_off[FIT_MAX_LAYERS], b_off[FIT_MAX_LAYERS];   // float offsets in W
   int a_off[FIT_MAX_LAYERS + 1], a_stride[FIT_MAX_LAYERS + 1];
   int n_params, delta_off, delta_stride, smem_floats, gsum_off;
+  int rows;      // resident chunk (64, 32 or 16: what fits shared memory)
+  int p_quarter; // ceil(n_params / FIT_CLUSTER)
   float lr, beta1, beta2, eps, tol;
   unsigned long long seed;
   long long m;
@@ -68,8 +70,8 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   float* G = fs + A.n_params;          // gradient of the current minibatch
   float* act = G + A.n_params;         // activations a_0..a_L of one chunk
   float* dl0 = fs + A.delta_off;       // delta ping-pong
-  float* dl1 = dl0 + FIT_ROWS * A.delta_stride;
-  float* Gsum = fs + A.gsum_off;       // all-reduced gradient
+  float* dl1 = dl0 + A.rows * A.delta_stride;
+  float* Gq = fs + A.gsum_off;         // this CTA's reduced quarter of G
   __shared__ float red[FIT_THREADS / 32];
   __shared__ float s_loss;
   __shared__ float s_bsq;              // this CTA's share of sum (y - t)^2
@@ -129,8 +131,8 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       // this CTA's slice of the minibatch
       const int per = (bn + FIT_CLUSTER - 1) / FIT_CLUSTER;
       const int my_lo = min(bn, crank * per), my_hi = min(bn, my_lo + per);
-      for (int c_lo = my_lo; c_lo < my_hi; c_lo += FIT_ROWS) {
-        const int R = min(FIT_ROWS, my_hi - c_lo);
+      for (int c_lo = my_lo; c_lo < my_hi; c_lo += A.rows) {
+        const int R = min(A.rows, my_hi - c_lo);
         // ---- gather chunk rows: a_0 = x[perm], targets in dl1 tail --------
         float* a0 = act + A.a_off[0];
         for (int e = tid; e < R * A.d; e += FIT_THREADS) {
@@ -266,28 +268,34 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       // ---- all-reduce of the gradient and the loss over the cluster -----------
       if (tid == 0) s_bsq = batch_sq;
       cluster.sync();
-      for (int e = tid; e < P; e += FIT_THREADS) {
-        float g = 0.f;
-#pragma unroll
-        for (int q = 0; q < FIT_CLUSTER; ++q)
-          g += cluster.map_shared_rank(G, q)[e];
-        Gsum[e] = g;
-      }
+      // reduce-scatter: this CTA sums ITS quarter of the gradient over all
+      // ranks (rank order => identical on every CTA) ...
       {
+        const int lo = crank * A.p_quarter;
+        const int hi = min(P, lo + A.p_quarter);
+        for (int e = lo + tid; e < hi; e += FIT_THREADS) {
+          float g = 0.f;
+#pragma unroll
+          for (int q = 0; q < FIT_CLUSTER; ++q)
+            g += cluster.map_shared_rank(G, q)[e];
+          Gq[e - lo] = g;
+        }
         float t = 0.f;
 #pragma unroll
         for (int q = 0; q < FIT_CLUSTER; ++q)
           t += *cluster.map_shared_rank(&s_bsq, q);
         batch_sq = t;
       }
-      cluster.sync();      // nobody may touch G / s_bsq before all have read
+      cluster.sync();      // ... all-gather happens inside the Adam loop
       // ---- Adam step on the whole minibatch gradient --------------------------
       t_adam += 1;
       const float b1t = powf(A.beta1, (float)t_adam);
       const float b2t = powf(A.beta2, (float)t_adam);
       const float lr_t = A.lr * sqrtf(1.f - b2t) / (1.f - b1t);
       for (int e = tid; e < P; e += FIT_THREADS) {
-        const float gq = Gsum[e];
+        const int owner = e / A.p_quarter;
+        const float gq =
+            cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
         const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
         const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
         mom_m[e] = mq;
@@ -305,6 +313,9 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
     if (no_improve > A.patience) { epoch += 1; break; }
   }
   // ---- export -------------------------------------------------------------------
+  // peers may still be reading this CTA's Gq (distributed shared memory)
+  // in their last Adam step: nobody leaves before everybody is done
+  cluster.sync();
   double* wo = weights_out + (size_t)net * P;
   if (crank == 0)
     for (int e = tid; e < P; e += FIT_THREADS) wo[e] = (double)W[e];
@@ -361,20 +372,26 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
     A.b_off[l] = off; off += A.sizes[l + 1];
   }
   A.n_params = off;
-  int aoff = 0;
-  for (int l = 0; l <= n_lay; ++l) {
-    A.a_stride[l] = A.sizes[l] | 1;
-    A.a_off[l] = aoff;
-    aoff += FIT_ROWS * A.a_stride[l];
-  }
   A.delta_stride = maxw | 1;
-  A.delta_off = 2 * A.n_params + aoff;
-  A.gsum_off = A.delta_off + 2 * FIT_ROWS * A.delta_stride;
-  A.smem_floats = A.gsum_off + A.n_params;
+  A.p_quarter = (A.n_params + FIT_CLUSTER - 1) / FIT_CLUSTER;
+  // largest resident chunk that fits: weights + gradient + a quarter-size
+  // reduction buffer + activations and two delta buffers of `rows` rows
+  for (A.rows = FIT_ROWS_MAX; A.rows >= 8; A.rows >>= 1) {
+    int aoff = 0;
+    for (int l = 0; l <= n_lay; ++l) {
+      A.a_stride[l] = A.sizes[l] | 1;
+      A.a_off[l] = aoff;
+      aoff += A.rows * A.a_stride[l];
+    }
+    A.delta_off = 2 * A.n_params + aoff;
+    A.gsum_off = A.delta_off + 2 * A.rows * A.delta_stride;
+    A.smem_floats = A.gsum_off + A.p_quarter;
+    if ((size_t)A.smem_floats * 4 <= 220 * 1024) break;
+  }
   const size_t smem = (size_t)A.smem_floats * 4;
   NB_CHECK(smem <= 220 * 1024,
-           "network too large for the on-chip trainer (weights + 2 gradient "
-           "buffers + one 64-row chunk of activations must fit 220 KB)");
+           "network too large for the on-chip trainer (weights + gradient + "
+           "an 8-row chunk of activations must fit 220 KB)");
   NB_CHECK(workspace_bytes >=
                nb200_mlp_fit_workspace_bytes(m, d, A.n_params, n_net),
            "workspace too small");

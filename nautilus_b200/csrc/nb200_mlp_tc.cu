@@ -34,7 +34,7 @@ constexpr int TC_GROUP_THREADS = 256;   // two threads per row of a tile
 constexpr int TC_COLS_PER_GROUP = 256;
 
 struct TcHeader {            // int32[32] in the meta tail (_pack.py:pack_tc)
-  int magic, n_net, n_hid, d;
+  int magic, n_net, n_hid, d;   // magic = 0x7F32 | (tile groups per CTA << 16)
   int k0p, net_stride, total_floats, a0_col;
   int np[TC_MAX_HID];        // padded fan_out of hidden layer l (mult. of 16)
   int kp[TC_MAX_HID];        // padded fan_in  of hidden layer l (mult. of 8)
@@ -190,6 +190,9 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
                                      // handles (warps w and w+4 share lanes)
 
   const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
+  // architectures that need more than 256 TMEM columns run ONE tile group per
+  // CTA (group 1 idles); otherwise two groups interleave
+  const int n_groups = h.magic >> 16;
   if (tid == 0) {
     mbar_init(&wbar, 1);
     for (int q = 0; q < TC_GROUPS * 3; ++q) mbar_init(&mbar[q], 1);
@@ -231,7 +234,9 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
 
   uint32_t phA = 0, phB = 0, phC = 0;
   const int64_t n_tiles = (n + 127) / 128;
-  const int64_t tile_step = (int64_t)gridDim.x * TC_GROUPS;
+  const int64_t tile_step = (int64_t)gridDim.x * n_groups;
+  const int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g
+                                     : n_tiles;
   // the input row of the NEXT tile is fetched into registers while the
   // current tile runs (k0p <= 32: 8 x 16 B per thread)
   const bool prefetch = h.k0p <= 32;
@@ -248,9 +253,8 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     }
   };
   bool next_active = false;
-  if (prefetch) fetch((int64_t)blockIdx.x * TC_GROUPS + g, next_active);
-  for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + g; tile < n_tiles;
-       tile += tile_step) {
+  if (prefetch) fetch(tile0, next_active);
+  for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
     const int64_t row = tile * 128 + r;
     bool active;
 
@@ -479,7 +483,8 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t n_tiles = (n + 127) / 128;
-  int64_t grid = (n_tiles + TC_GROUPS - 1) / TC_GROUPS;
+  const int n_groups = h.magic >> 16;
+  int64_t grid = (n_tiles + n_groups - 1) / n_groups;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
   if (tail.partial) NB_CHECK(grid <= STAT_MAX_BLOCKS, "too many partials");
@@ -497,7 +502,9 @@ static int tc_header(const int32_t* meta_h, int bound, int j, TcHeader* h) {
            "this emulator has no tensor-core blob (architecture outside the "
            "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
   memcpy(h, rec.r + nb[11], sizeof(*h));
-  NB_CHECK(h->magic == 0x7F32, "corrupt tensor-core blob header");
+  NB_CHECK((h->magic & 0xFFFF) == 0x7F32 && (h->magic >> 16) >= 1 &&
+               (h->magic >> 16) <= TC_GROUPS,
+           "corrupt tensor-core blob header");
   return 0;
 }
 

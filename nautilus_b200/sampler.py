@@ -43,7 +43,7 @@ class Sampler:
                  likelihood_args=[], likelihood_kwargs={}, n_batch=None,
                  n_like_new_bound=None, vectorized=False, pass_dict=None,
                  pool=None, seed=None, blobs_dtype=None, filepath=None,
-                 resume=True, emulator_arith='f64'):
+                 resume=True, emulator_arith='auto'):
         if filepath is not None:
             raise NotImplementedError(
                 'HDF5 checkpointing is outside the scope of nautilus_b200.')
@@ -85,8 +85,24 @@ class Sampler:
         self.neural_network_kwargs = neural_network_kwargs
         self.vectorized = vectorized
         self.pass_dict = pass_dict
-        self.mlp_mode = {'f64': ops.MLP_F64, 'tf32': ops.MLP_TF32}[
-            emulator_arith]
+        # 'auto': tensor cores (tf32) whenever the emulator architecture fits
+        # the tcgen05 kernel, fp64 otherwise; 'f64' is the bit-parity mode
+        self.emulator_arith = emulator_arith
+        self.mlp_mode = {'f64': ops.MLP_F64, 'tf32': ops.MLP_TF32,
+                         'auto': ops.MLP_F64}[emulator_arith]
+        if emulator_arith == 'auto':
+            from ._pack import pack_tc
+            hidden = tuple(np.atleast_1d(neural_network_kwargs.get(
+                'hidden_layer_sizes', (100, 50, 20))))
+            sizes = (self.n_dim, ) + tuple(int(h) for h in hidden) + (1, )
+            probe = dict(
+                coefs=[[np.zeros((a, b)) for a, b in zip(sizes[:-1],
+                                                         sizes[1:])]],
+                intercepts=[[np.zeros(b) for b in sizes[1:]]])
+            probe['coefs'] = probe['coefs'] * max(n_networks, 1)
+            probe['intercepts'] = probe['intercepts'] * max(n_networks, 1)
+            if n_networks > 0 and pack_tc(probe, 0.0) is not None:
+                self.mlp_mode = ops.MLP_TF32
 
         # pool = (likelihood pool, sampling pool); an int > 1 in the first
         # slot starts worker processes for a host likelihood

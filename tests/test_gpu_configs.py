@@ -1,0 +1,133 @@
+"""The BASELINE.json configurations beyond config 2, at sizes that run in
+seconds: multi-modal targets (multi-ellipsoid union, several neural bounds),
+a wider input that needs the single-tile-group mode of the tensor-core kernel,
+and a 100-D correlated Gaussian on a fixed bound (fp64 emulator path)."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from nautilus_b200 import Sampler, bounds, likelihoods, ops  # noqa: E402
+from nautilus_b200._pack import pack_stack  # noqa: E402
+from oracle import nautilus_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _ball_points(rng, n, d, radius, centre=0.5):
+    z = rng.normal(size=(n, d))
+    z /= np.linalg.norm(z, axis=1)[:, None]
+    return centre + radius * z * rng.random((n, 1))**(1.0 / d)
+
+
+def test_config4_like_four_modes():
+    # 4 well separated Gaussians in 6-D: the sampler must find 4 ellipsoids /
+    # 4 neural bounds and integrate to log Z = 0
+    d = 6
+    mus = np.full((4, d), 0.5)
+    mus[:, 0] = [0.25, 0.25, 0.75, 0.75]
+    mus[:, 1] = [0.25, 0.75, 0.25, 0.75]
+    like = likelihoods.GaussianMixture(mus, sigma=0.03)
+    sampler = Sampler(lambda x: x, like, n_dim=d, n_live=1500, seed=0,
+                      n_batch=500)
+    assert sampler.run(n_eff=5000, discard_exploration=True)
+    last = sampler.bounds[-1]
+    # the live set splits into 4 non-overlapping ellipsoids -> 4 neural
+    # bounds x 4 networks (nautilus.py:105-114); the outer sampling union is
+    # only refined while its volume is far above the target (:123-126)
+    assert len(last.neural_bounds) == 4 and last.n_net == 16, (
+        len(last.neural_bounds), last.n_net, last.n_ell)
+    assert abs(sampler.log_z - like.log_z_true) < 0.1, sampler.log_z
+    pts, log_w, _ = sampler.posterior()
+    w = np.exp(log_w)
+    # each mode carries a quarter of the posterior mass
+    for mu in mus:
+        near = np.linalg.norm(pts[:, :2] - mu[:2], axis=1) < 0.2
+        assert abs(np.sum(w[near]) - 0.25) < 0.05
+
+
+def test_wide_input_single_group_mode():
+    # d = 36 needs more than 256 TMEM columns per tile -> one tile group per
+    # CTA; scores must still match the fp64 path and the fused cycle must be
+    # consistent with contains()
+    d = 36
+    rng = np.random.default_rng(0)
+    pts = _ball_points(rng, 5000, d, 0.4)
+    log_l = -0.5 * np.sum((pts - 0.5)**2, axis=1) / 0.1**2
+    log_l_min = np.sort(log_l)[-2000]
+    nbound = bounds.NautilusBound.compute(
+        pts, log_l, log_l_min, np.log(0.4) * d, n_networks=4,
+        rng=np.random.default_rng(1), mode=ops.MLP_TF32)
+    spec = nbound.spec()
+    meta, _ = pack_stack([spec])
+    rec = meta[meta[1]:]
+    hdr = rec[rec[rec[8] + 11]:]
+    assert hdr[0] >> 16 == 1                       # single tile group
+    stack = ops.DeviceStack([spec])
+    raw, _, _ = stack.propose(0, 20000, seed=3)
+    t = bounds.Ellipsoid.from_matrices(
+        spec['neural'][0]['ell']['c'], np.eye(d), np.eye(d))  # placeholder
+    del t
+    whitened = torch.from_numpy(orc.ell_transform(
+        spec['neural'][0]['ell'], raw.cpu().numpy())).cuda()
+    p64 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_F64).cpu().numpy()
+    p32 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_TF32).cpu().numpy()
+    assert np.max(np.abs(p64 - p32)) < 5e-3
+    like = likelihoods.Gaussian(d)
+    out = stack.cycle(0, 1 << 15, seed=5, like_id=like.like_id,
+                      like_params=like.device_params('cuda'),
+                      mode=ops.MLP_TF32)
+    keep, _, n_keep = stack.compact(out['points'], out['log_l'], out['code'])
+    n_keep = int(n_keep.item())
+    assert n_keep > 0
+    assert bool(stack.contains(0, keep[:n_keep].contiguous(),
+                               mode=ops.MLP_TF32).all())
+
+
+def test_config5_like_fixed_bound_100d():
+    # 100-D equicorrelated Gaussian, fixed bound built from seeded points; the
+    # fp64 cycle must agree with the oracle bit-for-bit at d = 100
+    d = 100
+    like = likelihoods.EquicorrelatedGaussian(d, sigma=0.05, rho=0.5)
+    rng = np.random.default_rng(0)
+    cov = like.sigma**2 * ((1 - like.rho) * np.eye(d) + like.rho)
+    pts = 0.5 + rng.multivariate_normal(np.zeros(d), cov, size=2500) * 1.2
+    pts = pts[np.all((pts > 0) & (pts < 1), axis=1)]
+    log_l = like(pts)
+    log_l_min = np.sort(log_l)[-800]
+    nbound = bounds.NautilusBound.compute(
+        pts, log_l, log_l_min, -200.0, n_networks=2,
+        rng=np.random.default_rng(1))
+    spec = nbound.spec()
+    stack = ops.DeviceStack([spec])
+    # four default networks at d = 100 exceed the resident-weight envelope of
+    # the tensor-core kernel: no blob, and asking for tf32 fails loudly
+    from nautilus_b200._pack import pack_tc
+    emu2 = spec['neural'][0]['emulator']
+    emu4 = dict(emu2, coefs=emu2['coefs'] * 2, intercepts=emu2['intercepts'] * 2)
+    assert pack_tc(emu4, 0.5) is None
+    spec4 = dict(spec, neural=[dict(spec['neural'][0], emulator=emu4)])
+    with pytest.raises(RuntimeError):
+        ops.DeviceStack([spec4]).cycle(0, 256, mode=ops.MLP_TF32)
+    # two networks fit (one tile group, staged fp64 front end): tf32 scores
+    # track the fp64 ones
+    raw, _, _ = stack.propose(0, 4096, seed=9)
+    whitened = torch.from_numpy(orc.ell_transform(
+        spec['neural'][0]['ell'], raw.cpu().numpy())).cuda()
+    p64 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_F64).cpu().numpy()
+    p32 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_TF32).cpu().numpy()
+    assert np.max(np.abs(p64 - p32)) < 5e-3
+    n = 4096
+    out = stack.cycle(0, n, seed=2, like_id=like.like_id,
+                      like_params=like.device_params('cuda'),
+                      log_l_min=float(log_l_min), mode=ops.MLP_F64)
+    p = out['points'].cpu().numpy()
+    code = out['code'].cpu().numpy()
+    _, r, _ = orc.replay_integer_stream(n, 0, 0, 2, spec)
+    ref_code, _, ref_ll = orc.classify(spec, [], p, r, like)
+    assert np.array_equal(code, ref_code)
+    sel = code == ops.CODE_IN_SHELL
+    assert sel.sum() > 0
+    got = out['log_l'].cpu().numpy()[sel]
+    assert np.max(np.abs(got - ref_ll[sel]) / np.abs(ref_ll[sel])) < 1e-12
