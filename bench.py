@@ -19,7 +19,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -153,7 +152,9 @@ def run_reference(args):
 # clocks
 # --------------------------------------------------------------------------
 
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """One `nvidia-smi -lms 50` process for the duration of the timed region
+    (the recipe of B200_PROFILING.md)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
          'clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,'
@@ -161,23 +162,30 @@ class ClockSampler(threading.Thread):
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.proc = None
         self.rows = []
-        self.stop_flag = threading.Event()
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(
-                    ['nvidia-smi', '-i', str(self.gpu),
-                     '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                    capture_output=True, text=True, timeout=5).stdout
-                for ln in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in ln.split(',')])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '50'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for ln in out.strip().splitlines():
+            self.rows.append([c.strip() for c in ln.split(',')])
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -207,7 +215,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nautilus_b200 import likelihoods, ops
-    from nautilus_b200.pool import exchange_stats
+    from nautilus_b200.pool import exchange_stats_async, merge_gathered
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -247,10 +255,10 @@ def run_gpu(args):
                     like_params=like_params, log_l_min=log_l_min, mode=mode,
                     out=out)
         if world > 1:
-            # the one exchange step: per-rank counters + LSE partials, merged
-            # on every rank (update_shell_info needs the global sums)
-            state['merged'] = exchange_stats(out['counters'], out['lse'],
-                                             gathered=gathered, packed=packed)
+            # the one exchange step: per-rank counters + LSE partials; like
+            # the single-GPU results they stay on the device until read
+            exchange_stats_async(out['counters'], out['lse'],
+                                 gathered=gathered, packed=packed)
 
     def barrier():
         if world > 1:
@@ -264,7 +272,7 @@ def run_gpu(args):
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
-        time.sleep(0.25)
+        time.sleep(0.3)
 
     # ---- timed region: K steps, device time, max over ranks ---------------
     launches0 = ops.launch_count()
@@ -283,12 +291,11 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if clocks:
-        clocks.stop_flag.set()
-        clocks.join()
+        clocks.stop()
 
     # result of the last step (also a sanity check on the collective)
     if world > 1:
-        cnt, (m, s1, s2) = state['merged']
+        cnt, (m, s1, s2) = merge_gathered(gathered, ops.N_CNT)
         cnt = cnt.astype(float)
     else:
         cnt = out['counters'].cpu().numpy().astype(float)
@@ -452,7 +459,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1 << 20)

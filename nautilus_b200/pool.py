@@ -106,14 +106,16 @@ def merge_lse(parts):
     return m, s1, s2
 
 
-def exchange_stats(counters, lse, gathered=None, packed=None, group=None):
-    """All-gather every rank's int64 counters and fp64 LSE partials with ONE
-    collective (NCCL on GPUs, gloo in the CPU tests) and merge them.
+def exchange_stats_async(counters, lse, gathered=None, packed=None,
+                         group=None):
+    """Enqueue the one collective of a cycle: all-gather every rank's int64
+    counters and fp64 LSE partials (NCCL on GPUs, gloo in the CPU tests).
 
     counters i64[n_cnt], lse f64[>=3] are tensors on this rank's device.
     Counters (< 2^53) travel as float64 in the same buffer as the partials so
-    that a single collective suffices.  Returns (counters int64 ndarray,
-    (m, s1, s2)); every rank gets the same answer."""
+    that a single collective suffices.  Returns the gathered [world, n_cnt+4]
+    tensor (still on the device, nothing is synchronised); hand it to
+    :func:`merge_gathered` when the numbers are needed on the host."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -128,6 +130,19 @@ def exchange_stats(counters, lse, gathered=None, packed=None, group=None):
         gathered = torch.empty((world, n_cnt + 4), dtype=torch.float64,
                                device=counters.device)
     dist.all_gather_into_tensor(gathered.view(-1), packed, group=group)
+    return gathered
+
+
+def merge_gathered(gathered, n_cnt=8):
+    """(counters int64 ndarray, (m, s1, s2)) from the gathered per-rank rows;
+    every rank gets the same answer (merge in rank order)."""
     g = gathered.cpu().numpy()
     total = g[:, :n_cnt].sum(axis=0).round().astype('int64')
     return total, merge_lse([tuple(r[n_cnt:n_cnt + 3]) for r in g])
+
+
+def exchange_stats(counters, lse, gathered=None, packed=None, group=None):
+    """Blocking form: exchange and merge."""
+    return merge_gathered(exchange_stats_async(
+        counters, lse, gathered=gathered, packed=packed, group=group),
+        n_cnt=counters.numel())
