@@ -42,7 +42,9 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + sources() + ['-lcuda']
+    extra = os.environ.get('NB200_EXTRA_FLAGS', '').split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ['-o', LIB_PATH] + sources() + [
+        '-lcuda']
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

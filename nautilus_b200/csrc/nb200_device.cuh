@@ -195,7 +195,19 @@ __device__ __forceinline__ double loglike_eval(int like_id,
   if (like_id == NB200_LIKE_GAUSSIAN) {
     const double* mu = p + 2;
     double s2 = 0.0;
-    for (int j = 0; j < d; ++j) {
+    // loads are issued eight at a time (x may be a global row), the sum keeps
+    // its left-to-right FMA order
+    int j = 0;
+    for (; j + 8 <= d; j += 8) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = x[j + q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] -= __ldg(mu + j + q);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s2 = fma(v[q], v[q], s2);
+    }
+    for (; j < d; ++j) {
       const double v = x[j] - __ldg(mu + j);
       s2 = fma(v, v, s2);
     }

@@ -58,6 +58,22 @@ struct TcTail {
   int d, like_id;
 };
 
+// Debug timeline (clock64 stamps of the leader of group 0 in CTA 0), read
+// back with nb200_debug_read(); compiled in only with -DNB200_TIMELINE.
+#ifdef NB200_TIMELINE
+__device__ long long g_tl[512];
+__device__ int g_tl_n;
+#define TL_STAMP(tag)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_tl_n < 510) {          \
+      g_tl[g_tl_n++] = (long long)(tag);                                \
+      g_tl[g_tl_n++] = clock64();                                       \
+    }                                                                   \
+  } while (0)
+#else
+#define TL_STAMP(tag) do {} while (0)
+#endif
+
 // ---- PTX wrappers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -223,6 +239,16 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
+  // Warp-uniform copies for the MMA issuer: values that come out of a
+  // shuffle are uniform to the compiler, so the operands of tcgen05.mma live
+  // in uniform registers instead of being moved there one by one (R2UR) --
+  // the timeline showed ~200 cycles per MMA issue before this.
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const bool issuer_warp = (warp_u & 7) == 0;          // first warp of a group
+  const uint32_t tmem_base_u =
+      __shfl_sync(0xffffffffu, tmem_slot, 0) +
+      (uint32_t)((warp_u >> 3) * TC_COLS_PER_GROUP);
+  const uint32_t wsm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   mbar_wait(&wbar, 0);
 
@@ -258,6 +284,20 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     const int64_t row = tile * 128 + r;
     bool active;
 
+    TL_STAMP(1);
+    // the fused tail will need this row's disposition and (if accepted) its
+    // fp64 coordinates ~30k cycles from now: read the byte, and pull the
+    // row's cache lines into L2 while the tensor pipe works
+    int cd_in = NB200_CODE_IN_SHELL;
+    if (tail.partial && !hf && row < n) {
+      cd_in = code[row];
+      if (cd_in == NB200_CODE_IN_SHELL) {
+        const char* rp = (const char*)(tail.points + row * (int64_t)tail.d);
+        const int bytes = tail.d * 8;
+        for (int o = 0; o < bytes; o += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+      }
+    }
     // ---- standardised input row -> TMEM (A operand of layer 0) ----------
     if (prefetch) {
       active = next_active;
@@ -299,22 +339,34 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     // ---- helpers --------------------------------------------------------
     // leader: issue layer l of network `net`, completion arrives on `bar`
     auto issue = [&](int net, int l, uint64_t* bar) {
-      if (r == 0 && hf == 0) {
+      if (issuer_warp) {                 // warp-uniform branch
         tc_fence_after();
-        const float* wnet = wsm + (size_t)net * h.net_stride;
         const int np = h.np[l], kp = h.kp[l];
         const uint32_t a_col = (l == 0) ? (uint32_t)h.a0_col
                                         : (uint32_t)h.d_col[l - 1];
-        const uint32_t w_addr = smem_u32(wnet + h.w_off[l]);
+        const uint32_t w_addr =
+            wsm_u + 4u * (uint32_t)(net * h.net_stride + h.w_off[l]);
         const uint32_t idesc = idesc_tf32(np);
-        for (int s = 0; s < kp / 8; ++s) {
-          mma_tf32_ts(tmem_base + (uint32_t)h.d_col[l],
-                      tmem_base + a_col + (uint32_t)(s * 8),
-                      smem_desc(w_addr + (uint32_t)s * 256u, 128u,
-                                (uint32_t)kp * 32u),
-                      idesc, s > 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base_u + (uint32_t)h.d_col[l];
+        const uint32_t a_tmem = tmem_base_u + a_col;
+        const uint64_t desc0 = smem_desc(w_addr, 128u, (uint32_t)kp * 32u);
+        uint32_t elected = 0;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "elect.sync _|p, 0xffffffff;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(elected));
+        if (elected) {
+          const int ks = kp >> 3;
+          for (int s = 0; s < ks; ++s) {
+            // one K-step = 2 core matrices = 256 B -> +16 in the 16-B units
+            // of the descriptor's start-address field
+            mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(s * 8),
+                        desc0 + (uint64_t)(s * 16), idesc, s > 0 ? 1u : 0u);
+          }
+          mma_commit(bar);
         }
-        mma_commit(bar);
+        __syncwarp();
       }
     };
     // all: ReLU + tf32 rounding of layer l's accumulator, written back in
@@ -369,23 +421,37 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       uint64_t* bA = &mbar[g * 3 + 0];
       uint64_t* bB = &mbar[g * 3 + 1];
       uint64_t* bC = &mbar[g * 3 + 2];
+      TL_STAMP(2);
       issue(0, 0, bA);
+      TL_STAMP(3);
       mbar_wait(bA, phA); phA ^= 1u;
+      TL_STAMP(4);
       epi_hidden(0);
+      TL_STAMP(5);
       issue(0, 1, bB);
       for (int net = 0; net < h.n_net; ++net) {
         const bool more = net + 1 < h.n_net;
+        TL_STAMP(10);
         mbar_wait(bB, phB); phB ^= 1u;       // D1(net) ready, region 0 free
+        TL_STAMP(11);
         if (more) issue(net + 1, 0, bA);
+        TL_STAMP(12);
         epi_hidden(1);
+        TL_STAMP(13);
         issue(net, 2, bC);
+        TL_STAMP(14);
         if (more) {
           mbar_wait(bA, phA); phA ^= 1u;
+          TL_STAMP(15);
           epi_hidden(0);
+          TL_STAMP(16);
         }
         mbar_wait(bC, phC); phC ^= 1u;       // D2(net) ready, region 1 free
+        TL_STAMP(17);
         if (more) issue(net + 1, 1, bB);
+        TL_STAMP(18);
         sum += epi_last(net, 2);
+        TL_STAMP(19);
       }
     } else {
       uint64_t* bA = &mbar[g * 3 + 0];
@@ -413,7 +479,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       // disposition histogram, likelihood and log-sum-exp of this row
       const int cd = active ? (accepted ? NB200_CODE_IN_SHELL
                                         : NB200_CODE_NN_REJECT)
-                            : (int)code[row];
+                            : cd_in;
       cnt32[NB200_CNT_RAW] += 1;
       if (cd == NB200_CODE_IN_SHELL) {
         const double ll = loglike_eval(tail.like_id, tail.like_p,
@@ -550,4 +616,22 @@ int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                       n, nullptr, nullptr, code, tail, n_partial_out, st);
 }
 
+#ifdef NB200_TIMELINE
+int debug_timeline(long long* out, int n) {
+  int cnt = 0;
+  cudaMemcpyFromSymbol(&cnt, g_tl_n, sizeof(int));
+  if (cnt > n) cnt = n;
+  cudaMemcpyFromSymbol(out, g_tl, sizeof(long long) * cnt);
+  int zero = 0;
+  cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(int));
+  return cnt;
+}
+#endif
+
 }  // namespace nb200
+
+#ifdef NB200_TIMELINE
+extern "C" int nb200_debug_timeline(long long* out, int n) {
+  return nb200::debug_timeline(out, n);
+}
+#endif
