@@ -79,6 +79,7 @@ class NautilusBound(_DeviceBound):
         self._buffer = None
         self.n_sample = 0
         self.n_reject = 0
+        self._replicas = None
         self._invalidate()
 
     def spec(self):
@@ -93,28 +94,64 @@ class NautilusBound(_DeviceBound):
         return restore(self._device_stack().contains(0, t, mode=mode))
 
     # -- sampling ------------------------------------------------------------
-    def draw_raw(self, n_raw, mode=None):
+    def draw_raw(self, n_raw, mode=None, pool=None):
         """One raw batch through union proposal and neural filter.  Updates
         all four integer counters exactly as the reference's nested loops do
         in aggregate (union.py:322-323, nautilus.py:221-222) and returns the
-        accepted points (CUDA)."""
+        accepted points (CUDA).
+
+        With a ``GpuPool`` the batch is sharded over its devices the way the
+        reference shards it over worker processes (nautilus.py:223-237):
+        device i draws the global proposal indices of its slice (Philox is
+        keyed by the global index, so the result does not depend on the pool
+        size), the parent sums the four counters and concatenates the points
+        on the first device."""
         mode = self.mode if mode is None else mode
-        stack = self._device_stack()
+        n_raw = int(n_raw)
         offset = self.stream.take(n_raw)
-        out = stack.cycle(0, int(n_raw), seed=self.stream.seed, offset=offset,
-                          stream_id=self.stream.stream_id, mode=mode)
-        keep, _, n_keep = stack.compact(out['points'], None, out['code'])
-        cnt = out['counters'].cpu().numpy()
+        home = self._device_stack().device     # where the FIFO lives
+        if pool is None or getattr(pool, 'size', 1) <= 1 or \
+                not hasattr(pool, 'devices'):
+            devices, slices = [home], [(0, n_raw)]
+        else:
+            devices, slices = pool.devices, pool.slices(n_raw)
+        launched = []
+        for dev, (lo, hi) in zip(devices, slices):
+            if hi <= lo:
+                continue
+            with torch.cuda.device(dev):
+                stack = self._device_stack_on(dev)
+                out = stack.cycle(0, hi - lo, seed=self.stream.seed,
+                                  offset=offset + lo,
+                                  stream_id=self.stream.stream_id, mode=mode)
+                keep, _, _ = stack.compact(out['points'], None, out['code'])
+                launched.append((keep, out['counters']))
+        parts, cnt = [], np.zeros(ops.N_CNT, dtype=np.int64)
+        for keep, counters in launched:          # one sync per device
+            c = counters.cpu().numpy()
+            cnt += c
+            parts.append(keep[:int(c[ops.CNT_IN_SHELL])].to(home))
         n_union_reject = int(cnt[ops.CNT_CUBE_REJECT] +
                              cnt[ops.CNT_OVERLAP_REJECT])
-        n_nn_reject = int(cnt[ops.CNT_NN_REJECT])
-        self.outer_bound.n_sample += int(n_raw)
+        self.outer_bound.n_sample += n_raw
         self.outer_bound.n_reject += n_union_reject
-        self.n_sample += int(n_raw) - n_union_reject
-        self.n_reject += n_nn_reject
-        return keep[:int(cnt[ops.CNT_IN_SHELL])]
+        self.n_sample += n_raw - n_union_reject
+        self.n_reject += int(cnt[ops.CNT_NN_REJECT])
+        return torch.cat(parts) if len(parts) > 1 else parts[0]
 
-    def _refill(self, n_points):
+    def _device_stack_on(self, dev):
+        """The serialised bound on device ``dev`` (replicated on demand, like
+        the reference pickles the bound to every worker)."""
+        dev = torch.device(dev)
+        if dev == self._device_stack().device:
+            return self._device_stack()
+        if getattr(self, '_replicas', None) is None:
+            self._replicas = {}
+        if dev not in self._replicas:
+            self._replicas[dev] = ops.DeviceStack([self.spec()], device=dev)
+        return self._replicas[dev]
+
+    def _refill(self, n_points, pool=None):
         have = 0 if self._buffer is None else self._buffer.shape[0]
         chunks = [] if self._buffer is None else [self._buffer]
         while have < n_points:
@@ -127,7 +164,7 @@ class NautilusBound(_DeviceBound):
             n_raw = int(min(max(self.raw_batch,
                                 1.2 * (n_points - have) / max(acc, 1e-4)),
                             1 << 22))
-            keep = self.draw_raw(n_raw)
+            keep = self.draw_raw(n_raw, pool=pool)
             chunks.append(keep)
             have += keep.shape[0]
         self._buffer = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
@@ -135,9 +172,9 @@ class NautilusBound(_DeviceBound):
     def sample(self, n_points=100, return_points=True, pool=None,
                as_numpy=True):
         """Pop n points from the FIFO of accepted points, refilling it with
-        raw GPU batches (nautilus.py:193-244).  ``pool`` is accepted for API
-        compatibility: the batch is already data-parallel."""
-        self._refill(n_points)
+        raw GPU batches (nautilus.py:193-244).  ``pool`` may be a ``GpuPool``:
+        the raw batch is then sharded over its devices."""
+        self._refill(n_points, pool=pool)
         if not return_points:
             return None
         out = self._buffer[:n_points]

@@ -401,7 +401,9 @@ class Sampler:
         kept = []
         while n_have < self.n_batch:
             want = self.n_batch - n_have
-            pts = bound.sample(want, as_numpy=False)
+            pts = (bound.sample(want, as_numpy=False, pool=self.pool_s)
+                   if isinstance(self.pool_s, GpuPool)
+                   else bound.sample(want, as_numpy=False))
             n_bound += want
             # drop points that belong to a later shell (every later bound is
             # consulted, as in the reference)

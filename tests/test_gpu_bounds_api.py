@@ -281,3 +281,26 @@ def test_nautilus_bound_reset_and_sample(random_points_from_hypercube):
     points_2, volume_2 = nbound.sample(10000), nbound.log_v
     assert np.all(points_1 == points_2)
     assert volume_1 == volume_2
+
+
+@pytest.mark.parametrize('n_gpus', [1, 2])
+def test_nautilus_bound_gpu_pool(random_points_from_hypercube, n_gpus):
+    # tests/test_bounds.py:412-441 (pool n_jobs in {1, 2}): sampling through a
+    # pool is reproducible -- and here it is also independent of the pool size
+    from nautilus_b200.pool import GpuPool
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip('needs {} GPUs'.format(n_gpus))
+    points = random_points_from_hypercube
+    log_l = -np.linalg.norm(points - 0.5, axis=1)
+    nbound = bounds.NautilusBound.compute(
+        points, log_l, np.median(log_l), np.log(0.5), n_networks=1,
+        rng=np.random.default_rng(0))
+    pool = GpuPool(n_gpus)
+    nbound.reset(np.random.default_rng(0))
+    points_1, volume_1 = nbound.sample(10000, pool=pool), nbound.log_v
+    nbound.reset(np.random.default_rng(0))
+    points_2, volume_2 = nbound.sample(10000, pool=pool), nbound.log_v
+    assert np.all(points_1 == points_2) and volume_1 == volume_2
+    nbound.reset(np.random.default_rng(0))
+    points_3, volume_3 = nbound.sample(10000), nbound.log_v
+    assert np.all(points_1 == points_3) and volume_1 == volume_3
