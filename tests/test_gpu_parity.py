@@ -446,3 +446,34 @@ def test_cycle_host_entry(golden):
                       like_params=like.device_params('cuda'), log_l_min=-1.0)
     assert np.array_equal(host(out['counters']), cnt)
     assert np.array_equal(host(out['points'])[host(out['code']) == 4], pts[:k])
+
+
+def test_empty_and_degenerate_inputs(golden):
+    # n = 0 everywhere, nothing accepted, one-point batches
+    spec = flat_to_spec(golden('nautilus_d4'))
+    stack = ops.DeviceStack([spec])
+    empty = torch.empty((0, 4), dtype=torch.float64, device='cuda')
+    assert stack.contains(0, empty).shape == (0,)
+    assert stack.union_count(0, empty)[0].shape == (0,)
+    p, code, nb = stack.propose(0, 0)
+    assert p.shape == (0, 4) and code.numel() == 0
+    like = likelihoods.Gaussian(4, sigma=0.3)
+    out = stack.cycle(0, 0, like_id=like.like_id,
+                      like_params=like.device_params('cuda'))
+    assert host(out['counters'])[ops.CNT_RAW] == 0
+    assert host(out['lse'])[0] == -np.inf
+    # a batch in which nothing survives: every point far outside
+    far = dev(np.full((100, 4), 5.0))
+    assert not bool(stack.contains(0, far).any())
+    code0 = torch.zeros(100, dtype=torch.uint8, device='cuda')
+    cp, cl, cn = stack.compact(far, torch.zeros(100, dtype=torch.float64,
+                                                device='cuda'), code0)
+    assert int(cn.item()) == 0
+    # wrong dimensionality / dtype are refused at the Python boundary
+    with pytest.raises(ValueError):
+        stack.contains(0, dev(np.zeros((3, 5))))
+    with pytest.raises(ValueError):
+        stack.contains(0, dev(np.zeros((3, 4), dtype=np.float32)))
+    # out-of-range bound index is refused by the library
+    with pytest.raises(RuntimeError):
+        stack.contains(3, dev(np.zeros((3, 4))))

@@ -1,0 +1,217 @@
+"""Host-side logic that needs no GPU: Prior (tests/test_prior.py of the
+reference, re-stated), bound serialisation, the tensor-core weight layout and
+the construction helpers."""
+
+import numpy as np
+import pytest
+from scipy.stats import norm
+
+from nautilus_b200._pack import (_core_matrix_layout, flat_to_spec, pack_stack,
+                                 pack_tc, spec_to_flat, tf32_round, union_cdf)
+from nautilus_b200.bounds import _construct
+from nautilus_b200.prior import Prior
+from oracle import nautilus_oracle as orc
+
+
+# ---- Prior ---------------------------------------------------------------
+
+def test_prior_add_parameter_errors():
+    with pytest.raises(TypeError):
+        Prior().add_parameter(1.0)
+    prior = Prior()
+    prior.add_parameter('a')
+    prior.add_parameter('b')
+    with pytest.raises(ValueError):
+        prior.add_parameter('a')
+    with pytest.raises(ValueError):
+        Prior().add_parameter('a', dist='a')
+    with pytest.raises(TypeError):
+        Prior().add_parameter(dist=[0.0])
+
+
+def test_prior_dimensionality():
+    prior = Prior()
+    for _ in range(6):
+        prior.add_parameter()
+    assert prior.dimensionality() == 6
+    assert prior.keys[3] == 'x_3'
+    prior = Prior()
+    prior.add_parameter(key='a')
+    prior.add_parameter(key='b', dist=1)
+    prior.add_parameter(key='c', dist='a')
+    prior.add_parameter(key='d', dist='b')
+    prior.add_parameter(key='e')
+    assert prior.dimensionality() == 2
+
+
+def test_prior_unit_to_physical_and_dictionary():
+    prior = Prior()
+    prior.add_parameter(key='a', dist=(-1, +1))
+    prior.add_parameter(key='b', dist='a')
+    prior.add_parameter(key='c', dist='b')
+    d1, d2 = norm(loc=3.0, scale=2.0), norm(loc=5.0, scale=1.0)
+    prior.add_parameter(key='d', dist=d1)
+    prior.add_parameter(key='e', dist=d2)
+    prior.add_parameter(key='f', dist=0.5)
+    rng = np.random.default_rng(0)
+    with pytest.raises(ValueError):
+        prior.unit_to_physical(rng.random(4))
+    for shape in [(3, ), (10, 3)]:
+        unit = rng.random(shape)
+        phys = prior.unit_to_physical(unit)
+        assert phys.shape == unit.shape
+        assert np.allclose(phys[..., 0], unit[..., 0] * 2 - 1)
+        assert np.allclose(phys[..., 1], d1.isf(1 - unit[..., 1]))
+        assert np.allclose(phys[..., 2], d2.isf(1 - unit[..., 2]))
+        out = prior.unit_to_dictionary(unit)
+        assert set(out) == {'a', 'b', 'c', 'd', 'e', 'f'}
+        assert np.all(out['b'] == out['a']) and np.all(out['c'] == out['a'])
+        assert np.all(out['f'] == 0.5)
+        assert np.all(out['d'] == phys[..., 1])
+    with pytest.raises(ValueError):
+        prior.physical_to_dictionary(rng.random(4))
+
+
+# ---- serialisation ---------------------------------------------------------
+
+def test_spec_flat_round_trip(golden):
+    for name in ('union_d5', 'cfg2_bound_d30', 'mixture_d6'):
+        g = golden(name)
+        spec = flat_to_spec(g)
+        again = flat_to_spec(spec_to_flat(spec))
+        m1, d1 = pack_stack([spec])
+        m2, d2 = pack_stack([again])
+        assert np.array_equal(m1, m2) and np.array_equal(d1, d2)
+
+
+def test_pack_stack_layout(golden):
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    cube = dict(kind='cube', n_dim=30)
+    meta, data = pack_stack([cube, spec, spec])
+    assert meta[0] == 3
+    r0, r1, r2 = (meta[meta[1 + i]:] for i in range(3))
+    assert (r0[1], r0[2]) == (0, 30)
+    assert (r1[1], r1[2], r1[3], r1[4], r1[5]) == (1, 30, 1, 1, 1)
+    assert r1[10] == 1           # neural ellipsoid == mixture 0 (shared pass)
+    mix = r1[r1[7]:r1[7] + 8]
+    assert (mix[0], mix[1], mix[6]) == (30, 0, 1)
+    ell = spec['mixtures'][0]['ell']
+    assert np.array_equal(data[mix[3]:mix[3] + 30], ell['c'])
+    assert np.array_equal(data[mix[5]:mix[5] + 900], ell['B_inv'].ravel())
+    nb = r1[r1[8]:r1[8] + 12]
+    assert (nb[3], nb[4]) == (4, 4)
+    assert data[nb[7]] == spec['neural'][0]['score_predict_min'] - 1e-9
+    # the second copy owns different data offsets
+    assert r2[r2[7] + 3] != mix[3]
+    assert np.allclose(union_cdf(spec['log_v_all']), [1.0])
+    with pytest.raises(ValueError):
+        pack_stack([dict(kind='cube', n_dim=129)])
+
+
+def test_tensor_core_blob_layout(golden):
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    emu = spec['neural'][0]['emulator']
+    hdr, blob = pack_tc(emu, 0.5)
+    n_groups, n_net, n_hid, d, k0p = hdr[0] >> 16, hdr[1], hdr[2], hdr[3], hdr[4]
+    assert (hdr[0] & 0xFFFF, n_groups, n_net, n_hid, d, k0p) == (
+        0x7F32, 2, 4, 3, 30, 32)
+    np_, kp = hdr[8:11], hdr[12:15]
+    assert list(np_) == [112, 64, 32] and list(kp) == [32, 104, 56]
+    # element (n, k) of layer l sits at the core-matrix address the kernel's
+    # smem descriptor describes: (n/8)*(8*kp) + (k/4)*32 + (n%8)*4 + (k%4)
+    w_off, stride = hdr[16:19], hdr[5]
+    for net in (0, 3):
+        for lay in range(3):
+            w = emu['coefs'][net][lay]
+            b = emu['intercepts'][net][lay]
+            fi, fo = w.shape
+
+            def at(n, k):
+                return blob[net * stride + w_off[lay] + (n // 8) * 8 * kp[lay]
+                            + (k // 4) * 32 + (n % 8) * 4 + (k % 4)]
+            for n, k in [(0, 0), (7, 3), (8, 4), (fo - 1, fi - 1), (13, 17)]:
+                assert at(n, k) == tf32_round(np.float32(w[k, n]))
+            # bias rides in the constant-one column, which is regenerated
+            assert at(5, fi) == tf32_round(np.float32(b[5]))
+            assert at(fo, fi) == (1.0 if lay < 2 else 0.0)
+            assert at(fo, 0) == 0.0
+    thr = np.array(hdr[30:32], dtype=np.int32).view(np.float64)[0]
+    assert thr == 0.5 - 1e-9
+    lay = _core_matrix_layout(np.arange(16 * 8, dtype=np.float32).reshape(
+        16, 8), 16, 8)
+    assert lay[0] == 0 and lay[4] == 8 and lay[32] == 4 and lay[64] == 64
+    # too wide / too many TMEM columns -> no blob, the caller must use fp64
+    sizes = (50, 128, 128, 128, 128, 1)
+    big = dict(coefs=[[np.zeros((a, b)) for a, b in zip(sizes[:-1],
+                                                        sizes[1:])]] * 4,
+               intercepts=[[np.zeros(b) for b in sizes[1:]]] * 4)
+    assert pack_tc(big, 0.0) is None
+
+
+def test_tf32_round():
+    x = np.array([1.0, 1.0 + 2.0**-11, 1.0 + 2.0**-10, -3.1415927, 0.0],
+                 dtype=np.float32)
+    r = tf32_round(x)
+    assert r[0] == 1.0 and r[2] == x[2] and r[4] == 0.0
+    assert r[1] == np.float32(1.0 + 2.0**-10)        # ties away from zero
+    assert abs(r[3] - x[3]) <= abs(x[3]) * 2.0**-11
+    assert np.all((r.view(np.uint32) & 0x1FFF) == 0)
+
+
+# ---- construction helpers ----------------------------------------------------
+
+def test_enclosing_ellipsoid_known_answer():
+    # tests/test_bounds.py:88-101 of the reference
+    n_dim = 10
+    points = np.zeros((2 * n_dim, n_dim)) + 0.5
+    for i in range(n_dim * 2):
+        points[i, i // 2] += 1 if i % 2 else -1
+    np.random.seed(0)
+    points = np.concatenate([points, np.atleast_2d(
+        np.full(n_dim, 0.5) + np.random.random() - 0.5)])
+    c, A, A_inv = _construct.enclosing_ellipsoid(points)
+    assert np.allclose(c, 0.5, rtol=0, atol=1e-3)
+    assert np.allclose(A, np.eye(n_dim), rtol=0, atol=1e-2)
+    assert np.allclose(A @ A_inv, np.eye(n_dim), atol=1e-10)
+    maha = np.einsum('ij,jk,ik->i', points - c, A, points - c)
+    assert np.isclose(maha.max(), 1.0)
+
+
+def test_enclosing_ellipsoid_elongated_cloud():
+    np.random.seed(0)
+    radius = 1e-5
+    points = np.vstack([np.random.normal(size=(500, 2)) * radius + 0.1,
+                        np.random.normal(size=(500, 2)) * radius + 0.9])
+    c, A, A_inv = _construct.enclosing_ellipsoid(points)
+    maha = np.einsum('ij,jk,ik->i', points - c, A, points - c)
+    assert np.all(np.isfinite(A)) and np.isclose(maha.max(), 1.0)
+    assert np.allclose(c, 0.5, atol=0.05)
+
+
+def test_two_gaussians_and_overlap():
+    rng = np.random.default_rng(0)
+    x = np.vstack([rng.normal(size=(300, 4)), rng.normal(size=(300, 4)) + 8])
+    log_p = _construct.two_gaussians(x, rng)
+    labels = np.argmax(log_p, axis=1)
+    assert len(set(labels[:300])) == 1 and len(set(labels[300:])) == 1
+    assert labels[0] != labels[-1]
+
+    class E:
+        def __init__(self, c, r):
+            self.c = np.asarray(c, dtype=float)
+            self.A = np.eye(len(c)) / r**2
+    assert not _construct.ellipsoids_overlap([E([0, 0], 1), E([2.5, 0], 1)])
+    assert _construct.ellipsoids_overlap([E([0, 0], 1), E([1.5, 0], 1)])
+    assert _construct.ellipsoids_overlap(
+        [E([0, 0], 1), E([5, 5], 1), E([5.5, 5], 1)])
+
+
+def test_oracle_classify_is_consistent_with_contains(golden):
+    # the disposition codes of oracle.classify agree with bound_contains
+    spec = flat_to_spec(golden('nautilus_d4'))
+    rng = np.random.default_rng(1)
+    pts = rng.random((2000, 4)) * 1.1 - 0.05
+    code, nb, _ = orc.classify(spec, [], pts, np.full(len(pts), 0.999))
+    inside = orc.bound_contains(spec, pts)
+    assert np.array_equal(code == 4, inside)
+    assert np.all(nb[code == 0] == 0)
