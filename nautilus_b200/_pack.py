@@ -192,9 +192,6 @@ def pack_tc(emu, score_predict_min):
     for l in range(n_hid):
         d_col.append(col)
         col += _round_up(np_[l], 32)
-    if col > TC_COLS_SINGLE:
-        return None
-    n_groups = 2 if col <= TC_COLS else 1
     w_off, b_off, off = [], [], 0
     for l in range(n_hid):
         w_off.append(off)
@@ -208,8 +205,19 @@ def pack_tc(emu, score_predict_min):
     off += 4
     net_stride = _round_up(off, 4)
     total = net_stride * n_net
-    if total * 4 > TC_SMEM_LIMIT:
-        return None
+    if col <= TC_COLS_SINGLE and total * 4 <= TC_SMEM_LIMIT:
+        # resident mode: every weight of every network stays in shared memory
+        n_groups = 2 if col <= TC_COLS else 1
+    else:
+        # streamed mode (csrc/nb200_mlp_layer.cu): one launch per (network,
+        # layer); a layer's weights and its TMEM footprint must fit
+        n_groups = 0
+        for l in range(n_hid):
+            extra = np_[-1] + 4 if l == n_hid - 1 else 0
+            cols = _round_up(kp[l], 32) + _round_up(np_[l], 32)
+            if (np_[l] * kp[l] + extra) * 4 > TC_SMEM_LIMIT or \
+                    cols > TC_COLS_SINGLE:
+                return None
     blob = np.zeros(total, dtype=np.float32)
     for n in range(n_net):
         base = n * net_stride

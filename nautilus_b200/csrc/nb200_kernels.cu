@@ -1133,6 +1133,7 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
           fused_tail ? (void*)ws.partial : nullptr, &n_partial, st);
     }
     if (rc) return rc;
+    if (fused_tail && n_partial == 0) fused_tail = false;  // streamed emulator
     if (fused_tail) {
       ProfScope prof(ST_STATS, st);
       k_stats_final<<<1, STAT_THREADS, 0, st>>>(ws.partial, n_partial, lse_d,

@@ -24,6 +24,7 @@
 // ~1e-3; membership near the threshold can flip (rate reported by the tests),
 // which is why the fp64 kernel remains the parity mode.
 #include "nb200_device.cuh"
+#include "nb200_tc.cuh"
 
 namespace nb200 {
 
@@ -73,117 +74,6 @@ __device__ int g_tl_n;
 #else
 #define TL_STAMP(tag) do {} while (0)
 #endif
-
-// ---- PTX wrappers ----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t it = 0; !done; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (it > (1u << 22)) __trap();   // never hang the GPU on a lost arrival
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src,
-                                         uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-      "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void group_sync(int g) {
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]^T, kind::tf32, M=128, cta_group::1
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
-                                            uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
-      "[%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]),
-        "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-        "=r"(v[15])
-      : "r"(addr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-        "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8};"
-      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-        "r"(v[5]), "r"(v[6]), "r"(v[7])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32(float f) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
-  return r;
-}
-// K-major, no-swizzle shared-memory matrix descriptor (SmemDescriptor of
-// cute/arch/mma_sm100_desc.hpp): core matrix = 8 rows x 16 B, LBO = byte
-// distance between the two 16-B K chunks of one MMA, SBO = byte distance
-// between 8-row groups; version 1 (Blackwell).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo,
-                                              uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) |
-         ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
-// N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((128u >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_GROUPS * TC_GROUP_THREADS, 1)
@@ -536,12 +426,28 @@ __global__ void k_standardise_tf32(const double* __restrict__ t_rows,
   xs32[e] = __uint_as_float(rr);
 }
 
+int run_mlp_tf32_streamed(const int32_t* hdr, const float* blob,
+                          const float* xs32, const uint8_t* mask, int64_t n,
+                          double* score_out, uint8_t* passf, uint8_t* code,
+                          cudaStream_t st);
+
 static int run_mlp_tf32(const TcHeader& h, const float* blob,
                         const float* xs32, const uint8_t* mask, int64_t n,
                         double* score_out, uint8_t* passf, uint8_t* code,
                         const TcTail& tail, int* grid_out, cudaStream_t st) {
-  const size_t smem = (size_t)h.total_floats * 4;
+  if ((h.magic >> 16) == 0) {
+    // weights do not fit shared memory all at once: layer-at-a-time kernel
+    NB_CHECK(tail.partial == nullptr, "streamed emulator has no fused tail");
+    if (grid_out) *grid_out = 0;
+    ProfScope prof(ST_MLP, st);
+    return run_mlp_tf32_streamed((const int32_t*)&h, blob, xs32, mask, n,
+                                 score_out, passf, code, st);
+  }
+  // one CTA per SM is REQUIRED (every CTA allocates all 512 TMEM columns):
+  // ask for enough shared memory that two can never be co-resident
+  size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
+  if (smem < 120 * 1024) smem = 120 * 1024;
   NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
@@ -568,7 +474,7 @@ static int tc_header(const int32_t* meta_h, int bound, int j, TcHeader* h) {
            "this emulator has no tensor-core blob (architecture outside the "
            "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
   memcpy(h, rec.r + nb[11], sizeof(*h));
-  NB_CHECK((h->magic & 0xFFFF) == 0x7F32 && (h->magic >> 16) >= 1 &&
+  NB_CHECK((h->magic & 0xFFFF) == 0x7F32 && (h->magic >> 16) >= 0 &&
                (h->magic >> 16) <= TC_GROUPS,
            "corrupt tensor-core blob header");
   return 0;
@@ -612,6 +518,7 @@ int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
   tail.points = points; tail.like_p = like_p; tail.log_l = log_l;
   tail.partial = (StatPartial*)partial; tail.log_l_min = log_l_min;
   tail.d = rec.d(); tail.like_id = like_id;
+  if ((h.magic >> 16) == 0) tail.partial = nullptr;   // streamed: no tail
   return run_mlp_tf32(h, (const float*)(data_d + rec.nb(j)[10]), xs32, mask,
                       n, nullptr, nullptr, code, tail, n_partial_out, st);
 }

@@ -101,23 +101,22 @@ def test_config5_like_fixed_bound_100d():
         rng=np.random.default_rng(1))
     spec = nbound.spec()
     stack = ops.DeviceStack([spec])
-    # four default networks at d = 100 exceed the resident-weight envelope of
-    # the tensor-core kernel: no blob, and asking for tf32 fails loudly
+    # two default networks at d = 100 still fit shared memory (one tile group,
+    # staged fp64 front end); four do not and take the layer-at-a-time
+    # tensor-core kernel.  Both must track the fp64 scores.
     from nautilus_b200._pack import pack_tc
     emu2 = spec['neural'][0]['emulator']
     emu4 = dict(emu2, coefs=emu2['coefs'] * 2, intercepts=emu2['intercepts'] * 2)
-    assert pack_tc(emu4, 0.5) is None
+    assert pack_tc(emu2, 0.5)[0][0] >> 16 == 1
+    assert pack_tc(emu4, 0.5)[0][0] >> 16 == 0
     spec4 = dict(spec, neural=[dict(spec['neural'][0], emulator=emu4)])
-    with pytest.raises(RuntimeError):
-        ops.DeviceStack([spec4]).cycle(0, 256, mode=ops.MLP_TF32)
-    # two networks fit (one tile group, staged fp64 front end): tf32 scores
-    # track the fp64 ones
     raw, _, _ = stack.propose(0, 4096, seed=9)
     whitened = torch.from_numpy(orc.ell_transform(
         spec['neural'][0]['ell'], raw.cpu().numpy())).cuda()
-    p64 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_F64).cpu().numpy()
-    p32 = stack.mlp_predict(0, 0, whitened, mode=ops.MLP_TF32).cpu().numpy()
-    assert np.max(np.abs(p64 - p32)) < 5e-3
+    for st in (stack, ops.DeviceStack([spec4])):
+        p64 = st.mlp_predict(0, 0, whitened, mode=ops.MLP_F64).cpu().numpy()
+        p32 = st.mlp_predict(0, 0, whitened, mode=ops.MLP_TF32).cpu().numpy()
+        assert np.max(np.abs(p64 - p32)) < 5e-3
     n = 4096
     out = stack.cycle(0, n, seed=2, like_id=like.like_id,
                       like_params=like.device_params('cuda'),
@@ -131,3 +130,47 @@ def test_config5_like_fixed_bound_100d():
     assert sel.sum() > 0
     got = out['log_l'].cpu().numpy()[sel]
     assert np.max(np.abs(got - ref_ll[sel]) / np.abs(ref_ll[sel])) < 1e-12
+
+
+def test_config3_like_wide_network_streamed():
+    # config 3's emulator: 50 -> 4 x 128 -> 1, four networks (1 MB of tf32
+    # weights): layer-at-a-time tensor-core path against the fp64 kernel
+    d, hidden, n_net = 50, (128, 128, 128, 128), 4
+    rng = np.random.default_rng(0)
+    sizes = (d, ) + hidden + (1, )
+    coefs = [[rng.normal(size=(a, b)) * np.sqrt(2.0 / a)
+              for a, b in zip(sizes[:-1], sizes[1:])] for _ in range(n_net)]
+    intercepts = [[rng.normal(size=b) * 0.1 for b in sizes[1:]]
+                  for _ in range(n_net)]
+    for n in range(n_net):                  # keep the score O(1)
+        coefs[n][-1] *= 0.1
+    ell = dict(c=np.full(d, 0.5), B=np.eye(d) * 0.45, B_inv=np.eye(d) / 0.45)
+    emu = dict(mean=np.zeros(d), scale=np.full(d, 0.3), coefs=coefs,
+               intercepts=intercepts)
+    spec = dict(kind='nautilus', n_dim=d, unit=True,
+                log_v_all=np.array([0.0]),
+                mixtures=[dict(dim_cube=np.zeros(d, bool), ell=ell)],
+                neural=[dict(ell=ell, emulator=emu, score_predict_min=0.05)])
+    stack = ops.DeviceStack([spec])
+    t = torch.from_numpy(rng.normal(size=(5000, d)) * 0.3).cuda()
+    p64 = stack.mlp_predict(0, 0, t, mode=ops.MLP_F64).cpu().numpy()
+    p32 = stack.mlp_predict(0, 0, t, mode=ops.MLP_TF32).cpu().numpy()
+    ref = orc.emulator_predict(emu, t.cpu().numpy())
+    assert np.max(np.abs(p64 - ref)) < 1e-12
+    err = np.max(np.abs(p32 - p64))
+    print('streamed tf32 emulator (4 x 128): max |d score| = {:.2e} at score '
+          'scale {:.2f}'.format(err, np.std(p64)))
+    assert err < 5e-3 * max(1.0, np.std(p64))
+    # the cycle works end to end with the streamed emulator and agrees with
+    # contains() under the same arithmetic
+    like = likelihoods.Rosenbrock(d)
+    out = stack.cycle(0, 1 << 14, seed=1, like_id=like.like_id,
+                      like_params=like.device_params('cuda'),
+                      mode=ops.MLP_TF32)
+    keep, _, n_keep = stack.compact(out['points'], out['log_l'], out['code'])
+    n_keep = int(n_keep.item())
+    cnt = out['counters'].cpu().numpy()
+    assert cnt[ops.CNT_RAW] == 1 << 14 and n_keep == cnt[ops.CNT_IN_SHELL]
+    if n_keep:
+        assert bool(stack.contains(0, keep[:n_keep].contiguous(),
+                                   mode=ops.MLP_TF32).all())

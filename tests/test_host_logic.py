@@ -140,12 +140,16 @@ def test_tensor_core_blob_layout(golden):
     lay = _core_matrix_layout(np.arange(16 * 8, dtype=np.float32).reshape(
         16, 8), 16, 8)
     assert lay[0] == 0 and lay[4] == 8 and lay[32] == 4 and lay[64] == 64
-    # too wide / too many TMEM columns -> no blob, the caller must use fp64
-    sizes = (50, 128, 128, 128, 128, 1)
-    big = dict(coefs=[[np.zeros((a, b)) for a, b in zip(sizes[:-1],
-                                                        sizes[1:])]] * 4,
-               intercepts=[[np.zeros(b) for b in sizes[1:]]] * 4)
-    assert pack_tc(big, 0.0) is None
+    # config 3 (50 -> 4 x 128 -> 1, four networks): 1 MB of weights -> the
+    # streamed (layer-at-a-time) mode; five hidden layers -> no blob at all
+    def zeros(sizes, n_net=4):
+        return dict(coefs=[[np.zeros((a, b)) for a, b in zip(
+            sizes[:-1], sizes[1:])]] * n_net,
+            intercepts=[[np.zeros(b) for b in sizes[1:]]] * n_net)
+    hdr3, blob3 = pack_tc(zeros((50, 128, 128, 128, 128, 1)), 0.0)
+    assert hdr3[0] >> 16 == 0 and list(hdr3[8:12]) == [144] * 4
+    assert list(hdr3[12:16]) == [56, 136, 136, 136]
+    assert pack_tc(zeros((50, 64, 64, 64, 64, 64, 1)), 0.0) is None
 
 
 def test_tf32_round():
