@@ -48,6 +48,8 @@ struct FitArgs {
   int a_off[FIT_MAX_LAYERS + 1], a_stride[FIT_MAX_LAYERS + 1];
   int n_params, delta_off, delta_stride, smem_floats, gsum_off;
   int rows;      // resident chunk (64, 32 or 16: what fits shared memory)
+  int big;       // weights / gradient too large for shared memory: they live
+                 // in (L2-resident) global memory, activations stay on chip
   int p_quarter; // ceil(n_params / FIT_CLUSTER)
   float lr, beta1, beta2, eps, tol;
   unsigned long long seed;
@@ -64,14 +66,18 @@ __launch_bounds__(FIT_THREADS, 1)
 k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           const float* __restrict__ y, float* __restrict__ moments,
           double* __restrict__ weights_out, int* __restrict__ n_iter_out,
-          double* __restrict__ loss_out) {
+          double* __restrict__ loss_out, float* __restrict__ big_store) {
   extern __shared__ float fs[];
-  float* W = fs;                       // parameters of this network
-  float* G = fs + A.n_params;          // gradient of the current minibatch
-  float* act = G + A.n_params;         // activations a_0..a_L of one chunk
+  // per-CTA parameter storage: shared memory, or global memory in big mode
+  // ([W | G | Gq] per CTA, Gq padded to n_params for simple indexing)
+  float* big_base = big_store + (size_t)blockIdx.x * 3 * A.n_params;
+  float* W = A.big ? big_base : fs;    // parameters of this network
+  float* G = A.big ? big_base + A.n_params : fs + A.n_params;
+  float* act = A.big ? fs : fs + 2 * A.n_params;   // activations a_0..a_L
   float* dl0 = fs + A.delta_off;       // delta ping-pong
   float* dl1 = dl0 + A.rows * A.delta_stride;
-  float* Gq = fs + A.gsum_off;         // this CTA's reduced quarter of G
+  // this CTA's reduced quarter of G
+  float* Gq = A.big ? big_base + 2 * A.n_params : fs + A.gsum_off;
   __shared__ float red[FIT_THREADS / 32];
   __shared__ float s_loss;
   __shared__ float s_bsq;              // this CTA's share of sum (y - t)^2
@@ -267,6 +273,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       }
       // ---- all-reduce of the gradient and the loss over the cluster -----------
       if (tid == 0) s_bsq = batch_sq;
+      if (A.big) __threadfence();      // G lives in global memory
       cluster.sync();
       // reduce-scatter: this CTA sums ITS quarter of the gradient over all
       // ranks (rank order => identical on every CTA) ...
@@ -276,8 +283,13 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
         for (int e = lo + tid; e < hi; e += FIT_THREADS) {
           float g = 0.f;
 #pragma unroll
-          for (int q = 0; q < FIT_CLUSTER; ++q)
-            g += cluster.map_shared_rank(G, q)[e];
+          for (int q = 0; q < FIT_CLUSTER; ++q) {
+            const float* Gp =
+                A.big ? big_store + ((size_t)(blockIdx.x - crank + q) * 3 + 1) *
+                                        A.n_params
+                      : cluster.map_shared_rank(G, q);
+            g += A.big ? __ldcg(Gp + e) : Gp[e];
+          }
           Gq[e - lo] = g;
         }
         float t = 0.f;
@@ -286,6 +298,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           t += *cluster.map_shared_rank(&s_bsq, q);
         batch_sq = t;
       }
+      if (A.big) __threadfence();
       cluster.sync();      // ... all-gather happens inside the Adam loop
       // ---- Adam step on the whole minibatch gradient --------------------------
       t_adam += 1;
@@ -295,7 +308,10 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       for (int e = tid; e < P; e += FIT_THREADS) {
         const int owner = e / A.p_quarter;
         const float gq =
-            cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
+            A.big ? __ldcg(big_store +
+                           ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
+                               A.n_params + (e - owner * A.p_quarter))
+                  : cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
         const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
         const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
         mom_m[e] = mq;
@@ -339,8 +355,9 @@ extern "C" {
 
 size_t nb200_mlp_fit_workspace_bytes(int64_t m, int d, int n_params,
                                      int n_net) {
+  // x32, y32, Adam moments (2P) and big-mode parameter storage (3P) per CTA
   return (size_t)m * d * 4 + (size_t)m * 4 +
-         (size_t)n_net * FIT_CLUSTER * 2 * n_params * 4 + 1024;
+         (size_t)n_net * FIT_CLUSTER * 5 * n_params * 4 + 1024;
 }
 
 int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
@@ -388,16 +405,34 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
     A.smem_floats = A.gsum_off + A.p_quarter;
     if ((size_t)A.smem_floats * 4 <= 220 * 1024) break;
   }
+  if ((size_t)A.smem_floats * 4 > 220 * 1024) {
+    // big mode: weights, gradient and the reduction buffer in global memory
+    // (a few hundred KB, L2 resident); activations of 64 rows on chip
+    A.big = 1;
+    for (A.rows = FIT_ROWS_MAX; A.rows >= 8; A.rows >>= 1) {
+      int aoff = 0;
+      for (int l = 0; l <= n_lay; ++l) {
+        A.a_stride[l] = A.sizes[l] | 1;
+        A.a_off[l] = aoff;
+        aoff += A.rows * A.a_stride[l];
+      }
+      A.delta_off = aoff;
+      A.gsum_off = 0;
+      A.smem_floats = A.delta_off + 2 * A.rows * A.delta_stride;
+      if ((size_t)A.smem_floats * 4 <= 220 * 1024) break;
+    }
+  }
   const size_t smem = (size_t)A.smem_floats * 4;
   NB_CHECK(smem <= 220 * 1024,
-           "network too large for the on-chip trainer (weights + gradient + "
-           "an 8-row chunk of activations must fit 220 KB)");
+           "network too wide for the trainer (an 8-row chunk of activations "
+           "must fit 220 KB of shared memory)");
   NB_CHECK(workspace_bytes >=
                nb200_mlp_fit_workspace_bytes(m, d, A.n_params, n_net),
            "workspace too small");
   float* x32 = (float*)workspace_d;
   float* y32 = x32 + (size_t)m * d;
   float* moments = y32 + ((m + 3) / 4) * 4;
+  float* big_store = moments + (size_t)n_net * FIT_CLUSTER * 2 * A.n_params;
   ProfScope prof(ST_FIT, st);
   k_f64_to_f32<<<(unsigned)((m * d + 255) / 256), 256, 0, st>>>(x_d, m * d, x32);
   NB_LAUNCH_OK();
@@ -408,7 +443,7 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
                                (int)smem));
   k_mlp_fit<<<n_net * FIT_CLUSTER, FIT_THREADS, smem, st>>>(A, x32, y32, moments,
                                               weights_out_d, n_iter_out_d,
-                                              loss_out_d);
+                                              loss_out_d, big_store);
   NB_LAUNCH_OK();
   return 0;
 }

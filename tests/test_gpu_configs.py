@@ -174,3 +174,25 @@ def test_config3_like_wide_network_streamed():
     if n_keep:
         assert bool(stack.contains(0, keep[:n_keep].contiguous(),
                                    mode=ops.MLP_TF32).all())
+
+
+def test_config3_like_wide_network_training():
+    # the 4 x 128 emulator of config 3 does not fit shared memory: the trainer
+    # keeps weights / gradient in L2-resident global memory ("big" mode)
+    from nautilus_b200 import neural
+    rng = np.random.default_rng(0)
+    d, m = 50, 3000
+    x = rng.random((m, d))
+    y = np.linalg.norm(x[:, :5] - 0.5, axis=1)
+    y = np.argsort(np.argsort(y)) / float(m)
+    emu = neural.NeuralNetworkEmulator.train(
+        x, y, n_networks=2,
+        neural_network_kwargs=dict(hidden_layer_sizes=(128, 128, 128, 128)))
+    assert emu.neural_networks[0].coefs_[1].shape == (128, 128)
+    pred = emu.predict(x)
+    rmse = np.sqrt(np.mean((y - pred)**2))
+    print('4 x 128 emulator: rmse / std = {:.3f}, epochs = {}'.format(
+        rmse / np.std(y), [n.n_iter_ for n in emu.neural_networks]))
+    assert rmse < 0.3 * np.std(y)
+    p32 = emu.predict(x, mode=ops.MLP_TF32)
+    assert np.max(np.abs(p32 - pred)) < 5e-3
