@@ -25,11 +25,15 @@ def main():
     ap.add_argument('--timeout', type=float, default=1500)
     ap.add_argument('--profile', action='store_true')
     args = ap.parse_args()
+    nn_kwargs = {}
     if args.config == 1:
         like, n_live = likelihoods.Gaussian(3, mu=[0.4, 0.5, 0.6],
                                             sigma=0.1), 1000
     elif args.config == 2:
         like, n_live = likelihoods.Gaussian(30, sigma=0.1), 2000
+    elif args.config == 3:
+        like, n_live = likelihoods.Rosenbrock(50), 4000
+        nn_kwargs = dict(hidden_layer_sizes=(128, 128, 128, 128))
     elif args.config == 4:
         mus = np.full((4, 30), 0.5)
         mus[:, 0] = [0.25, 0.25, 0.75, 0.75]
@@ -39,7 +43,8 @@ def main():
         raise SystemExit('config not wired')
     sampler = Sampler(lambda x: x, like, n_dim=like.n_dim, n_live=n_live,
                       seed=args.seed, n_batch=args.n_batch,
-                      emulator_arith=args.arith)
+                      emulator_arith=args.arith,
+                      neural_network_kwargs=nn_kwargs)
     t0 = time.time()
     if args.profile:
         import cProfile
@@ -57,7 +62,9 @@ def main():
         'config': args.config, 'success': bool(ok), 'wall_s': wall,
         'n_like': int(sampler.n_like), 'n_bounds': len(sampler.bounds),
         'log_z': float(sampler.log_z), 'log_z_true': like.log_z_true,
-        'delta_log_z': abs(float(sampler.log_z) - like.log_z_true),
+        'delta_log_z': (None if like.log_z_true is None else
+                        abs(float(sampler.log_z) - like.log_z_true)),
+        'f_live': None if sampler.explored else float(sampler.f_live),
         'n_eff': float(sampler.n_eff), 'raw_proposals': int(raw),
         'emulator_arith': args.arith, 'n_batch': sampler.n_batch,
         'discard_exploration': not args.keep_exploration}), flush=True)
