@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D = 30
+CPU_BUDGET_S = 60.0      # CPU loop time the reference arm may spend
 ALGO_BYTES_PER_PROPOSAL = 8 * D + 8 + 1      # row + log_l + disposition
 MLP_FLOPS_PER_POINT = 4 * 2 * (30 * 100 + 100 * 50 + 50 * 20 + 20 * 1)
 WORKLOAD = ('cfg2: 30-D isotropic Gaussian (sigma=0.1), n_live=2000, bound '
@@ -34,11 +35,17 @@ WORKLOAD = ('cfg2: 30-D isotropic Gaussian (sigma=0.1), n_live=2000, bound '
             'batch=2^20 raw proposals per GPU per step')
 
 
+_SPEC = None
+
+
 def load_spec():
-    from nautilus_b200._pack import flat_to_spec
-    with np.load(os.path.join(ROOT, 'tests', 'golden',
-                              'cfg2_bound_d30.npz')) as f:
-        return flat_to_spec({k: f[k] for k in f.files})
+    global _SPEC
+    if _SPEC is None:
+        from nautilus_b200._pack import flat_to_spec
+        with np.load(os.path.join(ROOT, 'tests', 'golden',
+                                  'cfg2_bound_d30.npz')) as f:
+            _SPEC = flat_to_spec({k: f[k] for k in f.files})
+    return _SPEC
 
 
 def measured_peaks():
@@ -88,21 +95,38 @@ def _cpu_worker(args):
     return state['u_n_sample'], dt
 
 
+class CpuPool:
+    """Persistent worker pool (what the reference's `pool=` keeps alive,
+    sampler.py:283-298): forked once, reused for every step."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
+
+    def run(self, n_raw_per_core, seed=0):
+        """One pass of the oracle loop on every core; returns (raw proposals,
+        seconds) with seconds = the slowest worker's loop time."""
+        jobs = [(seed + i, n_raw_per_core) for i in range(self.cores)]
+        if self.pool is None:
+            res = [_cpu_worker(jobs[0])]
+        else:
+            res = self.pool.map(_cpu_worker, jobs, chunksize=1)
+        return sum(r[0] for r in res), max(r[1] for r in res)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
 def cpu_pass(cores, n_raw_per_core, seed=0):
     """Run the oracle loop on `cores` processes; returns (raw proposals, s)."""
-    import multiprocessing as mp
-    t0 = time.perf_counter()
-    if cores == 1:
-        res = [_cpu_worker((seed, n_raw_per_core))]
-    else:
-        ctx = mp.get_context('fork')
-        with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_worker, [(seed + i, n_raw_per_core)
-                                         for i in range(cores)])
-    # throughput of the persistent pool the reference would use: slowest
-    # worker's loop time (pool start-up and imports excluded)
-    del t0
-    return sum(r[0] for r in res), max(r[1] for r in res)
+    pool = CpuPool(cores)
+    try:
+        return pool.run(n_raw_per_core, seed)
+    finally:
+        pool.close()
 
 
 def host_cores():
@@ -118,14 +142,19 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    per_core = 100000
-    for _ in range(args.warmup):
-        cpu_pass(cores, 5000)
+    # bounded sample: about CPU_BUDGET_S seconds of loop time for the whole
+    # run whatever --steps is (one core does ~2e5 raw proposals/s)
+    per_core = int(CPU_BUDGET_S * 2.0e5 / max(args.steps, 1))
+    per_core = max(2000, min(400000, per_core // 1000 * 1000))
+    pool = CpuPool(cores)
+    for _ in range(min(args.warmup, 3)):
+        pool.run(2000)
     total, wall = 0, 0.0
     for s in range(args.steps):
-        n, dt = cpu_pass(cores, per_core, seed=1000 * (s + 1))
+        n, dt = pool.run(per_core, seed=1000 * (s + 1))
         total += n
         wall += dt
+    pool.close()
     value = total / wall
     sample = ('{} steps x {} processes x {} raw proposals through the oracle '
               'port of Union.sample/NautilusBound.sample/likelihood/'
@@ -317,53 +346,47 @@ def run_gpu(args):
     ops.profile_enable(False)
     barrier()
 
-    # ---- e2e leg: host buffers, H2D of the bound + D2H of the results ------
-    meta_pin = torch.from_numpy(stack.meta_h).pin_memory()
-    data_pin = stack.data_d.cpu().pin_memory()
-    par_pin = like_params.cpu().pin_memory()
-    cap = n
-    pts_pin = torch.empty((cap, D), dtype=torch.float64).pin_memory()
-    ll_pin = torch.empty(cap, dtype=torch.float64).pin_memory()
-    small_pin = torch.empty(ops.N_CNT + ops.N_LSE + 1,
-                            dtype=torch.float64).pin_memory()
-    cp = torch.empty((n, D), dtype=torch.float64, device=dev)
-    cl = torch.empty(n, dtype=torch.float64, device=dev)
+    # ---- e2e leg: the C-ABI host-buffer session (include/nautilus_b200.h,
+    # nb200_session_*): NumPy in, NumPy out.  Every step uploads the
+    # serialised bound + likelihood parameters from pinned host memory and
+    # brings the in-shell points, their log_l, the counters and the
+    # log-sum-exp triple back to host memory; two batches are in flight so the
+    # device->host copy of one runs under the kernels of the next.
+    sess = ops.HostSession([spec], n_max=n, cap=max(n // 4, 1024), n_slots=2,
+                           like_params_max=like_params.numel())
+    par_h = like_params.cpu().numpy()
     bytes_io = {'h2d': 0, 'd2h': 0}
+    host = {'points': 0, 'sum_ll': 0.0}
 
-    def e2e_step():
+    def e2e_submit(slot):
         s = state['step']
         state['step'] += 1
-        stack.meta_d.copy_(meta_pin, non_blocking=True)
-        stack.data_d.copy_(data_pin, non_blocking=True)
-        like_params.copy_(par_pin, non_blocking=True)
-        h2d = (meta_pin.numel() * 4 + data_pin.numel() * 8 +
-               par_pin.numel() * 8)
-        stack.cycle(0, n, seed=seed, offset=(s * world + rank) * n,
-                    like_id=like.like_id, like_params=like_params,
-                    log_l_min=log_l_min, mode=mode, out=out)
-        _, _, n_out = stack.compact(out['points'], out['log_l'], out['code'],
-                                    out_points=cp, out_log_l=cl)
-        small = torch.cat([out['counters'].double(), out['lse'],
-                           n_out.double()])
-        small_pin.copy_(small, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        k = int(small_pin[-1].item())
-        pts_pin[:k].copy_(cp[:k], non_blocking=True)
-        ll_pin[:k].copy_(cl[:k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        bytes_io['h2d'] = h2d
-        bytes_io['d2h'] = k * (D + 1) * 8 + small_pin.numel() * 8
+        sess.submit(slot, 0, n, seed=seed, offset=(s * world + rank) * n,
+                    like_id=like.like_id, like_params=par_h,
+                    log_l_min=log_l_min, mode=mode, upload_stack=True)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_wait(slot):
+        res = sess.wait(slot)
+        k = len(res['log_l'])
+        host['points'] += k
+        host['sum_ll'] += float(res['log_l'][-1]) if k else 0.0
+        bytes_io['h2d'] = sess.stack_bytes + par_h.nbytes
+        bytes_io['d2h'] = k * (D + 1) * 8 + (ops.N_LSE + ops.N_CNT + 1) * 8
+
+    def e2e_run(k_steps):
+        e2e_submit(0)
+        for i in range(k_steps):
+            if i + 1 < k_steps:
+                e2e_submit((i + 1) & 1)
+            e2e_wait(i & 1)
+
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
+    e2e_run(args.steps)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    sess.close()
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -446,7 +469,9 @@ def run_gpu(args):
         'e2e': {'value': e2e_value, 'unit': 'proposals/s',
                 'h2d_bytes_per_step': bytes_io['h2d'],
                 'd2h_bytes_per_step': bytes_io['d2h'],
-                'ms_per_step': e2e_ms / args.steps},
+                'ms_per_step': e2e_ms / args.steps,
+                'api': 'nb200_session_submit/_wait (C ABI, host buffers), 2 '
+                       'batches in flight, host wall clock'},
         'gpu_launches': launches,
         'clocks': clocks.summary() if clocks else None,
         'result': result,

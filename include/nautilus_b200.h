@@ -235,6 +235,45 @@ int nb200_cycle_host(const int32_t* meta_h, int64_t n_meta,
                      double* points_out_h, double* log_l_out_h,
                      int64_t* n_out_h, double* lse_h, int64_t* counters_h);
 
+/* ---- host-buffer session: the loop around add_samples ------------------- */
+
+/* A session owns the device buffers, two streams and pinned host buffers for
+ * batches of up to n_max raw proposals of one bound stack, so that a host
+ * caller (NumPy / ctypes, like the reference's Sampler) pays no allocation
+ * per batch and the device->host copy of batch i overlaps the kernels of
+ * batch i+1.  `cap` = most in-shell rows one batch may return (<= n_max),
+ * n_slots (1..4) = batches that may be in flight.  The stack is copied; it
+ * can be replaced by set_stack (same or smaller size) between shells
+ * (sampler.py:1023-1039, a new bound was accepted).
+ *
+ *   submit(slot, ...)  enqueues, without blocking the host: [H2D of the stack
+ *       if upload_stack] -> H2D of the likelihood parameters -> nb200_cycle ->
+ *       nb200_compact -> D2H of sums / counters / row count.
+ *   wait(slot, ...)    blocks until that batch is done, copies its in-shell
+ *       points and log_l into the slot's pinned buffers and returns pointers
+ *       to them (valid until the slot is submitted again): what
+ *       Sampler.add_samples appends (sampler.py:1135-1141), plus the inputs
+ *       of update_shell_info (sampler.py:925-943) as lse f64[4] and
+ *       counters i64[8].  *log_l_h is NULL when like_id < 0.
+ * Not thread-safe per session; different sessions are independent. */
+typedef struct nb200_session nb200_session;
+int nb200_session_create(const int32_t* meta_h, int64_t n_meta,
+                         const double* data_h, int64_t n_data, int64_t n_max,
+                         int64_t cap, int n_slots, int like_params_max,
+                         nb200_session** out);
+int nb200_session_destroy(nb200_session* s);
+int nb200_session_set_stack(nb200_session* s, const int32_t* meta_h,
+                            int64_t n_meta, const double* data_h,
+                            int64_t n_data);
+int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
+                         int bound, int first_later, int n_later, int64_t n,
+                         uint64_t seed, uint64_t offset, uint32_t stream_id,
+                         int like_id, const double* like_params_h,
+                         int n_like_params, double log_l_min, int mlp_mode);
+int nb200_session_wait(nb200_session* s, int slot, const double** points_h,
+                       const double** log_l_h, int64_t* n_out, double* lse_h,
+                       int64_t* counters_h);
+
 #ifdef __cplusplus
 }
 #endif

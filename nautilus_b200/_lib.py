@@ -98,6 +98,14 @@ PROTOTYPES = {
     'nb200_cycle_host': (_int, [_i32p, _i64, _vp, _i64, _int, _int, _int,
                                 _i64, _u64, _u64, _u32, _int, _vp, _int, _dbl,
                                 _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'nb200_session_create': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int,
+                                    _int, _vp]),
+    'nb200_session_destroy': (_int, [_vp]),
+    'nb200_session_set_stack': (_int, [_vp, _vp, _i64, _vp, _i64]),
+    'nb200_session_submit': (_int, [_vp, _int, _int, _int, _int, _int, _i64,
+                                    _u64, _u64, _u32, _int, _vp, _int, _dbl,
+                                    _int]),
+    'nb200_session_wait': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -265,16 +265,19 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     auto epi_hidden = [&](int l) {
       tc_fence_after();
       const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-      for (int c = hf * 16; c < h.np[l]; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(d_addr + (uint32_t)c, v);
+      // 32 columns per TMEM load (the accumulator regions are 32-column
+      // aligned; pad columns meet zero weights), halves interleaved, so the
+      // TMEM read latency is exposed once per 32 columns
+      for (int c = hf * 32; c < h.np[l]; c += 64) {
+        uint32_t v[32];
+        tmem_ld32(d_addr + (uint32_t)c, v);
         tmem_wait_ld();
         // ReLU, then round-half-up to tf32: the MMA reads only the top 19
         // bits, so adding half an ulp of tf32 is the whole rounding
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
+        for (int q = 0; q < 32; ++q)
           v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
-        tmem_st16(d_addr + (uint32_t)c, v);
+        tmem_st32(d_addr + (uint32_t)c, v);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -290,10 +293,15 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       for (int c = hf * 16; c < h.np[l]; c += 32) {
         uint32_t v[16];
         tmem_ld16(d_addr + (uint32_t)c, v);
+        // the output weights of these 16 columns: four broadcast LDS.128
+        const float4* w4 = reinterpret_cast<const float4*>(wout + c);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                             w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), wout[c + q], acc);
+          acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), w[q], acc);
       }
       if (hf) part[g][r] = acc;
       // a later MMA overwrites these columns: order the loads before it

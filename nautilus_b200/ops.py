@@ -229,6 +229,101 @@ class DeviceStack:
         return out_points, out_log_l, n_out
 
 
+class HostSession:
+    """Host-buffer form of the cycle (``nb200_session_*``): NumPy in, NumPy
+    out, no torch tensors.  ``submit`` enqueues one raw batch and returns at
+    once; ``wait`` returns what ``Sampler.add_samples`` appends to its host
+    arrays (sampler.py:1135-1141) and what ``update_shell_info`` reduces
+    (sampler.py:925-943).  With ``n_slots >= 2`` the device->host copy of one
+    batch runs under the kernels of the next.
+
+    The arrays returned by ``wait`` are views of the slot's pinned buffers:
+    valid until that slot is submitted again (copy them to keep them).
+    """
+
+    def __init__(self, specs, n_max, cap=None, n_slots=2, like_params_max=0,
+                 device=None):
+        if device is not None:
+            torch.cuda.set_device(device)
+        meta, data = pack_stack(specs)
+        self.meta_h = np.ascontiguousarray(meta, dtype=np.int32)
+        self.data_h = np.ascontiguousarray(data, dtype=np.float64)
+        self.n_dim = int(specs[0]['n_dim'])
+        self.n_max = int(n_max)
+        self.cap = int(cap if cap is not None else n_max)
+        self.n_slots = int(n_slots)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().nb200_session_create(
+            self.meta_h.ctypes.data_as(ctypes.c_void_p), self.meta_h.size,
+            self.data_h.ctypes.data_as(ctypes.c_void_p), self.data_h.size,
+            self.n_max, self.cap, self.n_slots, int(like_params_max),
+            ctypes.byref(self._h)))
+
+    @property
+    def stack_bytes(self):
+        return self.meta_h.nbytes + self.data_h.nbytes
+
+    def set_stack(self, specs):
+        meta, data = pack_stack(specs)
+        self.meta_h = np.ascontiguousarray(meta, dtype=np.int32)
+        self.data_h = np.ascontiguousarray(data, dtype=np.float64)
+        _lib.check(_lib.lib().nb200_session_set_stack(
+            self._h, self.meta_h.ctypes.data_as(ctypes.c_void_p),
+            self.meta_h.size, self.data_h.ctypes.data_as(ctypes.c_void_p),
+            self.data_h.size))
+
+    def submit(self, slot, bound, n, later=(0, 0), seed=0, offset=0,
+               stream_id=0, like_id=-1, like_params=None, log_l_min=-np.inf,
+               mode=MLP_F64, upload_stack=False):
+        if like_params is None:
+            par, n_par = None, 0
+        else:
+            like_params = np.ascontiguousarray(like_params, dtype=np.float64)
+            par = like_params.ctypes.data_as(ctypes.c_void_p)
+            n_par = like_params.size
+        _lib.check(_lib.lib().nb200_session_submit(
+            self._h, int(slot), int(bool(upload_stack)), int(bound),
+            int(later[0]), int(later[1]), int(n), int(seed), int(offset),
+            int(stream_id), int(like_id), par, n_par, float(log_l_min),
+            int(mode)))
+
+    def wait(self, slot):
+        """dict(points f64[k,d], log_l f64[k] | None, lse f64[4],
+        counters i64[8]) for the batch submitted on ``slot``."""
+        p_pts, p_ll = ctypes.c_void_p(), ctypes.c_void_p()
+        k = ctypes.c_int64()
+        lse = np.empty(N_LSE)
+        counters = np.empty(N_CNT, dtype=np.int64)
+        _lib.check(_lib.lib().nb200_session_wait(
+            self._h, int(slot), ctypes.byref(p_pts), ctypes.byref(p_ll),
+            ctypes.byref(k), lse.ctypes.data_as(ctypes.c_void_p),
+            counters.ctypes.data_as(ctypes.c_void_p)))
+        k = int(k.value)
+        d = self.n_dim
+
+        def view(ptr, shape):
+            if not ptr.value or k == 0:
+                return np.empty(shape)
+            buf = (ctypes.c_double * int(np.prod(shape))).from_address(
+                ptr.value)
+            return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+        return dict(points=view(p_pts, (k, d)),
+                    log_l=view(p_ll, (k,)) if p_ll.value else None,
+                    lse=lse, counters=counters)
+
+    def close(self):
+        if self._h:
+            _lib.lib().nb200_session_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # -- single-ellipsoid primitives -------------------------------------------
 
 def ell_transform(points, c, M, inverse=False):
