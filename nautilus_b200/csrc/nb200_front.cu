@@ -34,7 +34,19 @@ struct FrontArgs {
   unsigned long long seed, offset;
   unsigned int stream_id;
   long long n;
+  // optional: built-in likelihood of the rows that are still candidates
+  // after the ellipsoid tests (log_l == nullptr: off); NaN for the others
+  int like_id;
+  const double* like_p;
+  double* log_l;
 };
+
+// kept out of line so that the four likelihood bodies do not take part in
+// the register allocation of the matrix-vector loops
+__device__ __noinline__ double front_loglike(int like_id, const double* p,
+                                             const double* x, int d) {
+  return loglike_eval(like_id, p, x, d);
+}
 
 // acc[r] = sum_{j < jmax} MT[j][i0 + r] * v_j,  v_j = x[j] - (c ? c[j] : 0)
 template <bool SUBTRACT>
@@ -222,6 +234,10 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
       }
       code[i] = cd;
       maskj[i] = in_ell ? 1 : 0;
+      if (A.log_l)
+        A.log_l[i] = cd == NB200_CODE_IN_SHELL
+                         ? front_loglike(A.like_id, A.like_p, x, d)
+                         : nan("");
     }
     __syncthreads();
     store_rows(points, base, nrows, d, stride, rows);
@@ -262,11 +278,13 @@ bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
 int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  const double* data_d, int bound, int64_t n, uint64_t seed,
                  uint64_t offset, uint32_t stream_id, double* points,
-                 uint8_t* code, uint8_t* maskj, float* xs32, cudaStream_t st) {
+                 uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
+                 const double* like_p, double* log_l, cudaStream_t st) {
   FrontArgs A;
   size_t smem = 0;
   NB_CHECK(front_applicable(meta_h, bound, &smem, &A), "front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
+  A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
   NB_CUDA(cudaFuncSetAttribute(k_front,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));

@@ -705,16 +705,16 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
 int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
-                         const double* points, int like_id,
-                         const double* like_p, double log_l_min,
-                         double* log_l, void* partial, int* n_partial_out,
-                         cudaStream_t st);
+                         double log_l_min, double* log_l, void* partial,
+                         int* n_partial_out, cudaStream_t st);
+bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j);
 bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
                       struct FrontArgs* args);
 int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  const double* data_d, int bound, int64_t n, uint64_t seed,
                  uint64_t offset, uint32_t stream_id, double* points,
-                 uint8_t* code, uint8_t* maskj, float* xs32, cudaStream_t st);
+                 uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
+                 const double* like_p, double* log_l, cudaStream_t st);
 
 // emulator of neural bound j on whitened rows; ORs into passf and/or writes
 // the scores.
@@ -1117,24 +1117,29 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
   bool fused_tail = false;
   int n_partial = 0;
   if (fused) {
+    // without later bounds the likelihood and the shell sums ride along: the
+    // front kernel evaluates the likelihood of every row that is still a
+    // candidate (it holds the row on chip anyway), the emulator kernel sums
+    // the survivors
+    fused_tail = n_later == 0 && like_id >= 0 && lse_d && counters_d &&
+                 mlp_tf32_resident(meta_h, bound, 0);
     // 1+2 fused: proposal, cube cut, overlap acceptance, neural-ellipsoid
     // whitening and standardisation in one fp64 kernel, then the emulator on
     // tensor cores writes NN rejects straight into the disposition bytes
     rc = launch_front(meta_h, meta_d, data_d, bound, n, seed, offset,
-                      stream_id, points_d, code_d, ws.maskj, ws.xs32, st);
+                      stream_id, points_d, code_d, ws.maskj, ws.xs32,
+                      fused_tail ? like_id : -1, like_params_d,
+                      fused_tail ? log_l_d : nullptr, st);
     if (rc) return rc;
-    // without later bounds the likelihood and the shell sums ride along
-    fused_tail = n_later == 0 && like_id >= 0 && lse_d && counters_d;
     {
       ProfScope prof(ST_MLP, st);
       rc = launch_mlp_tf32_rows(
-          meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n, code_d, points_d,
-          like_id, like_params_d, log_l_min, log_l_d,
-          fused_tail ? (void*)ws.partial : nullptr, &n_partial, st);
+          meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n, code_d, log_l_min,
+          log_l_d, fused_tail ? (void*)ws.partial : nullptr, &n_partial, st);
     }
     if (rc) return rc;
-    if (fused_tail && n_partial == 0) fused_tail = false;  // streamed emulator
     if (fused_tail) {
+      NB_CHECK(n_partial > 0, "resident emulator kernel expected");
       ProfScope prof(ST_STATS, st);
       k_stats_final<<<1, STAT_THREADS, 0, st>>>(ws.partial, n_partial, lse_d,
                                                 (long long*)counters_d);

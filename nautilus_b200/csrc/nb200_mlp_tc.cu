@@ -47,16 +47,14 @@ struct TcHeader {            // int32[32] in the meta tail (_pack.py:pack_tc)
 };
 static_assert(sizeof(TcHeader) == TC_HDR_WORDS * 4, "header size");
 
-// Optional fused tail: built-in likelihood of the accepted points and the
-// per-block partials of the shell sums (nb200_stats), so that a cycle without
-// later bounds is front kernel -> this kernel -> one tiny final reduction.
+// Optional fused tail: the per-block partials of the shell sums (nb200_stats)
+// over the likelihoods k_front already evaluated (log_l, NaN for the rows it
+// rejected), so that a cycle without later bounds is front kernel -> this
+// kernel -> one tiny final reduction.  Rows this kernel rejects get NaN.
 struct TcTail {
-  const double* points;
-  const double* like_p;
   double* log_l;
   StatPartial* partial;     // nullptr: tail disabled
   double log_l_min;
-  int d, like_id;
 };
 
 // Debug timeline (clock64 stamps of the leader of group 0 in CTA 0), read
@@ -142,55 +140,65 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   mbar_wait(&wbar, 0);
 
+  // ---- MMA issue table: everything tcgen05.mma needs per layer, computed
+  // once (the timeline showed 600-900 cycles per issue when the descriptors
+  // were rebuilt from the header on the critical path) ----------------------
+  __shared__ uint4 mma_tab[TC_MAX_HID];       // {d_col, a_col, idesc, k steps}
+  __shared__ uint64_t desc_tab[TC_MAX_HID];   // weight descriptor of network 0
+  if (tid < h.n_hid) {
+    const int l = tid;
+    mma_tab[l] = make_uint4(
+        (uint32_t)h.d_col[l],
+        (uint32_t)(l == 0 ? h.a0_col : h.d_col[l - 1]),
+        idesc_tf32(h.np[l]), (uint32_t)(h.kp[l] >> 3));
+    desc_tab[l] = smem_desc(smem_u32(smem) + 4u * (uint32_t)h.w_off[l], 128u,
+                            (uint32_t)h.kp[l] * 32u);
+  }
+  __syncthreads();
+  // descriptor address field counts 16-byte units: + net * net_stride floats
+  const uint32_t net_step16 = (uint32_t)h.net_stride >> 2;
+
   Lse lse_acc;
   lse_acc.init();
-  int cnt32[NB200_N_CNT];
-#pragma unroll
-  for (int q = 0; q < NB200_N_CNT; ++q) cnt32[q] = 0;
+  int c_rej0 = 0, c_rej1 = 0, c_rej2 = 0, c_rej3 = 0, c_in = 0, c_upd = 0,
+      c_raw = 0;
 
   uint32_t phA = 0, phB = 0, phC = 0;
   const int64_t n_tiles = (n + 127) / 128;
   const int64_t tile_step = (int64_t)gridDim.x * n_groups;
   const int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g
                                      : n_tiles;
-  // the input row of the NEXT tile is fetched into registers while the
-  // current tile runs (k0p <= 32: 8 x 16 B per thread)
+  const bool with_tail = tail.partial != nullptr;
+  // The inputs of the NEXT tile are fetched into registers while the current
+  // tile runs: this half's 16 columns of the standardised row (k0p <= 32:
+  // 4 x 16 B), the candidate flag, and for the fused tail the disposition
+  // byte and the likelihood the front kernel already evaluated.  None of the
+  // loads depends on another one.
   const bool prefetch = h.k0p <= 32;
-  uint4 pre[4];                        // this half's 16 columns
-  auto fetch = [&](int64_t t, bool& act) {
+  uint4 pre[4];
+  uint32_t nx_mask = 0, nx_cd = NB200_CODE_IN_SHELL;
+  double nx_ll = 0.0;
+  auto fetch = [&](int64_t t) {
     const int64_t rw = t * 128 + r;
-    act = t < n_tiles && rw < n && (!mask || mask[rw]);
-    if (act) {
-      const uint4* src =
-          (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
+    nx_mask = 0;
+    if (t < n_tiles && rw < n) {
+      nx_mask = mask ? (uint32_t)mask[rw] : 1u;
+      if (with_tail && !hf) {
+        nx_cd = code[rw];
+        nx_ll = tail.log_l[rw];
+      }
+      if (prefetch) {
+        const uint4* src =
+            (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
-    }
-  };
-  bool next_active = false;
-  if (prefetch) fetch(tile0, next_active);
-  for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-    const int64_t row = tile * 128 + r;
-    bool active;
-
-    TL_STAMP(1);
-    // the fused tail will need this row's disposition and (if accepted) its
-    // fp64 coordinates ~30k cycles from now: read the byte, and pull the
-    // row's cache lines into L2 while the tensor pipe works
-    int cd_in = NB200_CODE_IN_SHELL;
-    if (tail.partial && !hf && row < n) {
-      cd_in = code[row];
-      if (cd_in == NB200_CODE_IN_SHELL) {
-        const char* rp = (const char*)(tail.points + row * (int64_t)tail.d);
-        const int bytes = tail.d * 8;
-        for (int o = 0; o < bytes; o += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+        for (int q = 0; q < 4; ++q)
+          if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
       }
     }
-    // ---- standardised input row -> TMEM (A operand of layer 0) ----------
+  };
+  // standardised input rows of tile t -> TMEM (A operand of layer 0)
+  auto stage_a0 = [&](int64_t t, bool active) {
     if (prefetch) {
-      active = next_active;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c = hf * 16 + q * 8;
@@ -203,11 +211,9 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
           tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
         }
       }
-      tmem_wait_st();
-      fetch(tile + tile_step, next_active);
     } else {
-      active = row < n && (!mask || mask[row]);
-      const uint4* src = (const uint4*)(xs32 + row * (int64_t)h.k0p);
+      const int64_t rw = t * 128 + r;
+      const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
       for (int c = hf * 8; c < h.k0p; c += 16) {
         uint32_t v[8];
         if (active) {
@@ -221,118 +227,172 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
         }
         tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
       }
-      tmem_wait_st();
     }
+  };
+
+  // ---- helpers ------------------------------------------------------------
+  // leader: issue layer l of network `net`, completion arrives on `bar`
+  auto issue = [&](int net, int l, uint64_t* bar) {
+    if (issuer_warp) {                 // warp-uniform branch
+      tc_fence_after();
+      if (elect_one()) {
+        const uint4 t = mma_tab[l];
+        const uint64_t desc0 =
+            desc_tab[l] + (uint64_t)((uint32_t)net * net_step16);
+        const uint32_t d_tmem = tmem_base_u + t.x;
+        const uint32_t a_tmem = tmem_base_u + t.y;
+        const int ks = (int)t.w;
+        for (int s = 0; s < ks; ++s) {
+          // one K-step = 2 core matrices = 256 B -> +16 in the 16-B units
+          // of the descriptor's start-address field
+          mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(s * 8),
+                      desc0 + (uint64_t)(s * 16), t.z, s > 0 ? 1u : 0u);
+        }
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+  // all: ReLU + tf32 rounding of layer l's accumulator, written back in
+  // place as the next layer's A operand (the bias was added by the MMA
+  // through the constant-one column, see _pack.py:pack_tc)
+  auto epi_hidden = [&](int l) {
+    tc_fence_after();
+    const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+    // 32 columns per TMEM load (the accumulator regions are 32-column
+    // aligned; pad columns meet zero weights), halves interleaved
+    for (int c = hf * 32; c < h.np[l]; c += 64) {
+      uint32_t v[32];
+      tmem_ld32(d_addr + (uint32_t)c, v);
+      tmem_wait_ld();
+      // ReLU, then round-half-up to tf32: the MMA reads only the top 19
+      // bits, so adding half an ulp of tf32 is the whole rounding
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
+      tmem_st32(d_addr + (uint32_t)c, v);
+    }
+    tmem_wait_st();
     tc_fence_before();
     group_sync(g);
-
-    // ---- helpers --------------------------------------------------------
-    // leader: issue layer l of network `net`, completion arrives on `bar`
-    auto issue = [&](int net, int l, uint64_t* bar) {
-      if (issuer_warp) {                 // warp-uniform branch
-        tc_fence_after();
-        const int np = h.np[l], kp = h.kp[l];
-        const uint32_t a_col = (l == 0) ? (uint32_t)h.a0_col
-                                        : (uint32_t)h.d_col[l - 1];
-        const uint32_t w_addr =
-            wsm_u + 4u * (uint32_t)(net * h.net_stride + h.w_off[l]);
-        const uint32_t idesc = idesc_tf32(np);
-        const uint32_t d_tmem = tmem_base_u + (uint32_t)h.d_col[l];
-        const uint32_t a_tmem = tmem_base_u + a_col;
-        const uint64_t desc0 = smem_desc(w_addr, 128u, (uint32_t)kp * 32u);
-        uint32_t elected = 0;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "elect.sync _|p, 0xffffffff;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(elected));
-        if (elected) {
-          const int ks = kp >> 3;
-          for (int s = 0; s < ks; ++s) {
-            // one K-step = 2 core matrices = 256 B -> +16 in the 16-B units
-            // of the descriptor's start-address field
-            mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(s * 8),
-                        desc0 + (uint64_t)(s * 16), idesc, s > 0 ? 1u : 0u);
-          }
-          mma_commit(bar);
+  };
+  // all: last hidden layer, the fan_out-1 output layer folded in registers
+  auto epi_last = [&](int net, int l) -> float {
+    tc_fence_after();
+    const float* wnet = wsm + (size_t)net * h.net_stride;
+    const float* wout = wnet + h.w_out_off;
+    const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+    float acc = hf ? 0.f : wnet[h.b_out_off];
+    for (int c = hf * 16; c < h.np[l]; c += 32) {
+      uint32_t v[16];
+      tmem_ld16(d_addr + (uint32_t)c, v);
+      // the output weights of these 16 columns: four broadcast LDS.128
+      const float4* w4 = reinterpret_cast<const float4*>(wout + c);
+      const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+      const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                           w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), w[q], acc);
+    }
+    if (hf) part[g][r] = acc;
+    // a later MMA overwrites these columns: order the loads before it
+    tc_fence_before();
+    group_sync(g);
+    return hf ? 0.f : acc + part[g][r];
+  };
+  // half 0: score -> decision -> outputs of one row, and with the fused tail
+  // the disposition histogram and the log-sum-exp of the likelihood that
+  // k_front evaluated for this row
+  auto finalize = [&](int64_t tile, float sum, bool active, uint32_t cd_in,
+                      double ll) {
+    const int64_t row = tile * 128 + r;
+    bool accepted = false;
+    if (active) {
+      const double score = (double)(sum / (float)h.n_net);
+      accepted = score > thr;
+      if (score_out) score_out[row] = score;
+      if (passf && accepted) passf[row] = 1;
+      if (code && !accepted) code[row] = NB200_CODE_NN_REJECT;
+    } else if (score_out && row < n) {
+      score_out[row] = nan("");
+    }
+    if (with_tail && row < n) {
+      c_raw += 1;
+      if (active ? accepted : cd_in == NB200_CODE_IN_SHELL) {
+        lse_acc.add(ll);
+        c_in += 1;
+        if (ll >= tail.log_l_min) c_upd += 1;
+      } else {
+        if (active) {
+          tail.log_l[row] = nan("");      // the front's value is void now
+          c_rej2 += 1;
+        } else {
+          c_rej0 += cd_in == NB200_CODE_CUBE_REJECT;
+          c_rej1 += cd_in == NB200_CODE_OVERLAP_REJECT;
+          c_rej2 += cd_in == NB200_CODE_NN_REJECT;
+          c_rej3 += cd_in == NB200_CODE_EXCLUDED;
         }
-        __syncwarp();
       }
-    };
-    // all: ReLU + tf32 rounding of layer l's accumulator, written back in
-    // place as the next layer's A operand (the bias was added by the MMA
-    // through the constant-one column, see _pack.py:pack_tc)
-    auto epi_hidden = [&](int l) {
-      tc_fence_after();
-      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-      // 32 columns per TMEM load (the accumulator regions are 32-column
-      // aligned; pad columns meet zero weights), halves interleaved, so the
-      // TMEM read latency is exposed once per 32 columns
-      for (int c = hf * 32; c < h.np[l]; c += 64) {
-        uint32_t v[32];
-        tmem_ld32(d_addr + (uint32_t)c, v);
-        tmem_wait_ld();
-        // ReLU, then round-half-up to tf32: the MMA reads only the top 19
-        // bits, so adding half an ulp of tf32 is the whole rounding
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
-        tmem_st32(d_addr + (uint32_t)c, v);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      group_sync(g);
-    };
-    // all: last hidden layer, the fan_out-1 output layer folded in registers
-    auto epi_last = [&](int net, int l) -> float {
-      tc_fence_after();
-      const float* wnet = wsm + (size_t)net * h.net_stride;
-      const float* wout = wnet + h.w_out_off;
-      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-      float acc = hf ? 0.f : wnet[h.b_out_off];
-      for (int c = hf * 16; c < h.np[l]; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(d_addr + (uint32_t)c, v);
-        // the output weights of these 16 columns: four broadcast LDS.128
-        const float4* w4 = reinterpret_cast<const float4*>(wout + c);
-        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-        const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                             w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-        tmem_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), w[q], acc);
-      }
-      if (hf) part[g][r] = acc;
-      // a later MMA overwrites these columns: order the loads before it
-      tc_fence_before();
-      group_sync(g);
-      return hf ? 0.f : acc + part[g][r];
-    };
+    }
+  };
 
-    float sum = 0.f;
-    if (h.n_hid == 3) {
-      // Two networks in flight per group: while the CUDA cores run one
-      // network's epilogue, the tensor pipe runs the other's next layer.
-      //   L0(n+1) || epilogue1(n),  L2(n) || epilogue0(n+1),
-      //   L1(n+1) || epilogue2(n)
-      uint64_t* bA = &mbar[g * 3 + 0];
-      uint64_t* bB = &mbar[g * 3 + 1];
-      uint64_t* bC = &mbar[g * 3 + 2];
+  uint64_t* bA = &mbar[g * 3 + 0];
+  uint64_t* bB = &mbar[g * 3 + 1];
+  uint64_t* bC = &mbar[g * 3 + 2];
+  fetch(tile0);
+  if (h.n_hid == 3) {
+    // One continuous stream of (tile, network) instances per group, two in
+    // flight: while the CUDA cores run one instance's epilogue the tensor
+    // pipe runs the other's next layer,
+    //   L0(i+1) || epilogue1(i),  L2(i) || epilogue0(i+1),
+    //   L1(i+1) || epilogue2(i),
+    // and the stream does not drain at tile boundaries: the next tile's
+    // input rows go to TMEM as soon as the last network of this tile has
+    // consumed the old ones.
+    int64_t tile = tile0;
+    bool have = tile < n_tiles;
+    bool cur_active = false, hold_active = false;
+    uint32_t cur_cd = NB200_CODE_IN_SHELL, hold_cd = NB200_CODE_IN_SHELL;
+    double cur_ll = 0.0, hold_ll = 0.0;
+    if (have) {
+      TL_STAMP(1);
+      cur_active = nx_mask != 0; cur_cd = nx_cd; cur_ll = nx_ll;
+      stage_a0(tile, cur_active);
+      tmem_wait_st();
+      fetch(tile + tile_step);
+      tc_fence_before();
+      group_sync(g);
       TL_STAMP(2);
       issue(0, 0, bA);
-      TL_STAMP(3);
       mbar_wait(bA, phA); phA ^= 1u;
-      TL_STAMP(4);
       epi_hidden(0);
-      TL_STAMP(5);
       issue(0, 1, bB);
+    }
+    while (have) {
+      const int64_t next_tile = tile + tile_step;
+      const bool have_next = next_tile < n_tiles;
+      float sum = 0.f;
       for (int net = 0; net < h.n_net; ++net) {
-        const bool more = net + 1 < h.n_net;
+        const bool last = net + 1 == h.n_net;
+        const bool more = !last || have_next;
+        const int nn = last ? 0 : net + 1;
         TL_STAMP(10);
-        mbar_wait(bB, phB); phB ^= 1u;       // D1(net) ready, region 0 free
+        mbar_wait(bB, phB); phB ^= 1u;     // D1(i) ready, region 0 free
         TL_STAMP(11);
-        if (more) issue(net + 1, 0, bA);
+        if (last && have_next) {
+          // every network of this tile has read the input rows: stage the
+          // next tile's
+          hold_active = nx_mask != 0; hold_cd = nx_cd; hold_ll = nx_ll;
+          stage_a0(next_tile, hold_active);
+          tmem_wait_st();
+          fetch(next_tile + tile_step);
+          tc_fence_before();
+          group_sync(g);
+          TL_STAMP(1);
+        }
+        if (more) issue(nn, 0, bA);
         TL_STAMP(12);
         epi_hidden(1);
         TL_STAMP(13);
@@ -344,15 +404,29 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
           epi_hidden(0);
           TL_STAMP(16);
         }
-        mbar_wait(bC, phC); phC ^= 1u;       // D2(net) ready, region 1 free
+        mbar_wait(bC, phC); phC ^= 1u;     // D2(i) ready, region 1 free
         TL_STAMP(17);
-        if (more) issue(net + 1, 1, bB);
+        if (more) issue(nn, 1, bB);
         TL_STAMP(18);
         sum += epi_last(net, 2);
         TL_STAMP(19);
       }
-    } else {
-      uint64_t* bA = &mbar[g * 3 + 0];
+      if (!hf) finalize(tile, sum, cur_active, cur_cd, cur_ll);
+      tile = next_tile;
+      have = have_next;
+      cur_active = hold_active; cur_cd = hold_cd; cur_ll = hold_ll;
+    }
+  } else {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+      const bool active = nx_mask != 0;
+      const uint32_t cd_in = nx_cd;
+      const double ll = nx_ll;
+      stage_a0(tile, active);
+      tmem_wait_st();
+      fetch(tile + tile_step);
+      tc_fence_before();
+      group_sync(g);
+      float sum = 0.f;
       for (int net = 0; net < h.n_net; ++net) {
         for (int l = 0; l < h.n_hid; ++l) {
           issue(net, l, bA);
@@ -361,43 +435,21 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
           else sum += epi_last(net, l);
         }
       }
-    }
-    if (hf) continue;                 // results are written by half 0
-    bool accepted = false;
-    if (active) {
-      const double score = (double)(sum / (float)h.n_net);
-      accepted = score > thr;
-      if (score_out) score_out[row] = score;
-      if (passf && accepted) passf[row] = 1;
-      if (code && !accepted) code[row] = NB200_CODE_NN_REJECT;
-    } else if (score_out && row < n) {
-      score_out[row] = nan("");
-    }
-    if (tail.partial && row < n) {
-      // disposition histogram, likelihood and log-sum-exp of this row
-      const int cd = active ? (accepted ? NB200_CODE_IN_SHELL
-                                        : NB200_CODE_NN_REJECT)
-                            : cd_in;
-      cnt32[NB200_CNT_RAW] += 1;
-      if (cd == NB200_CODE_IN_SHELL) {
-        const double ll = loglike_eval(tail.like_id, tail.like_p,
-                                       tail.points + row * (int64_t)tail.d,
-                                       tail.d);
-        tail.log_l[row] = ll;
-        lse_acc.add(ll);
-        cnt32[NB200_CNT_IN_SHELL] += 1;
-        if (ll >= tail.log_l_min) cnt32[NB200_CNT_UPDATE] += 1;
-      } else {
-        tail.log_l[row] = nan("");
-        cnt32[1 + cd] += 1;
-      }
+      if (!hf) finalize(tile, sum, active, cd_in, ll);
     }
   }
 
   if (tail.partial) {
     long long cnt[NB200_N_CNT];
 #pragma unroll
-    for (int q = 0; q < NB200_N_CNT; ++q) cnt[q] = cnt32[q];
+    for (int q = 0; q < NB200_N_CNT; ++q) cnt[q] = 0;
+    cnt[NB200_CNT_RAW] = c_raw;
+    cnt[NB200_CNT_CUBE_REJECT] = c_rej0;
+    cnt[NB200_CNT_OVERLAP_REJECT] = c_rej1;
+    cnt[NB200_CNT_NN_REJECT] = c_rej2;
+    cnt[NB200_CNT_EXCLUDED] = c_rej3;
+    cnt[NB200_CNT_IN_SHELL] = c_in;
+    cnt[NB200_CNT_UPDATE] = c_upd;
     stat_block_reduce<TC_GROUPS * TC_GROUP_THREADS>(
         lse_acc, cnt, tail.partial + blockIdx.x);
   }
@@ -488,6 +540,17 @@ static int tc_header(const int32_t* meta_h, int bound, int j, TcHeader* h) {
   return 0;
 }
 
+// does neural bound j of `bound` run on the resident tensor-core kernel (the
+// one that can carry the fused tail)?
+bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j) {
+  const Rec rec = record(meta_h, bound);
+  const int32_t* nb = rec.nb(j);
+  if (nb[10] < 0 || nb[11] <= 0) return false;
+  TcHeader h;
+  memcpy(&h, rec.r + nb[11], sizeof(h));
+  return (h.magic & 0xFFFF) == 0x7F32 && (h.magic >> 16) >= 1;
+}
+
 // whitened fp64 rows in, scores / pass flags out
 int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
                     int j, const double* t_rows, const uint8_t* mask,
@@ -514,18 +577,15 @@ int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
 int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
-                         const double* points, int like_id,
-                         const double* like_p, double log_l_min,
-                         double* log_l, void* partial, int* n_partial_out,
-                         cudaStream_t st) {
+                         double log_l_min, double* log_l, void* partial,
+                         int* n_partial_out, cudaStream_t st) {
   TcHeader h;
   if (tc_header(meta_h, bound, j, &h)) return 1;
   const Rec rec = record(meta_h, bound);
   TcTail tail;
   memset(&tail, 0, sizeof(tail));
-  tail.points = points; tail.like_p = like_p; tail.log_l = log_l;
+  tail.log_l = log_l;
   tail.partial = (StatPartial*)partial; tail.log_l_min = log_l_min;
-  tail.d = rec.d(); tail.like_id = like_id;
   if ((h.magic >> 16) == 0) tail.partial = nullptr;   // streamed: no tail
   return run_mlp_tf32(h, (const float*)(data_d + rec.nb(j)[10]), xs32, mask,
                       n, nullptr, nullptr, code, tail, n_partial_out, st);
