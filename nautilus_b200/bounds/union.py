@@ -84,9 +84,10 @@ class Union(_DeviceBound):
                                            -np.inf)))
             pts = self.points_bounds[index]
             whitened = self.bounds[index].transform(pts)
-            log_p = _construct.two_gaussians(
+            # EM of all restarts advanced together on the device
+            log_p = _construct.two_gaussians_batched(
                 whitened, np.random.default_rng(
-                    self.rng.integers(2**32 - 1)))
+                    self.rng.integers(2**32 - 1)), device=default_device())
             labels = np.argmax(log_p, axis=1)
             counts = np.bincount(labels, minlength=2)
             if np.any(counts < self.n_points_min):

@@ -22,7 +22,9 @@
 
 namespace nb200 {
 
-constexpr int FRONT_THREADS = 256;
+constexpr int FRONT_THREADS = 128;
+constexpr int FRONT_PTS = 2;     // proposals per thread (register blocking)
+constexpr int FRONT_TILE = FRONT_THREADS * FRONT_PTS;
 
 struct FrontArgs {
   int rec_off, d, d8, K, unit, k0p, stride;
@@ -48,41 +50,41 @@ __device__ __noinline__ double front_loglike(int like_id, const double* p,
   return loglike_eval(like_id, p, x, d);
 }
 
-// acc[r] = sum_{j < jmax} MT[j][i0 + r] * v_j,  v_j = x[j] - (c ? c[j] : 0)
-template <bool SUBTRACT>
-__device__ __forceinline__ void mv8(const double* __restrict__ MT, int d8,
-                                    int i0, int jmax, const double* x,
-                                    const double* __restrict__ c,
-                                    double (&acc)[8]) {
+// The kernel is bound by shared-memory wavefronts (ncu: 81 % of the LSU data
+// pipe with one proposal per thread), so every thread carries TWO proposals
+// through the matrix-vector products: the eight factor entries of a step
+// (4 x LDS.128) are loaded once and feed 16 DFMA.
+//
+// acc_p[r] = sum_{j < jmax} MT[j][i0 + r] * v_pj,
+//   v_pj = x_p[j] * s_p          (SCALE: the radial factor of the ball draw)
+//   v_pj = x_p[j] - c[j]         (SUBTRACT: whitening)
+template <bool SUBTRACT, bool SCALE>
+__device__ __forceinline__ void mv8x2(const double* __restrict__ MT, int d8,
+                                      int i0, int jmax, const double* x0,
+                                      const double* x1,
+                                      const double* __restrict__ c, double s0,
+                                      double s1, double (&a0)[8],
+                                      double (&a1)[8]) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+  for (int r = 0; r < 8; ++r) { a0[r] = 0.0; a1[r] = 0.0; }
   const double2* col = reinterpret_cast<const double2*>(MT + i0);
   const int ld = d8 >> 1;   // double2 per transposed row
 #pragma unroll 2
   for (int j = 0; j < jmax; ++j) {
-    const double v = SUBTRACT ? x[j] - c[j] : x[j];
+    double v0 = x0[j], v1 = x1[j];
+    if (SUBTRACT) { const double cj = c[j]; v0 -= cj; v1 -= cj; }
+    if (SCALE) { v0 *= s0; v1 *= s1; }
     const double2 m0 = col[j * ld], m1 = col[j * ld + 1];
     const double2 m2 = col[j * ld + 2], m3 = col[j * ld + 3];
-    acc[0] = fma(m0.x, v, acc[0]); acc[1] = fma(m0.y, v, acc[1]);
-    acc[2] = fma(m1.x, v, acc[2]); acc[3] = fma(m1.y, v, acc[3]);
-    acc[4] = fma(m2.x, v, acc[4]); acc[5] = fma(m2.y, v, acc[5]);
-    acc[6] = fma(m3.x, v, acc[6]); acc[7] = fma(m3.y, v, acc[7]);
+    a0[0] = fma(m0.x, v0, a0[0]); a1[0] = fma(m0.x, v1, a1[0]);
+    a0[1] = fma(m0.y, v0, a0[1]); a1[1] = fma(m0.y, v1, a1[1]);
+    a0[2] = fma(m1.x, v0, a0[2]); a1[2] = fma(m1.x, v1, a1[2]);
+    a0[3] = fma(m1.y, v0, a0[3]); a1[3] = fma(m1.y, v1, a1[3]);
+    a0[4] = fma(m2.x, v0, a0[4]); a1[4] = fma(m2.x, v1, a1[4]);
+    a0[5] = fma(m2.y, v0, a0[5]); a1[5] = fma(m2.y, v1, a1[5]);
+    a0[6] = fma(m3.x, v0, a0[6]); a1[6] = fma(m3.x, v1, a1[6]);
+    a0[7] = fma(m3.y, v0, a0[7]); a1[7] = fma(m3.y, v1, a1[7]);
   }
-}
-
-// r2 = sum_i (sum_j Binv[i][j] (x_j - c_j))^2, rows in increasing order
-__device__ __forceinline__ double r2_staged(const double* __restrict__ MT,
-                                            int d, int d8, int lower,
-                                            const double* x,
-                                            const double* __restrict__ c) {
-  double r2 = 0.0;
-  for (int i0 = 0; i0 < d8; i0 += 8) {
-    double acc[8];
-    mv8<true>(MT, d8, i0, lower ? min(i0 + 8, d) : d, x, c, acc);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) r2 = fma(acc[r], acc[r], r2);  // pad rows: 0
-  }
-  return r2;
 }
 
 __global__ void __launch_bounds__(FRONT_THREADS, 2)
@@ -102,7 +104,7 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
   double* cN = cK + (size_t)K * d8;        // d8
   double* meanN = cN + d8;                 // d8
   double* iscaleN = meanN + d8;            // d8: 1 / scale
-  double* rows = iscaleN + d8;             // FRONT_THREADS x stride
+  double* rows = iscaleN + d8;             // FRONT_TILE x stride
   const int32_t* nb = rec.nb(0);
 
   for (int e = threadIdx.x; e < (2 * K + 1) * mat; e += FRONT_THREADS) {
@@ -129,115 +131,211 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
 
   const double* cdf = data + rec.off_cdf();
   const int stride = A.stride;
-  double* x = rows + threadIdx.x * stride;
-  const long long n_tiles = (A.n + FRONT_THREADS - 1) / FRONT_THREADS;
+  // proposal p of this thread is local row p * FRONT_THREADS + threadIdx.x
+  // (consecutive threads -> consecutive rows: conflict-free 64-bit accesses)
+  double* xr[FRONT_PTS];
+#pragma unroll
+  for (int p = 0; p < FRONT_PTS; ++p)
+    xr[p] = rows + (p * FRONT_THREADS + (int)threadIdx.x) * stride;
+  const long long n_tiles = (A.n + FRONT_TILE - 1) / FRONT_TILE;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long base = tile * FRONT_THREADS;
-    const int nrows = (int)min((long long)FRONT_THREADS, A.n - base);
-    const long long i = base + threadIdx.x;
-    if ((int)threadIdx.x < nrows) {
-      const Philox rng(A.offset + (unsigned long long)i, A.stream_id, A.seed);
-      const uint4 w0 = rng.block(0);
-      const double uk = u01_32(w0.x);
-      int k = 0;
-      while (k < K - 1 && !(uk < __ldg(cdf + k))) ++k;
-      const double r = u01_32(w0.y);
-      const double u = u01_53(w0.z, w0.w);
-      // normals -> uniform point of the unit ball (basic.py:376-379)
-      double n2 = 0.0;
-      for (int j = 0; j < d; j += 4) {
-        const uint4 w = rng.block(1 + (j >> 2));
-        float g0, g1, g2, g3;
-        normal2(w.x, w.y, g0, g1);
-        normal2(w.z, w.w, g2, g3);
-        const float gq[4] = {g0, g1, g2, g3};
+    const long long base = tile * FRONT_TILE;
+    const int nrows = (int)min((long long)FRONT_TILE, A.n - base);
+    long long gi[FRONT_PTS];
+    bool valid[FRONT_PTS];
+    int kq[FRONT_PTS];
+    double rq[FRONT_PTS], sq[FRONT_PTS];
+    // ---- normals -> direction and radial factor of a uniform point of the
+    // unit ball (basic.py:376-379); the row holds the raw normals, the factor
+    // scale = u^(1/d) / |z| is applied on the fly in the product below -------
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (j + q < d) {
-            const double v = (double)gq[q];
-            x[j + q] = v;
-            n2 = fma(v, v, n2);
+    for (int p = 0; p < FRONT_PTS; ++p) {
+      const int li = p * FRONT_THREADS + (int)threadIdx.x;
+      gi[p] = base + li;
+      valid[p] = li < nrows;
+      kq[p] = 0; rq[p] = 0.0; sq[p] = 0.0;
+      double* x = xr[p];
+      if (valid[p]) {
+        const Philox rng(A.offset + (unsigned long long)gi[p], A.stream_id,
+                         A.seed);
+        const uint4 w0 = rng.block(0);
+        const double uk = u01_32(w0.x);
+        int k = 0;
+        while (k < K - 1 && !(uk < __ldg(cdf + k))) ++k;
+        kq[p] = k;
+        rq[p] = u01_32(w0.y);
+        const double u = u01_53(w0.z, w0.w);
+        double n2 = 0.0;
+        for (int j = 0; j < d; j += 4) {
+          const uint4 w = rng.block(1 + (j >> 2));
+          float g0, g1, g2, g3;
+          normal2(w.x, w.y, g0, g1);
+          normal2(w.z, w.w, g2, g3);
+          const float gq[4] = {g0, g1, g2, g3};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (j + q < d) {
+              const double v = (double)gq[q];
+              x[j + q] = v;
+              n2 = fma(v, v, n2);
+            }
+          }
+        }
+        sq[p] = pow(u, 1.0 / (double)d) / sqrt(n2);
+      } else {
+        for (int j = 0; j < d; ++j) x[j] = 0.0;
+      }
+    }
+    // ---- x = B (z * scale) + c in place (basic.py:380 -> :342), highest row
+    // group first; the unit-cube test (union.py:313-314) runs on the
+    // registers as the coordinates are produced ------------------------------
+    bool in_cube[FRONT_PTS] = {true, true};
+    if (kq[0] == kq[1]) {
+      const double* Bk = BT + (size_t)kq[0] * mat;
+      const double* ck = cK + kq[0] * d8;
+      for (int i0 = d8 - 8; i0 >= 0; i0 -= 8) {
+        double a0[8], a1[8];
+        mv8x2<false, true>(Bk, d8, i0, min(i0 + 8, d), xr[0], xr[1], nullptr,
+                           sq[0], sq[1], a0, a1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (i0 + q < d) {
+            const double cq = ck[i0 + q];
+            const double v0 = a0[q] + cq, v1 = a1[q] + cq;
+            xr[0][i0 + q] = v0; xr[1][i0 + q] = v1;
+            in_cube[0] = in_cube[0] && (v0 >= 0.0) && (v0 < 1.0);
+            in_cube[1] = in_cube[1] && (v1 >= 0.0) && (v1 < 1.0);
           }
         }
       }
-      const double scale = pow(u, 1.0 / (double)d) / sqrt(n2);
-      for (int j = 0; j < d; ++j) x[j] *= scale;
-      // x = B y + c in place (basic.py:380 -> :342), highest row group first
-      {
-        const double* Bk = BT + (size_t)k * mat;
-        const double* ck = cK + k * d8;
+    } else {
+      // the two proposals picked different ellipsoids: one factor each (the
+      // second operand of the pair is a dummy)
+#pragma unroll
+      for (int p = 0; p < FRONT_PTS; ++p) {
+        const double* Bk = BT + (size_t)kq[p] * mat;
+        const double* ck = cK + kq[p] * d8;
         for (int i0 = d8 - 8; i0 >= 0; i0 -= 8) {
-          double acc[8];
-          mv8<false>(Bk, d8, i0, min(i0 + 8, d), x, nullptr, acc);
+          double a0[8], a1[8];
+          mv8x2<false, true>(Bk, d8, i0, min(i0 + 8, d), xr[p], xr[p], nullptr,
+                             sq[p], sq[p], a0, a1);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (i0 + q < d) {
+              const double v0 = a0[q] + ck[i0 + q];
+              xr[p][i0 + q] = v0;
+              in_cube[p] = in_cube[p] && (v0 >= 0.0) && (v0 < 1.0);
+            }
+          }
+        }
+      }
+    }
+    // ---- dispositions ------------------------------------------------------
+    uint8_t cd[FRONT_PTS];
+    bool alive[FRONT_PTS];    // still needs ellipsoid tests
+#pragma unroll
+    for (int p = 0; p < FRONT_PTS; ++p) {
+      cd[p] = NB200_CODE_IN_SHELL;
+      if (A.unit && !in_cube[p]) cd[p] = NB200_CODE_CUBE_REJECT;
+      alive[p] = valid[p] && cd[p] == NB200_CODE_IN_SHELL;
+    }
+    // whitening w.r.t. the neural bound's ellipsoid: r2 and the standardised,
+    // tf32-rounded emulator input row (with the constant-one bias column at
+    // index d), for the proposals flagged in `want`
+    double r2_nb[FRONT_PTS] = {-1.0, -1.0};
+    auto whiten_store = [&](const bool (&want)[FRONT_PTS]) {
+      if (!(want[0] || want[1])) return;
+      float* xrow0 = xs32 + gi[0] * (long long)A.k0p;
+      float* xrow1 = xs32 + gi[1] * (long long)A.k0p;
+      double r20 = 0.0, r21 = 0.0;
+      for (int i0 = 0; i0 < A.k0p; i0 += 8) {
+        uint32_t pk0[8], pk1[8];
+        if (i0 < d8) {
+          double a0[8], a1[8];
+          mv8x2<true, false>(nbT, d8, i0, A.lower_n ? min(i0 + 8, d) : d,
+                             xr[0], xr[1], cN, 0.0, 0.0, a0, a1);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            r20 = fma(a0[q], a0[q], r20);
+            r21 = fma(a1[q], a1[q], r21);
+            const double mq = meanN[i0 + q], iq = iscaleN[i0 + q];
+            float v0 = (float)((a0[q] - mq) * iq);
+            float v1 = (float)((a1[q] - mq) * iq);
+            if (i0 + q == d) { v0 = 1.0f; v1 = 1.0f; }
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk0[q]) : "f"(v0));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk1[q]) : "f"(v1));
+          }
+        } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (i0 + q < d) x[i0 + q] = acc[q] + ck[i0 + q];
+            pk0[q] = pk1[q] = (i0 + q == d) ? 0x3F800000u : 0u;
+        }
+        if (want[0]) {
+          *reinterpret_cast<uint4*>(xrow0 + i0) =
+              make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+          *reinterpret_cast<uint4*>(xrow0 + i0 + 4) =
+              make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
+        }
+        if (want[1]) {
+          *reinterpret_cast<uint4*>(xrow1 + i0) =
+              make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+          *reinterpret_cast<uint4*>(xrow1 + i0 + 4) =
+              make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
         }
       }
-      uint8_t cd = NB200_CODE_IN_SHELL;
-      bool in_ell = false;
-      float* xrow = xs32 + i * (long long)A.k0p;
-      // whitening w.r.t. the neural bound's ellipsoid: r2 and the
-      // standardised, tf32-rounded emulator input row (with the constant-one
-      // bias column at index d)
-      auto whiten_store = [&]() -> double {
-        double r2 = 0.0;
-        for (int i0 = 0; i0 < A.k0p; i0 += 8) {
-          uint32_t pk[8];
-          if (i0 < d8) {
-            double acc[8];
-            mv8<true>(nbT, d8, i0, A.lower_n ? min(i0 + 8, d) : d, x, cN, acc);
+      if (want[0]) r2_nb[0] = r20;
+      if (want[1]) r2_nb[1] = r21;
+    };
+    // overlap count n_bound = sum_k contains_k (union.py:316-317)
+    if (alive[0] || alive[1]) {
+      int nbnd[FRONT_PTS] = {0, 0};
+      for (int kk = 0; kk < K; ++kk) {
+        double r20, r21;
+        if (kk == A.same_k) {
+          whiten_store(alive);      // same ellipsoid: one pass serves both
+          r20 = r2_nb[0]; r21 = r2_nb[1];
+        } else {
+          const double* MT = BinvT + (size_t)kk * mat;
+          const int lower = (A.lower_k >> kk) & 1;
+          r20 = 0.0; r21 = 0.0;
+          for (int i0 = 0; i0 < d8; i0 += 8) {
+            double a0[8], a1[8];
+            mv8x2<true, false>(MT, d8, i0, lower ? min(i0 + 8, d) : d, xr[0],
+                               xr[1], cK + kk * d8, 0.0, 0.0, a0, a1);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              r2 = fma(acc[q], acc[q], r2);
-              float v = (float)((acc[q] - meanN[i0 + q]) * iscaleN[i0 + q]);
-              if (i0 + q == d) v = 1.0f;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[q]) : "f"(v));
+            for (int q = 0; q < 8; ++q) {      // pad rows contribute 0
+              r20 = fma(a0[q], a0[q], r20);
+              r21 = fma(a1[q], a1[q], r21);
             }
-          } else {
+          }
+        }
+        nbnd[0] += r20 < 1.0 ? 1 : 0;
+        nbnd[1] += r21 < 1.0 ? 1 : 0;
+      }
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              pk[q] = (i0 + q == d) ? 0x3F800000u : 0u;
-          }
-          *reinterpret_cast<uint4*>(xrow + i0) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(xrow + i0 + 4) =
-              make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      for (int p = 0; p < FRONT_PTS; ++p)
+        if (alive[p] && !(rq[p] > 1.0 - 1.0 / (double)nbnd[p])) {
+          cd[p] = NB200_CODE_OVERLAP_REJECT;      // union.py:318-319
+          alive[p] = false;
         }
-        return r2;
-      };
-      double r2_nb = -1.0;
-      if (A.unit && !cube_ok(x, nullptr, d)) {
-        cd = NB200_CODE_CUBE_REJECT;                  // union.py:313-314
-      } else {
-        int nbnd = 0;                                 // union.py:316-317
-        for (int kk = 0; kk < K; ++kk) {
-          double r2;
-          if (kk == A.same_k) {
-            r2 = whiten_store();      // same ellipsoid: one pass serves both
-            r2_nb = r2;
-          } else {
-            r2 = r2_staged(BinvT + (size_t)kk * mat, d, d8,
-                           (A.lower_k >> kk) & 1, x, cK + kk * d8);
-          }
-          nbnd += r2 < 1.0 ? 1 : 0;
-        }
-        if (!(r > 1.0 - 1.0 / (double)nbnd))          // union.py:318-319
-          cd = NB200_CODE_OVERLAP_REJECT;
+      // NeuralBound: ellipsoid test (neural.py:117)
+      if (A.same_k < 0) whiten_store(alive);
+    }
+#pragma unroll
+    for (int p = 0; p < FRONT_PTS; ++p) {
+      if (!valid[p]) continue;
+      bool in_ell = false;
+      if (alive[p]) {
+        in_ell = r2_nb[p] < 1.0;
+        if (!in_ell) cd[p] = NB200_CODE_NN_REJECT;
       }
-      if (cd == NB200_CODE_IN_SHELL) {
-        // NeuralBound: ellipsoid test (neural.py:117)
-        if (A.same_k < 0) r2_nb = whiten_store();
-        in_ell = r2_nb < 1.0;
-        if (!in_ell) cd = NB200_CODE_NN_REJECT;
-      }
-      code[i] = cd;
-      maskj[i] = in_ell ? 1 : 0;
+      code[gi[p]] = cd[p];
+      maskj[gi[p]] = in_ell ? 1 : 0;
       if (A.log_l)
-        A.log_l[i] = cd == NB200_CODE_IN_SHELL
-                         ? front_loglike(A.like_id, A.like_p, x, d)
-                         : nan("");
+        A.log_l[gi[p]] = cd[p] == NB200_CODE_IN_SHELL
+                             ? front_loglike(A.like_id, A.like_p, xr[p], d)
+                             : nan("");
     }
     __syncthreads();
     store_rows(points, base, nrows, d, stride, rows);
@@ -261,7 +359,7 @@ bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   }
   const int d8 = (d + 7) / 8 * 8;
   const size_t doubles = (size_t)(2 * K + 1) * d * d8 + (size_t)(K + 3) * d8 +
-                         (size_t)FRONT_THREADS * (d | 1);
+                         (size_t)FRONT_TILE * (d | 1);
   if (doubles * 8 > 110 * 1024) return false;   // two CTAs per SM
   if (smem_out) *smem_out = doubles * 8;
   if (args) {
@@ -291,7 +389,7 @@ int launch_front(const int32_t* meta_h, const int32_t* meta_d,
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t n_tiles = (n + FRONT_THREADS - 1) / FRONT_THREADS;
+  const int64_t n_tiles = (n + FRONT_TILE - 1) / FRONT_TILE;
   int64_t grid = 2 * (int64_t)sms;
   if (grid > n_tiles) grid = n_tiles;
   ProfScope prof(ST_FUSED, st);

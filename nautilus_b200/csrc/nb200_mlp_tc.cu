@@ -57,24 +57,46 @@ struct TcTail {
   double log_l_min;
 };
 
-// Debug timeline (clock64 stamps of the leader of group 0 in CTA 0), read
-// back with nb200_debug_read(); compiled in only with -DNB200_TIMELINE.
+// Debug timeline: clock64 stamps of one epilogue thread (slot 0) and of the
+// MMA issuer (slot 1) of tile group 0 in CTA 0, read back with
+// nb200_debug_timeline(); compiled in only with -DNB200_TIMELINE.  The index
+// lives in a register so that a stamp is one fire-and-forget store.
 #ifdef NB200_TIMELINE
-__device__ long long g_tl[512];
-__device__ int g_tl_n;
+__device__ long long g_tl[2][1024];
+#define TL_DECL int tl_i = 0; const int tl_slot = threadIdx.x == 0 ? 0 : \
+    (threadIdx.x == TC_GROUPS * TC_GROUP_THREADS ? 1 : -1)
 #define TL_STAMP(tag)                                                   \
   do {                                                                  \
-    if (blockIdx.x == 0 && threadIdx.x == 0 && g_tl_n < 510) {          \
-      g_tl[g_tl_n++] = (long long)(tag);                                \
-      g_tl[g_tl_n++] = clock64();                                       \
+    if (blockIdx.x == 0 && tl_slot >= 0 && tl_i < 1022) {               \
+      g_tl[tl_slot][tl_i++] = (long long)(tag);                         \
+      g_tl[tl_slot][tl_i++] = clock64();                                \
     }                                                                   \
   } while (0)
 #else
+#define TL_DECL do {} while (0)
 #define TL_STAMP(tag) do {} while (0)
 #endif
 
+constexpr int TC_EPI_THREADS = TC_GROUPS * TC_GROUP_THREADS;   // 512
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_GROUPS;    // + issuers
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// the two threads that share a TMEM lane (warps w and w+4 of a group)
+__device__ __forceinline__ void pair_sync(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_GROUPS * TC_GROUP_THREADS, 1)
+// Warp-specialised: per tile group 8 epilogue warps (two threads per TMEM
+// lane) and ONE issuer warp.  They follow the same static schedule and meet
+// only through mbarriers: the issuer commits every layer's MMAs to bA/bB/bC,
+// the epilogue warps arrive on s0/s1/s2/sA when the operand they produced (or
+// the region they finished reading) is ready -- nobody waits at a CTA
+// barrier, a fast warp runs ahead.
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
            int64_t n, double* __restrict__ score_out,
@@ -82,16 +104,23 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
            const TcTail tail) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t wbar;
-  __shared__ uint64_t mbar[TC_GROUPS * 3];
+  __shared__ uint64_t mbar[TC_GROUPS * 3];    // MMA completion: bA, bB, bC
+  __shared__ uint64_t sbar[TC_GROUPS * 4];    // epilogue -> issuer: s0 s1 s2 sA
   __shared__ uint32_t tmem_slot;
   __shared__ float part[TC_GROUPS][128];
+  __shared__ uint4 mma_tab[TC_MAX_HID];       // {d_col, a_col, idesc, k steps}
+  __shared__ uint64_t desc_tab[TC_MAX_HID];   // weight descriptor of network 0
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int g = tid >> 8;            // tile group (8 warps)
+  const int lane = tid & 31;
+  const bool is_issuer = tid >= TC_EPI_THREADS;
+  // tile group: 8 epilogue warps each, then one issuer warp each
+  const int g = is_issuer ? (tid - TC_EPI_THREADS) >> 5 : tid >> 8;
   const int r = tid & 127;           // row in tile == TMEM lane
   const int hf = (tid >> 7) & 1;     // which half of the columns this thread
                                      // handles (warps w and w+4 share lanes)
+  TL_DECL;
 
   const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
   // architectures that need more than 256 TMEM columns run ONE tile group per
@@ -100,7 +129,19 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   if (tid == 0) {
     mbar_init(&wbar, 1);
     for (int q = 0; q < TC_GROUPS * 3; ++q) mbar_init(&mbar[q], 1);
+    // one arrival per epilogue warp
+    for (int q = 0; q < TC_GROUPS * 4; ++q) mbar_init(&sbar[q], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // MMA issue table: everything tcgen05.mma needs per layer, computed once
+  if (tid >= 64 && tid < 64 + h.n_hid) {
+    const int l = tid - 64;
+    mma_tab[l] = make_uint4(
+        (uint32_t)h.d_col[l],
+        (uint32_t)(l == 0 ? h.a0_col : h.d_col[l - 1]),
+        idesc_tf32(h.np[l]), (uint32_t)(h.kp[l] >> 3));
+    desc_tab[l] = smem_desc(smem_u32(smem) + 4u * (uint32_t)h.w_off[l], 128u,
+                            (uint32_t)h.kp[l] * 32u);
   }
   __syncthreads();
   float* wsm = (float*)smem;
@@ -127,116 +168,41 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
-  // Warp-uniform copies for the MMA issuer: values that come out of a
-  // shuffle are uniform to the compiler, so the operands of tcgen05.mma live
-  // in uniform registers instead of being moved there one by one (R2UR) --
-  // the timeline showed ~200 cycles per MMA issue before this.
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const bool issuer_warp = (warp_u & 7) == 0;          // first warp of a group
-  const uint32_t tmem_base_u =
-      __shfl_sync(0xffffffffu, tmem_slot, 0) +
-      (uint32_t)((warp_u >> 3) * TC_COLS_PER_GROUP);
-  const uint32_t wsm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   mbar_wait(&wbar, 0);
 
-  // ---- MMA issue table: everything tcgen05.mma needs per layer, computed
-  // once (the timeline showed 600-900 cycles per issue when the descriptors
-  // were rebuilt from the header on the critical path) ----------------------
-  __shared__ uint4 mma_tab[TC_MAX_HID];       // {d_col, a_col, idesc, k steps}
-  __shared__ uint64_t desc_tab[TC_MAX_HID];   // weight descriptor of network 0
-  if (tid < h.n_hid) {
-    const int l = tid;
-    mma_tab[l] = make_uint4(
-        (uint32_t)h.d_col[l],
-        (uint32_t)(l == 0 ? h.a0_col : h.d_col[l - 1]),
-        idesc_tf32(h.np[l]), (uint32_t)(h.kp[l] >> 3));
-    desc_tab[l] = smem_desc(smem_u32(smem) + 4u * (uint32_t)h.w_off[l], 128u,
-                            (uint32_t)h.kp[l] * 32u);
-  }
-  __syncthreads();
-  // descriptor address field counts 16-byte units: + net * net_stride floats
-  const uint32_t net_step16 = (uint32_t)h.net_stride >> 2;
+  uint64_t* bA = &mbar[g * 3 + 0];
+  uint64_t* bB = &mbar[g * 3 + 1];
+  uint64_t* bC = &mbar[g * 3 + 2];
+  uint64_t* s0 = &sbar[g * 4 + 0];   // epilogue 0 done: A of layer 1 ready
+  uint64_t* s1 = &sbar[g * 4 + 1];   // epilogue 1 done: A of layer 2 ready
+  uint64_t* s2 = &sbar[g * 4 + 2];   // last epilogue done: D2 region free
+  uint64_t* sA = &sbar[g * 4 + 3];   // input rows of a tile staged
+
+  const int64_t n_tiles = (n + 127) / 128;
+  const int64_t tile_step = (int64_t)gridDim.x * n_groups;
+  const int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g
+                                     : n_tiles;
+  // tiles this group processes
+  const int64_t my_tiles =
+      tile0 < n_tiles ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
 
   Lse lse_acc;
   lse_acc.init();
   int c_rej0 = 0, c_rej1 = 0, c_rej2 = 0, c_rej3 = 0, c_in = 0, c_upd = 0,
       c_raw = 0;
 
-  uint32_t phA = 0, phB = 0, phC = 0;
-  const int64_t n_tiles = (n + 127) / 128;
-  const int64_t tile_step = (int64_t)gridDim.x * n_groups;
-  const int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g
-                                     : n_tiles;
-  const bool with_tail = tail.partial != nullptr;
-  // The inputs of the NEXT tile are fetched into registers while the current
-  // tile runs: this half's 16 columns of the standardised row (k0p <= 32:
-  // 4 x 16 B), the candidate flag, and for the fused tail the disposition
-  // byte and the likelihood the front kernel already evaluated.  None of the
-  // loads depends on another one.
-  const bool prefetch = h.k0p <= 32;
-  uint4 pre[4];
-  uint32_t nx_mask = 0, nx_cd = NB200_CODE_IN_SHELL;
-  double nx_ll = 0.0;
-  auto fetch = [&](int64_t t) {
-    const int64_t rw = t * 128 + r;
-    nx_mask = 0;
-    if (t < n_tiles && rw < n) {
-      nx_mask = mask ? (uint32_t)mask[rw] : 1u;
-      if (with_tail && !hf) {
-        nx_cd = code[rw];
-        nx_ll = tail.log_l[rw];
-      }
-      if (prefetch) {
-        const uint4* src =
-            (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
-      }
-    }
-  };
-  // standardised input rows of tile t -> TMEM (A operand of layer 0)
-  auto stage_a0 = [&](int64_t t, bool active) {
-    if (prefetch) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = hf * 16 + q * 8;
-        if (c < h.k0p) {
-          uint32_t v[8];
-          const uint4 a = active ? pre[2 * q] : make_uint4(0, 0, 0, 0);
-          const uint4 b = active ? pre[2 * q + 1] : make_uint4(0, 0, 0, 0);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
-        }
-      }
-    } else {
-      const int64_t rw = t * 128 + r;
-      const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
-      for (int c = hf * 8; c < h.k0p; c += 16) {
-        uint32_t v[8];
-        if (active) {
-          const uint4 a = __ldg(src + (c >> 2));
-          const uint4 b = __ldg(src + (c >> 2) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = 0u;
-        }
-        tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
-      }
-    }
-  };
-
-  // ---- helpers ------------------------------------------------------------
-  // leader: issue layer l of network `net`, completion arrives on `bar`
-  auto issue = [&](int net, int l, uint64_t* bar) {
-    if (issuer_warp) {                 // warp-uniform branch
+  if (is_issuer) {
+    // =====================================================================
+    // MMA issuer: one elected lane issues, the warp stays converged
+    // =====================================================================
+    const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t net_step16 = (uint32_t)h.net_stride >> 2;
+    auto issue = [&](int net, int l, uint64_t* bar) {
       tc_fence_after();
       if (elect_one()) {
         const uint4 t = mma_tab[l];
+        // descriptor address field counts 16-byte units
         const uint64_t desc0 =
             desc_tab[l] + (uint64_t)((uint32_t)net * net_step16);
         const uint32_t d_tmem = tmem_base_u + t.x;
@@ -251,81 +217,199 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
         mma_commit(bar);
       }
       __syncwarp();
+    };
+    uint32_t p0 = 0, p1 = 0, p2 = 0, pA = 0;
+    const int N = h.n_net;
+    if (h.n_hid == 3) {
+      // instance i = (tile, network); MMAs execute in issue order, so region
+      // reuse between MMAs needs no wait -- only operands written by the
+      // epilogue warps do:
+      //   L1(i)   after epilogue0(i);  L0(i+1) right behind it (after the
+      //   next tile's rows are staged if i+1 opens a tile);
+      //   L2(i)   after epilogue1(i) and after the last epilogue of i-1 has
+      //   read the D2 region.
+      const int64_t M = my_tiles * N;
+      if (M > 0) {
+        mbar_wait(sA, pA); pA ^= 1u;
+        issue(0, 0, bA);
+      }
+      int net = 0;
+      for (int64_t i = 0; i < M; ++i) {
+        mbar_wait(s0, p0); p0 ^= 1u;
+        TL_STAMP(20);
+        issue(net, 1, bB);
+        const int nn = net + 1 == N ? 0 : net + 1;
+        if (i + 1 < M) {
+          if (nn == 0) { mbar_wait(sA, pA); pA ^= 1u; }
+          issue(nn, 0, bA);
+        }
+        TL_STAMP(21);
+        mbar_wait(s1, p1); p1 ^= 1u;
+        if (i > 0) { mbar_wait(s2, p2); p2 ^= 1u; }
+        TL_STAMP(22);
+        issue(net, 2, bC);
+        TL_STAMP(23);
+        net = nn;
+      }
+    } else {
+      // serial schedule: one layer at a time, s0 carries every hand-over
+      for (int64_t t = 0; t < my_tiles; ++t)
+        for (int net = 0; net < N; ++net)
+          for (int l = 0; l < h.n_hid; ++l) {
+            mbar_wait(s0, p0); p0 ^= 1u;
+            issue(net, l, bA);
+          }
     }
-  };
-  // all: ReLU + tf32 rounding of layer l's accumulator, written back in
-  // place as the next layer's A operand (the bias was added by the MMA
-  // through the constant-one column, see _pack.py:pack_tc)
-  auto epi_hidden = [&](int l) {
-    tc_fence_after();
-    const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-    // 32 columns per TMEM load (the accumulator regions are 32-column
-    // aligned; pad columns meet zero weights), halves interleaved
-    for (int c = hf * 32; c < h.np[l]; c += 64) {
-      uint32_t v[32];
-      tmem_ld32(d_addr + (uint32_t)c, v);
-      tmem_wait_ld();
-      // ReLU, then round-half-up to tf32: the MMA reads only the top 19
-      // bits, so adding half an ulp of tf32 is the whole rounding
+  } else {
+    // =====================================================================
+    // epilogue warps
+    // =====================================================================
+    const bool with_tail = tail.partial != nullptr;
+    // The inputs of the NEXT tile are fetched into registers while the
+    // current tile runs: this half's 16 columns of the standardised row
+    // (k0p <= 32: 4 x 16 B), the candidate flag, and for the fused tail the
+    // disposition byte and the likelihood the front kernel already
+    // evaluated.  None of the loads depends on another one.
+    const bool prefetch = h.k0p <= 32;
+    uint4 pre[4];
+    uint32_t nx_mask = 0, nx_cd = NB200_CODE_IN_SHELL;
+    double nx_ll = 0.0;
+    auto fetch = [&](int64_t t) {
+      const int64_t rw = t * 128 + r;
+      nx_mask = 0;
+      if (t < n_tiles && rw < n) {
+        nx_mask = mask ? (uint32_t)mask[rw] : 1u;
+        if (with_tail && !hf) {
+          nx_cd = code[rw];
+          nx_ll = tail.log_l[rw];
+        }
+        if (prefetch) {
+          const uint4* src =
+              (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
 #pragma unroll
-      for (int q = 0; q < 32; ++q)
-        v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
-      tmem_st32(d_addr + (uint32_t)c, v);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    group_sync(g);
-  };
-  // all: last hidden layer, the fan_out-1 output layer folded in registers
-  auto epi_last = [&](int net, int l) -> float {
-    tc_fence_after();
-    const float* wnet = wsm + (size_t)net * h.net_stride;
-    const float* wout = wnet + h.w_out_off;
-    const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
-    float acc = hf ? 0.f : wnet[h.b_out_off];
-    for (int c = hf * 16; c < h.np[l]; c += 32) {
-      uint32_t v[16];
-      tmem_ld16(d_addr + (uint32_t)c, v);
-      // the output weights of these 16 columns: four broadcast LDS.128
-      const float4* w4 = reinterpret_cast<const float4*>(wout + c);
-      const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-      const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                           w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-      tmem_wait_ld();
+          for (int q = 0; q < 4; ++q)
+            if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
+        }
+      }
+    };
+    // this warp's part of a hand-over to the issuer: TMEM stores complete,
+    // ordered before the arrival
+    auto signal = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // standardised input rows of tile t -> TMEM (A operand of layer 0)
+    auto stage_a0 = [&](int64_t t, bool active) {
+      if (prefetch) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), w[q], acc);
-    }
-    if (hf) part[g][r] = acc;
-    // a later MMA overwrites these columns: order the loads before it
-    tc_fence_before();
-    group_sync(g);
-    return hf ? 0.f : acc + part[g][r];
-  };
-  // half 0: score -> decision -> outputs of one row, and with the fused tail
-  // the disposition histogram and the log-sum-exp of the likelihood that
-  // k_front evaluated for this row
-  auto finalize = [&](int64_t tile, float sum, bool active, uint32_t cd_in,
-                      double ll) {
-    const int64_t row = tile * 128 + r;
-    bool accepted = false;
-    if (active) {
-      const double score = (double)(sum / (float)h.n_net);
-      accepted = score > thr;
-      if (score_out) score_out[row] = score;
-      if (passf && accepted) passf[row] = 1;
-      if (code && !accepted) code[row] = NB200_CODE_NN_REJECT;
-    } else if (score_out && row < n) {
-      score_out[row] = nan("");
-    }
-    if (with_tail && row < n) {
-      c_raw += 1;
-      if (active ? accepted : cd_in == NB200_CODE_IN_SHELL) {
-        lse_acc.add(ll);
-        c_in += 1;
-        if (ll >= tail.log_l_min) c_upd += 1;
+        for (int q = 0; q < 2; ++q) {
+          const int c = hf * 16 + q * 8;
+          if (c < h.k0p) {
+            uint32_t v[8];
+            const uint4 a = active ? pre[2 * q] : make_uint4(0, 0, 0, 0);
+            const uint4 b = active ? pre[2 * q + 1] : make_uint4(0, 0, 0, 0);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
+          }
+        }
       } else {
-        if (active) {
+        const int64_t rw = t * 128 + r;
+        const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
+        for (int c = hf * 8; c < h.k0p; c += 16) {
+          uint32_t v[8];
+          if (active) {
+            const uint4 a = __ldg(src + (c >> 2));
+            const uint4 b = __ldg(src + (c >> 2) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0u;
+          }
+          tmem_st8(tmem_base + lane_addr + (uint32_t)(h.a0_col + c), v);
+        }
+      }
+      tmem_wait_st();
+      signal(sA);
+    };
+    // ReLU + tf32 rounding of layer l's accumulator, written back in place
+    // as the next layer's A operand (the bias was added by the MMA through
+    // the constant-one column, see _pack.py:pack_tc)
+    auto epi_hidden = [&](int l, uint64_t* done) {
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+      // 32 columns per TMEM load (the accumulator regions are 32-column
+      // aligned; pad columns meet zero weights), halves interleaved
+      for (int c = hf * 32; c < h.np[l]; c += 64) {
+        uint32_t v[32];
+        tmem_ld32(d_addr + (uint32_t)c, v);
+        tmem_wait_ld();
+        // ReLU, then round-half-up to tf32: the MMA reads only the top 19
+        // bits, so adding half an ulp of tf32 is the whole rounding
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
+        tmem_st32(d_addr + (uint32_t)c, v);
+      }
+      tmem_wait_st();
+      signal(done);
+    };
+    // last hidden layer, the fan_out-1 output layer folded in registers;
+    // `done` (may be null) tells the issuer the region has been read
+    auto epi_last = [&](int net, int l, uint64_t* done) -> float {
+      tc_fence_after();
+      const float* wnet = wsm + (size_t)net * h.net_stride;
+      const float* wout = wnet + h.w_out_off;
+      const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+      float acc = hf ? 0.f : wnet[h.b_out_off];
+      for (int c = hf * 16; c < h.np[l]; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(d_addr + (uint32_t)c, v);
+        // the output weights of these 16 columns: four broadcast LDS.128
+        const float4* w4 = reinterpret_cast<const float4*>(wout + c);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                             w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          acc = fmaf(fmaxf(__uint_as_float(v[q]), 0.f), w[q], acc);
+      }
+      if (done) signal(done);
+      // the partner half's partial dot product: two pair barriers, the
+      // second one frees `part` for the next network
+      const int pid = 1 + g * 4 + (warp & 3);
+      if (hf) part[g][r] = acc;
+      pair_sync(pid);
+      const float tot = hf ? 0.f : acc + part[g][r];
+      pair_sync(pid);
+      return tot;
+    };
+    // half 0: score -> decision -> outputs of one row, and with the fused
+    // tail the disposition histogram and the log-sum-exp of the likelihood
+    // that k_front evaluated for this row
+    auto finalize = [&](int64_t tile, float sum, bool active, uint32_t cd_in,
+                        double ll) {
+      const int64_t row = tile * 128 + r;
+      bool accepted = false;
+      if (active) {
+        const double score = (double)(sum / (float)h.n_net);
+        accepted = score > thr;
+        if (score_out) score_out[row] = score;
+        if (passf && accepted) passf[row] = 1;
+        if (code && !accepted) code[row] = NB200_CODE_NN_REJECT;
+      } else if (score_out && row < n) {
+        score_out[row] = nan("");
+      }
+      if (with_tail && row < n) {
+        c_raw += 1;
+        if (active ? accepted : cd_in == NB200_CODE_IN_SHELL) {
+          lse_acc.add(ll);
+          c_in += 1;
+          if (ll >= tail.log_l_min) c_upd += 1;
+        } else if (active) {
           tail.log_l[row] = nan("");      // the front's value is void now
           c_rej2 += 1;
         } else {
@@ -335,107 +419,85 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
           c_rej3 += cd_in == NB200_CODE_EXCLUDED;
         }
       }
-    }
-  };
+    };
 
-  uint64_t* bA = &mbar[g * 3 + 0];
-  uint64_t* bB = &mbar[g * 3 + 1];
-  uint64_t* bC = &mbar[g * 3 + 2];
-  fetch(tile0);
-  if (h.n_hid == 3) {
-    // One continuous stream of (tile, network) instances per group, two in
-    // flight: while the CUDA cores run one instance's epilogue the tensor
-    // pipe runs the other's next layer,
-    //   L0(i+1) || epilogue1(i),  L2(i) || epilogue0(i+1),
-    //   L1(i+1) || epilogue2(i),
-    // and the stream does not drain at tile boundaries: the next tile's
-    // input rows go to TMEM as soon as the last network of this tile has
-    // consumed the old ones.
-    int64_t tile = tile0;
-    bool have = tile < n_tiles;
-    bool cur_active = false, hold_active = false;
-    uint32_t cur_cd = NB200_CODE_IN_SHELL, hold_cd = NB200_CODE_IN_SHELL;
-    double cur_ll = 0.0, hold_ll = 0.0;
-    if (have) {
-      TL_STAMP(1);
-      cur_active = nx_mask != 0; cur_cd = nx_cd; cur_ll = nx_ll;
-      stage_a0(tile, cur_active);
-      tmem_wait_st();
-      fetch(tile + tile_step);
-      tc_fence_before();
-      group_sync(g);
-      TL_STAMP(2);
-      issue(0, 0, bA);
-      mbar_wait(bA, phA); phA ^= 1u;
-      epi_hidden(0);
-      issue(0, 1, bB);
-    }
-    while (have) {
-      const int64_t next_tile = tile + tile_step;
-      const bool have_next = next_tile < n_tiles;
-      float sum = 0.f;
-      for (int net = 0; net < h.n_net; ++net) {
-        const bool last = net + 1 == h.n_net;
-        const bool more = !last || have_next;
-        const int nn = last ? 0 : net + 1;
-        TL_STAMP(10);
-        mbar_wait(bB, phB); phB ^= 1u;     // D1(i) ready, region 0 free
-        TL_STAMP(11);
-        if (last && have_next) {
-          // every network of this tile has read the input rows: stage the
-          // next tile's
-          hold_active = nx_mask != 0; hold_cd = nx_cd; hold_ll = nx_ll;
-          stage_a0(next_tile, hold_active);
-          tmem_wait_st();
-          fetch(next_tile + tile_step);
-          tc_fence_before();
-          group_sync(g);
-          TL_STAMP(1);
-        }
-        if (more) issue(nn, 0, bA);
-        TL_STAMP(12);
-        epi_hidden(1);
-        TL_STAMP(13);
-        issue(net, 2, bC);
-        TL_STAMP(14);
-        if (more) {
-          mbar_wait(bA, phA); phA ^= 1u;
-          TL_STAMP(15);
-          epi_hidden(0);
-          TL_STAMP(16);
-        }
-        mbar_wait(bC, phC); phC ^= 1u;     // D2(i) ready, region 1 free
-        TL_STAMP(17);
-        if (more) issue(nn, 1, bB);
-        TL_STAMP(18);
-        sum += epi_last(net, 2);
-        TL_STAMP(19);
+    uint32_t phA = 0, phB = 0, phC = 0;
+    const int N = h.n_net;
+    fetch(tile0);
+    if (h.n_hid == 3) {
+      // One continuous stream of (tile, network) instances per group, two in
+      // flight: while these warps run one instance's epilogue the tensor
+      // pipe runs the other's next layer, and the stream does not drain at
+      // tile boundaries.
+      int64_t tile = tile0;
+      bool have = tile < n_tiles;
+      bool cur_active = false, hold_active = false;
+      uint32_t cur_cd = NB200_CODE_IN_SHELL, hold_cd = NB200_CODE_IN_SHELL;
+      double cur_ll = 0.0, hold_ll = 0.0;
+      if (have) {
+        TL_STAMP(1);
+        cur_active = nx_mask != 0; cur_cd = nx_cd; cur_ll = nx_ll;
+        stage_a0(tile, cur_active);
+        fetch(tile + tile_step);
+        mbar_wait(bA, phA); phA ^= 1u;
+        epi_hidden(0, s0);
       }
-      if (!hf) finalize(tile, sum, cur_active, cur_cd, cur_ll);
-      tile = next_tile;
-      have = have_next;
-      cur_active = hold_active; cur_cd = hold_cd; cur_ll = hold_ll;
-    }
-  } else {
-    for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-      const bool active = nx_mask != 0;
-      const uint32_t cd_in = nx_cd;
-      const double ll = nx_ll;
-      stage_a0(tile, active);
-      tmem_wait_st();
-      fetch(tile + tile_step);
-      tc_fence_before();
-      group_sync(g);
-      float sum = 0.f;
-      for (int net = 0; net < h.n_net; ++net) {
-        for (int l = 0; l < h.n_hid; ++l) {
-          issue(net, l, bA);
-          mbar_wait(bA, phA); phA ^= 1u;
-          if (l + 1 < h.n_hid) epi_hidden(l);
-          else sum += epi_last(net, l);
+      while (have) {
+        const int64_t next_tile = tile + tile_step;
+        const bool have_next = next_tile < n_tiles;
+        float sum = 0.f;
+        for (int net = 0; net < N; ++net) {
+          const bool last = net + 1 == N;
+          const bool more = !last || have_next;
+          if (last && have_next) {
+            // every network of this tile has read the input rows (the last
+            // L0 was awaited before its epilogue): stage the next tile's
+            hold_active = nx_mask != 0; hold_cd = nx_cd; hold_ll = nx_ll;
+            stage_a0(next_tile, hold_active);
+            fetch(next_tile + tile_step);
+            TL_STAMP(1);
+          }
+          TL_STAMP(10);
+          mbar_wait(bB, phB); phB ^= 1u;       // D1(i) ready
+          TL_STAMP(11);
+          epi_hidden(1, s1);
+          TL_STAMP(13);
+          if (more) {
+            mbar_wait(bA, phA); phA ^= 1u;     // D0(i+1) ready
+            TL_STAMP(15);
+            epi_hidden(0, s0);
+            TL_STAMP(16);
+          }
+          mbar_wait(bC, phC); phC ^= 1u;       // D2(i) ready
+          TL_STAMP(17);
+          sum += epi_last(net, 2, more ? s2 : nullptr);
+          TL_STAMP(19);
         }
+        if (!hf) finalize(tile, sum, cur_active, cur_cd, cur_ll);
+        tile = next_tile;
+        have = have_next;
+        cur_active = hold_active; cur_cd = hold_cd; cur_ll = hold_ll;
       }
-      if (!hf) finalize(tile, sum, active, cd_in, ll);
+    } else {
+      for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+        const bool active = nx_mask != 0;
+        const uint32_t cd_in = nx_cd;
+        const double ll = nx_ll;
+        // (for the tiles after the first this arrival also tells the issuer
+        // that the last epilogue of the previous tile is over)
+        stage_a0(tile, active);
+        if (lane == 0) mbar_arrive(s0);       // s0 carries every hand-over
+        fetch(tile + tile_step);
+        float sum = 0.f;
+        for (int net = 0; net < N; ++net) {
+          for (int l = 0; l < h.n_hid; ++l) {
+            mbar_wait(bA, phA); phA ^= 1u;
+            if (l + 1 < h.n_hid) epi_hidden(l, s0);
+            else sum += epi_last(net, l, net + 1 < N ? s0 : nullptr);
+          }
+        }
+        if (!hf) finalize(tile, sum, active, cd_in, ll);
+      }
     }
   }
 
@@ -450,8 +512,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     cnt[NB200_CNT_EXCLUDED] = c_rej3;
     cnt[NB200_CNT_IN_SHELL] = c_in;
     cnt[NB200_CNT_UPDATE] = c_upd;
-    stat_block_reduce<TC_GROUPS * TC_GROUP_THREADS>(
-        lse_acc, cnt, tail.partial + blockIdx.x);
+    stat_block_reduce<TC_THREADS>(lse_acc, cnt, tail.partial + blockIdx.x);
   }
   tc_fence_before();
   __syncthreads();
@@ -521,7 +582,7 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   if (grid < 1) grid = 1;
   if (tail.partial) NB_CHECK(grid <= STAT_MAX_BLOCKS, "too many partials");
   if (grid_out) *grid_out = (int)grid;
-  k_mlp_tf32<<<(unsigned)grid, TC_GROUPS * TC_GROUP_THREADS, smem, st>>>(
+  k_mlp_tf32<<<(unsigned)grid, TC_THREADS, smem, st>>>(
       h, blob, xs32, mask, n, score_out, passf, code, tail);
   NB_LAUNCH_OK();
   return 0;
@@ -593,13 +654,14 @@ int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
 
 #ifdef NB200_TIMELINE
 int debug_timeline(long long* out, int n) {
-  int cnt = 0;
-  cudaMemcpyFromSymbol(&cnt, g_tl_n, sizeof(int));
-  if (cnt > n) cnt = n;
-  cudaMemcpyFromSymbol(out, g_tl, sizeof(long long) * cnt);
-  int zero = 0;
-  cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(int));
-  return cnt;
+  // out: [2][1024] (tag, clock) pairs of the epilogue thread and the issuer
+  if (n < 2048) return -1;
+  cudaMemcpyFromSymbol(out, g_tl, sizeof(long long) * 2048);
+  cudaMemset(nullptr, 0, 0);
+  long long zero[2048];
+  memset(zero, 0, sizeof(zero));
+  cudaMemcpyToSymbol(g_tl, zero, sizeof(zero));
+  return 2048;
 }
 #endif
 

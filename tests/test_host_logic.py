@@ -219,3 +219,25 @@ def test_oracle_classify_is_consistent_with_contains(golden):
     inside = orc.bound_contains(spec, pts)
     assert np.array_equal(code == 4, inside)
     assert np.all(nb[code == 0] == 0)
+
+
+def test_batched_gmm_matches_sequential():
+    # the device EM (all restarts advanced together) follows the sequential
+    # host EM restart by restart: same seeding draws, same winner, same split
+    from nautilus_b200.bounds import _construct
+    rng = np.random.default_rng(3)
+    for n, d, k in [(900, 6, 3), (400, 3, 2), (300, 10, 1)]:
+        centres = rng.uniform(0.2, 0.8, size=(k, d))
+        x = np.concatenate([c + 0.03 * rng.normal(size=(n // k, d))
+                            for c in centres])
+        a = _construct.two_gaussians(x, np.random.default_rng(5))
+        b = _construct.two_gaussians_batched(x, np.random.default_rng(5),
+                                             device='cpu')
+        assert np.max(np.abs(a - b)) < 1e-8
+        assert np.array_equal(a.argmax(axis=1), b.argmax(axis=1))
+    # degenerate input: fewer points than a covariance needs
+    x = rng.normal(size=(4, 6))
+    a = _construct.two_gaussians(x, np.random.default_rng(1))
+    b = _construct.two_gaussians_batched(x, np.random.default_rng(1),
+                                         device='cpu')
+    assert np.array_equal(a, b)
