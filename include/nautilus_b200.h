@@ -235,6 +235,22 @@ int nb200_cycle_host(const int32_t* meta_h, int64_t n_meta,
                      double* points_out_h, double* log_l_out_h,
                      int64_t* n_out_h, double* lse_h, int64_t* counters_h);
 
+/* ---- bound construction (between shells) -------------------------------- */
+
+/* Weights u f64[n] of Khachiyan's algorithm for the minimum-volume enclosing
+ * ellipsoid of n points in d dimensions (minimum_volume_enclosing_ellipsoid,
+ * bounds/basic.py:175-241): the ellipsoid is centred at c = sum u_i x_i with
+ * shape A^-1 = d * sum u_i (x_i - c)(x_i - c)^T.  qT_d f64[d, n] holds the
+ * points COORDINATE-MAJOR (and, for conditioning, whitened by their sample
+ * covariance: the MVEE is affine equivariant).  Stops after max_updates
+ * rank-one updates or when max_i g_i <= (d+1)(1+tol).  iters_d (may be NULL)
+ * receives the number of updates.  workspace: nb200_mvee_workspace_bytes(n). */
+size_t nb200_mvee_workspace_bytes(int64_t n);
+int nb200_mvee_weights(const double* qT_d, int64_t n, int d, int max_updates,
+                       double tol, double* u_d, int32_t* iters_d,
+                       void* workspace_d, size_t workspace_bytes,
+                       void* stream);
+
 /* ---- host-buffer session: the loop around add_samples ------------------- */
 
 /* A session owns the device buffers, two streams and pinned host buffers for

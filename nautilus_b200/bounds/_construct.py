@@ -23,6 +23,16 @@ from collections import OrderedDict
 
 import numpy as np
 
+def construction_device():
+    """Where the enclosing-ellipsoid iteration and the mixture EM run: the
+    current CUDA device, or None (host NumPy) with NB200_CONSTRUCT=host."""
+    import os
+    if os.environ.get('NB200_CONSTRUCT', 'device') == 'host':
+        return None
+    from .._device import default_device
+    return default_device()
+
+
 _MVEE_CACHE = OrderedDict()      # the same live set is bounded several times
 _MVEE_CACHE_SIZE = 32            # per new bound (nautilus.py:100-119)
 
@@ -56,8 +66,13 @@ def _khachiyan(points, max_updates, tol):
     return u
 
 
-def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
+def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3, device=None):
     """Approximate MVEE of ``points`` [N, d].
+
+    With ``device`` (a CUDA device) the Khachiyan iteration runs in the
+    persistent kernel ``k_mvee`` (csrc/nb200_construct.cu) and the O(N d^2)
+    pre- and post-processing as fp64 tensor operations on that device;
+    otherwise everything is NumPy on the host.
 
     Returns ``(c, A, A_inv)`` with ``max_i (x_i - c)^T A (x_i - c) == 1``
     (the convention of nautilus/bounds/basic.py:233-241).  The MVEE is affine
@@ -72,6 +87,12 @@ def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
         _MVEE_CACHE.move_to_end(key)
         c, a, a_inv = _MVEE_CACHE[key]
         return c.copy(), a.copy(), a_inv.copy()
+    if device is not None:
+        result = _enclosing_ellipsoid_device(points, max_updates, tol, device)
+        _MVEE_CACHE[key] = result
+        if len(_MVEE_CACHE) > _MVEE_CACHE_SIZE:
+            _MVEE_CACHE.popitem(last=False)
+        return tuple(r.copy() for r in result)
     mu = np.mean(points, axis=0)
     cov = np.atleast_2d(np.cov(points, rowvar=False))
     cov = cov + np.eye(d) * 1e-14 * max(np.trace(cov) / d, 1e-300)
@@ -90,6 +111,32 @@ def enclosing_ellipsoid(points, max_updates=3000, tol=1e-3):
     if len(_MVEE_CACHE) > _MVEE_CACHE_SIZE:
         _MVEE_CACHE.popitem(last=False)
     return tuple(r.copy() for r in result)
+
+
+def _enclosing_ellipsoid_device(points, max_updates, tol, device):
+    """``enclosing_ellipsoid`` with the points on ``device``: same steps, the
+    sequential loop in one persistent CUDA kernel."""
+    import torch
+    from .. import ops
+    x = torch.from_numpy(points).to(device)
+    n, d = x.shape
+    mu = x.mean(dim=0)
+    xc = x - mu
+    cov = xc.T @ xc / (n - 1)
+    eye = torch.eye(d, dtype=torch.float64, device=x.device)
+    cov = cov + eye * 1e-14 * max(float(torch.trace(cov)) / d, 1e-300)
+    chol = torch.linalg.cholesky(cov)
+    white_t = torch.linalg.solve_triangular(chol, xc.T, upper=False)
+    u, _ = ops.mvee_weights(white_t.contiguous(), max_updates, tol)
+    c = u @ x
+    diff = x - c
+    a_inv = (diff * u[:, None]).T @ diff
+    a_inv = 0.5 * (a_inv + a_inv.T)
+    a = torch.linalg.inv(a_inv)
+    a = 0.5 * (a + a.T)
+    scale = torch.max(((diff @ a) * diff).sum(dim=1))
+    return (np.atleast_1d(c.cpu().numpy()), (a / scale).cpu().numpy(),
+            (a_inv * scale).cpu().numpy())
 
 
 # --------------------------------------------------------------------------

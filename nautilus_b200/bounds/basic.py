@@ -87,7 +87,8 @@ class Ellipsoid(_DeviceBound):
         if not points.shape[0] > points.shape[1]:
             raise ValueError('Number of points must be larger than number '
                              'dimensions.')
-        c, a, a_inv = _construct.enclosing_ellipsoid(points)
+        c, a, a_inv = _construct.enclosing_ellipsoid(
+            points, device=_construct.construction_device())
         return cls.from_matrices(c, a / enlarge_per_dim**2.0,
                                  a_inv * enlarge_per_dim**2.0, rng=rng)
 

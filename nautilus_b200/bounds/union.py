@@ -85,9 +85,13 @@ class Union(_DeviceBound):
             pts = self.points_bounds[index]
             whitened = self.bounds[index].transform(pts)
             # EM of all restarts advanced together on the device
-            log_p = _construct.two_gaussians_batched(
-                whitened, np.random.default_rng(
-                    self.rng.integers(2**32 - 1)), device=default_device())
+            dev = _construct.construction_device()
+            gmm_rng = np.random.default_rng(self.rng.integers(2**32 - 1))
+            if dev is None:
+                log_p = _construct.two_gaussians(whitened, gmm_rng)
+            else:
+                log_p = _construct.two_gaussians_batched(whitened, gmm_rng,
+                                                         device=dev)
             labels = np.argmax(log_p, axis=1)
             counts = np.bincount(labels, minlength=2)
             if np.any(counts < self.n_points_min):

@@ -69,7 +69,7 @@ __device__ __forceinline__ void mv8x2(const double* __restrict__ MT, int d8,
   for (int r = 0; r < 8; ++r) { a0[r] = 0.0; a1[r] = 0.0; }
   const double2* col = reinterpret_cast<const double2*>(MT + i0);
   const int ld = d8 >> 1;   // double2 per transposed row
-#pragma unroll 2
+#pragma unroll 4
   for (int j = 0; j < jmax; ++j) {
     double v0 = x0[j], v1 = x1[j];
     if (SUBTRACT) { const double cj = c[j]; v0 -= cj; v1 -= cj; }
@@ -149,43 +149,53 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
     // ---- normals -> direction and radial factor of a uniform point of the
     // unit ball (basic.py:376-379); the row holds the raw normals, the factor
     // scale = u^(1/d) / |z| is applied on the fly in the product below -------
+    // (the two proposals run through the generator side by side, in
+    // straight-line code, so that their dependent integer chains interleave;
+    // rows past the end of the batch are computed and dropped)
+    {
+      double n2[FRONT_PTS];
+      double uq[FRONT_PTS];
+      const Philox rng0(A.offset + (unsigned long long)(base + threadIdx.x),
+                        A.stream_id, A.seed);
+      const Philox rng1(A.offset + (unsigned long long)(base + FRONT_THREADS +
+                                                        threadIdx.x),
+                        A.stream_id, A.seed);
 #pragma unroll
-    for (int p = 0; p < FRONT_PTS; ++p) {
-      const int li = p * FRONT_THREADS + (int)threadIdx.x;
-      gi[p] = base + li;
-      valid[p] = li < nrows;
-      kq[p] = 0; rq[p] = 0.0; sq[p] = 0.0;
-      double* x = xr[p];
-      if (valid[p]) {
-        const Philox rng(A.offset + (unsigned long long)gi[p], A.stream_id,
-                         A.seed);
-        const uint4 w0 = rng.block(0);
+      for (int p = 0; p < FRONT_PTS; ++p) {
+        const int li = p * FRONT_THREADS + (int)threadIdx.x;
+        gi[p] = base + li;
+        valid[p] = li < nrows;
+        const uint4 w0 = p == 0 ? rng0.block(0) : rng1.block(0);
         const double uk = u01_32(w0.x);
         int k = 0;
         while (k < K - 1 && !(uk < __ldg(cdf + k))) ++k;
         kq[p] = k;
         rq[p] = u01_32(w0.y);
-        const double u = u01_53(w0.z, w0.w);
-        double n2 = 0.0;
-        for (int j = 0; j < d; j += 4) {
-          const uint4 w = rng.block(1 + (j >> 2));
-          float g0, g1, g2, g3;
-          normal2(w.x, w.y, g0, g1);
-          normal2(w.z, w.w, g2, g3);
-          const float gq[4] = {g0, g1, g2, g3};
+        uq[p] = u01_53(w0.z, w0.w);
+        n2[p] = 0.0;
+      }
+      for (int j = 0; j < d; j += 4) {
+        const uint4 wa = rng0.block(1 + (j >> 2));
+        const uint4 wb = rng1.block(1 + (j >> 2));
+        float ga[4], gb[4];
+        normal2(wa.x, wa.y, ga[0], ga[1]);
+        normal2(wb.x, wb.y, gb[0], gb[1]);
+        normal2(wa.z, wa.w, ga[2], ga[3]);
+        normal2(wb.z, wb.w, gb[2], gb[3]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (j + q < d) {
-              const double v = (double)gq[q];
-              x[j + q] = v;
-              n2 = fma(v, v, n2);
-            }
+        for (int q = 0; q < 4; ++q) {
+          if (j + q < d) {
+            const double va = (double)ga[q], vb = (double)gb[q];
+            xr[0][j + q] = va;
+            xr[1][j + q] = vb;
+            n2[0] = fma(va, va, n2[0]);
+            n2[1] = fma(vb, vb, n2[1]);
           }
         }
-        sq[p] = pow(u, 1.0 / (double)d) / sqrt(n2);
-      } else {
-        for (int j = 0; j < d; ++j) x[j] = 0.0;
       }
+#pragma unroll
+      for (int p = 0; p < FRONT_PTS; ++p)
+        sq[p] = pow(uq[p], 1.0 / (double)d) / sqrt(n2[p]);
     }
     // ---- x = B (z * scale) + c in place (basic.py:380 -> :342), highest row
     // group first; the unit-cube test (union.py:313-314) runs on the

@@ -384,6 +384,24 @@ def loglike(points, like_id, params, code=None):
     return out
 
 
+def mvee_weights(q_t, max_updates=3000, tol=1e-3):
+    """Khachiyan weights of the MVEE of the points ``q_t`` f64[d, n] (CUDA,
+    coordinate-major, ideally whitened) -- basic.py:175-241.  Returns
+    (u f64[n] CUDA, iterations int32[1] CUDA)."""
+    if not (q_t.is_cuda and q_t.dtype == torch.float64 and q_t.dim() == 2 and
+            q_t.is_contiguous()):
+        raise ValueError('q_t must be a contiguous CUDA float64 [d, n] tensor')
+    d, n = q_t.shape
+    u = torch.empty(n, dtype=torch.float64, device=q_t.device)
+    iters = torch.zeros(1, dtype=torch.int32, device=q_t.device)
+    nbytes = int(_lib.lib().nb200_mvee_workspace_bytes(n))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=q_t.device)
+    _lib.check(_lib.lib().nb200_mvee_weights(
+        _ptr(q_t), n, d, int(max_updates), float(tol), _ptr(u), _ptr(iters),
+        _ptr(buf), nbytes, _stream()))
+    return u, iters
+
+
 def mlp_fit(x, y, sizes, n_networks, seed=0, lr=1e-2, beta1=0.9, beta2=0.999,
             eps=1e-8, batch_size=200, max_epochs=10000, tol=0.0, patience=10):
     """Train an ensemble on standardised inputs (neural.py:50-98).

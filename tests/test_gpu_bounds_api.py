@@ -304,3 +304,33 @@ def test_nautilus_bound_gpu_pool(random_points_from_hypercube, n_gpus):
     nbound.reset(np.random.default_rng(0))
     points_3, volume_3 = nbound.sample(10000), nbound.log_v
     assert np.all(points_1 == points_3) and volume_1 == volume_3
+
+
+def test_device_mvee_matches_host():
+    # k_mvee (persistent Khachiyan kernel) against the host restatement and
+    # the reference's known answer (tests/test_bounds.py:88-101)
+    from nautilus_b200.bounds import _construct
+    rng = np.random.default_rng(0)
+    for n, d in [(2000, 30), (500, 4), (300, 10), (40, 3)]:
+        z = rng.normal(size=(n, d))
+        z *= (rng.uniform(size=(n, 1))**(1.0 / d) /
+              np.linalg.norm(z, axis=1)[:, None])
+        mix = rng.normal(size=(d, d)) * 0.05 + np.eye(d) * 0.1
+        x = 0.5 + z @ mix.T
+        _construct._MVEE_CACHE.clear()
+        c0, a0, ai0 = _construct.enclosing_ellipsoid(x)
+        _construct._MVEE_CACHE.clear()
+        c1, a1, ai1 = _construct.enclosing_ellipsoid(x, device='cuda')
+        quad = np.einsum('ij,jk,ik->i', x - c1, a1, x - c1)
+        assert abs(np.max(quad) - 1) < 1e-9          # touches, encloses all
+        assert np.max(np.abs(c1 - c0)) < 1e-6
+        assert np.max(np.abs(a1 - a0)) / np.max(np.abs(a0)) < 1e-5
+        assert np.allclose(a1 @ ai1, np.eye(d), atol=1e-8)
+    # 2d points on the axes at +-1: the unit sphere
+    d = 10
+    x = np.concatenate([np.eye(d), -np.eye(d)])
+    _construct._MVEE_CACHE.clear()
+    c, a, _ = _construct.enclosing_ellipsoid(x, device='cuda', tol=1e-6,
+                                             max_updates=20000)
+    assert np.allclose(c, 0, atol=1e-3) and np.allclose(a, np.eye(d),
+                                                        atol=1e-2)

@@ -8,6 +8,13 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1
 echo "smoke rc=$?" | tee -a $OUT/summary.txt
+# gate: the tensor-core and fused-cycle tests first, under a short timeout (a
+# deadlocked kernel traps after 2^22 polls; do not spend the budget on it)
+timeout 300 python -m pytest tests/test_gpu_tensor.py tests/test_gpu_session.py -x -q > $OUT/pytest_gate.log 2>&1
+GATE=$?
+echo "gate rc=$GATE" | tee -a $OUT/summary.txt
+tail -5 $OUT/pytest_gate.log
+if [ $GATE -ne 0 ]; then tail -40 $OUT/pytest_gate.log; exit 1; fi
 if [ "$2" != "skip-tests" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q --durations=12 > $OUT/pytest_gpu.log 2>&1
   echo "pytest rc=$?" | tee -a $OUT/summary.txt
