@@ -17,6 +17,8 @@
 // order of oracle/c/nb200_oracle.c; entries above the diagonal are exact
 // zeros, so including some of them changes nothing).  One shared row per
 // thread: x = B y + c is formed in place, walking the row groups downwards.
+#include <stdlib.h>
+
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
 
@@ -354,8 +356,23 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
 }
 
 // Host side: does the fast path apply, and launch.
-bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
-                      FrontArgs* args) {
+struct FrontMmaArgs;
+bool front_mma_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
+                          FrontMmaArgs* args);
+int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
+                     const double* data_d, int bound, int64_t n, uint64_t seed,
+                     uint64_t offset, uint32_t stream_id, double* points,
+                     uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
+                     const double* like_p, double* log_l, cudaStream_t st);
+
+// NB200_FRONT=dfma forces the DFMA kernel (A/B measurements, tests)
+static bool front_mma_wanted() {
+  const char* e = getenv("NB200_FRONT");
+  return !(e && strcmp(e, "dfma") == 0);
+}
+
+static bool front2_applicable(const int32_t* meta_h, int bound,
+                              size_t* smem_out, FrontArgs* args) {
   const Rec rec = record(meta_h, bound);
   if (rec.kind() != 1 || rec.J() != 1) return false;
   const int32_t* nb = rec.nb(0);
@@ -383,14 +400,28 @@ bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   return true;
 }
 
+// one ellipsoid: the DMMA kernel; several: the DFMA kernel above
+bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
+                      FrontArgs* args) {
+  if (front_mma_wanted() &&
+      front_mma_applicable(meta_h, bound, nullptr, nullptr))
+    return true;
+  return front2_applicable(meta_h, bound, smem_out, args);
+}
+
 int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  const double* data_d, int bound, int64_t n, uint64_t seed,
                  uint64_t offset, uint32_t stream_id, double* points,
                  uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
                  const double* like_p, double* log_l, cudaStream_t st) {
+  if (front_mma_wanted() &&
+      front_mma_applicable(meta_h, bound, nullptr, nullptr))
+    return launch_front_mma(meta_h, meta_d, data_d, bound, n, seed, offset,
+                            stream_id, points, code, maskj, xs32, like_id,
+                            like_p, log_l, st);
   FrontArgs A;
   size_t smem = 0;
-  NB_CHECK(front_applicable(meta_h, bound, &smem, &A), "front kernel n/a");
+  NB_CHECK(front2_applicable(meta_h, bound, &smem, &A), "front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
   NB_CUDA(cudaFuncSetAttribute(k_front,

@@ -1,0 +1,376 @@
+// Fused fp64 front end of the cycle on the FP64 tensor cores (DMMA), for the
+// common bound with ONE ellipsoid (K == 1, a plain Ellipsoid mixture) and one
+// neural bound: the same job as k_front in nb200_front.cu --
+//   Union.sample draw (nautilus/bounds/union.py:305-319, basic.py:376-381),
+//   unit-cube cut, overlap acceptance, NeuralBound's ellipsoid test and
+//   whitening (bounds/neural.py:117-119), emulator input standardisation
+//   (nautilus/neural.py:115), optional built-in likelihood --
+// but the two matrix-vector products per proposal, x = B z + c and
+// t = B_inv (x - c), run as mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): measured
+// here at 37.0 TFLOP/s, the same rate as the DFMA pipe, for 1/8 of the issue
+// slots and no shared-memory traffic per FMA (k_front was bound by LDS
+// wavefronts, then by issue latency).
+//
+// Mapping: a warp owns 32 proposals whose rows live in its private slice of
+// shared memory (row stride S = d8 + 4 doubles: conflict-free A-fragment
+// loads); lane = (p, q) = (lane / 4, lane % 4).  For every group g of 8
+// proposals
+//   A fragment  a[p][q]      = row (8g + p), column 4 Kb + q
+//   B fragment  b[q][n=p]    = M[8 I + p][4 Kb + q]   (staged in this order)
+//   C fragment  c[p][2q..]   = output rows 8 I + 2q, 8 I + 2q + 1 of row 8g+p
+// Lower-triangular factors skip the blocks above the diagonal (exact zeros).
+// The generator is spread the same way: lane (p, q) draws the Philox blocks
+// b = q, q + 4, ... (4 normals each) of the proposals 8g + p, and owns
+// proposal 8q + p for everything scalar (acceptance uniform, radial factor,
+// disposition, likelihood).  The warps of a CTA never synchronise with each
+// other inside the loop.
+#include "nb200_device.cuh"
+#include "nb200_rng.cuh"
+
+namespace nb200 {
+
+constexpr int FM_WARPS = 8;
+constexpr int FM_THREADS = FM_WARPS * 32;
+
+struct FrontMmaArgs {
+  int rec_off, d, d8, unit, k0p, S;
+  int lower_b, lower_n;   // B_inv of the mixture / of the neural bound is
+                          // exactly lower-triangular
+  int same;               // neural bound's ellipsoid == the mixture's
+  unsigned long long seed, offset;
+  unsigned int stream_id;
+  long long n;
+  int like_id;
+  const double* like_p;
+  double* log_l;
+};
+
+__device__ __noinline__ double front_mma_loglike(int like_id, const double* p,
+                                                 const double* x, int d) {
+  return loglike_eval(like_id, p, x, d);
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 "
+      "{%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// T[g] = M (rows 8I..8I+7) . (row_g - c) for the four proposal groups
+template <bool SUBTRACT>
+__device__ __forceinline__ void mma_rows(const double* __restrict__ frag,
+                                         int nK, int I, int kb_end,
+                                         const double* rows, int S, int p,
+                                         int q, const double* __restrict__ c,
+                                         double (&T)[4][2]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
+  const double* f = frag + ((size_t)I * nK) * 32 + (p * 4 + q);
+  const double* a0 = rows + p * S + q;
+#pragma unroll 2
+  for (int Kb = 0; Kb < kb_end; ++Kb) {
+    const double b = f[Kb * 32];
+    const double cq = SUBTRACT ? c[4 * Kb + q] : 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double a = a0[g * 8 * S + 4 * Kb];
+      if (SUBTRACT) a -= cq;
+      dmma(T[g], a, b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FM_THREADS, 2)
+k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
+            const double* __restrict__ data, double* __restrict__ points,
+            uint8_t* __restrict__ code, uint8_t* __restrict__ maskj,
+            float* __restrict__ xs32) {
+  extern __shared__ __align__(16) double sm[];
+  const Rec rec{meta + A.rec_off};
+  const int d = A.d, d8 = A.d8, S = A.S;
+  const int nI = d8 >> 3, nK = d8 >> 2;
+  const int fsz = d8 * d8;                 // doubles per staged factor
+  double* fB = sm;                         // B        in fragment order
+  double* fBinv = fB + fsz;                // B_inv (mixture)
+  double* fN = fBinv + fsz;                // B_inv (neural), if different
+  double* cM = fN + (A.same ? 0 : fsz);    // d8: centre of the mixture
+  double* cN = cM + d8;                    // d8: centre of the neural bound
+  double* meanN = cN + d8;                 // d8
+  double* iscaleN = meanN + d8;            // d8: 1 / scale
+  double* rows_all = iscaleN + d8;         // FM_WARPS x 32 x S
+  const int32_t* nb = rec.nb(0);
+  const int32_t* mix = rec.mix(0);
+
+  // factors -> fragment order: frag[I][Kb][lane] = M[8I + lane/4][4Kb + lane%4]
+  const int n_fac = A.same ? 2 : 3;
+  for (int e = threadIdx.x; e < n_fac * fsz; e += FM_THREADS) {
+    const int which = e / fsz, rem = e - which * fsz;
+    const int blk = rem >> 5, ln = rem & 31;
+    const int I = blk / nK, Kb = blk - I * nK;
+    const int i = 8 * I + (ln >> 2), j = 4 * Kb + (ln & 3);
+    const double* src = data + (which == 0 ? mix[4] : which == 1 ? mix[5]
+                                                                 : nb[1]);
+    sm[e] = (i < d && j < d) ? src[(size_t)i * d + j] : 0.0;
+  }
+  for (int e = threadIdx.x; e < 4 * d8; e += FM_THREADS) {
+    const int which = e / d8, i = e - which * d8;
+    double v = 0.0;
+    if (i < d) {
+      if (which == 0) v = data[mix[3] + i];
+      else if (which == 1) v = data[nb[0] + i];
+      else if (which == 2) v = data[nb[5] + i];
+      else v = 1.0 / data[nb[6] + i];
+    }
+    cM[e] = v;
+  }
+  __syncthreads();
+  const double* fNeural = A.same ? fBinv : fN;
+  const int lower_n = A.same ? A.lower_b : A.lower_n;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = lane >> 2, q = lane & 3;
+  double* rows = rows_all + (size_t)warp * 32 * S;
+  const int nblk = (d + 3) >> 2;           // Philox blocks of 4 normals
+  const long long n_tiles = (A.n + 31) / 32;
+  const long long tile_step = (long long)gridDim.x * FM_WARPS;
+
+  for (long long tile = (long long)blockIdx.x * FM_WARPS + warp;
+       tile < n_tiles; tile += tile_step) {
+    const long long base = tile * 32;
+    // ---- generator ---------------------------------------------------------
+    // this lane's own proposal: 8q + p
+    const long long gi_own = base + 8 * q + p;
+    const Philox rng_own(A.offset + (unsigned long long)gi_own, A.stream_id,
+                         A.seed);
+    const uint4 w0 = rng_own.block(0);
+    const double r_own = u01_32(w0.y);     // acceptance uniform (K == 1: the
+    const double u_own = u01_53(w0.z, w0.w);   // ellipsoid choice is moot)
+    double n2g[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const Philox rng(A.offset + (unsigned long long)(base + 8 * g + p),
+                       A.stream_id, A.seed);
+      double acc = 0.0;
+      double* zr = rows + (8 * g + p) * S;
+      for (int b = q; b < nK; b += 4) {   // nK blocks cover the padded row
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (b < nblk) {
+          const uint4 w = rng.block(1 + b);
+          float g0, g1, g2, g3;
+          normal2(w.x, w.y, g0, g1);
+          normal2(w.z, w.w, g2, g3);
+          v[0] = (double)g0; v[1] = (double)g1;
+          v[2] = (double)g2; v[3] = (double)g3;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (4 * b + t >= d) v[t] = 0.0;
+            acc = fma(v[t], v[t], acc);
+          }
+        }
+        *reinterpret_cast<double2*>(zr + 4 * b) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(zr + 4 * b + 2) = make_double2(v[2], v[3]);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      n2g[g] = acc;
+    }
+    const double n2_own = q == 0 ? n2g[0] : q == 1 ? n2g[1]
+                                                   : q == 2 ? n2g[2] : n2g[3];
+    // radial factor of the uniform ball draw (basic.py:377-379)
+    const double s_own = pow(u_own, 1.0 / (double)d) / sqrt(n2_own);
+    double sg[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      sg[g] = __shfl_sync(0xffffffffu, s_own, 4 * p + g);
+    __syncwarp();
+
+    // ---- x = s (B z) + c in place, highest row block first (B is lower
+    // triangular: block I needs z[k < 8I + 8], which the blocks below have
+    // not overwritten); unit-cube test on the fragments ----------------------
+    bool cube[4] = {true, true, true, true};
+    for (int I = nI - 1; I >= 0; --I) {
+      double T[4][2];
+      mma_rows<false>(fB, nK, I, 2 * I + 2, rows, S, p, q, nullptr, T);
+      __syncwarp();              // every lane has read this block's columns
+      const int i0 = 8 * I + 2 * q;
+      const double c0 = cM[i0], c1 = cM[i0 + 1];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const double x0 = fma(sg[g], T[g][0], c0);
+        const double x1 = fma(sg[g], T[g][1], c1);
+        *reinterpret_cast<double2*>(rows + (8 * g + p) * S + i0) =
+            make_double2(x0, x1);
+        if (i0 < d) cube[g] = cube[g] && (x0 >= 0.0) && (x0 < 1.0);
+        if (i0 + 1 < d) cube[g] = cube[g] && (x1 >= 0.0) && (x1 < 1.0);
+      }
+    }
+    unsigned cube_bits = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      unsigned ok = cube[g] ? 1u : 0u;
+      ok &= __shfl_xor_sync(0xffffffffu, ok, 1);
+      ok &= __shfl_xor_sync(0xffffffffu, ok, 2);
+      cube_bits |= ok << g;
+    }
+    __syncwarp();
+
+    // ---- whitening(s): squared radii, emulator input rows -------------------
+    double r2m[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the mixture's ellipsoid
+    double r2n[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the neural bound's
+    if (!A.same) {
+      for (int I = 0; I < nI; ++I) {
+        double T[4][2];
+        mma_rows<true>(fBinv, nK, I, A.lower_b ? 2 * I + 2 : nK, rows, S, p,
+                       q, cM, T);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          r2m[g] = fma(T[g][1], T[g][1], fma(T[g][0], T[g][0], r2m[g]));
+      }
+    }
+    for (int I = 0; 8 * I < A.k0p; ++I) {
+      double T[4][2];
+      if (I < nI) {
+        mma_rows<true>(fNeural, nK, I, lower_n ? 2 * I + 2 : nK, rows, S, p,
+                       q, cN, T);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
+      }
+      const int i0 = 8 * I + 2 * q;
+      const double m0 = i0 < d8 ? meanN[i0] : 0.0;
+      const double m1 = i0 < d8 ? meanN[i0 + 1] : 0.0;
+      const double s0 = i0 < d8 ? iscaleN[i0] : 0.0;
+      const double s1 = i0 < d8 ? iscaleN[i0 + 1] : 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        r2n[g] = fma(T[g][1], T[g][1], fma(T[g][0], T[g][0], r2n[g]));
+        // standardised, tf32-rounded input row with the constant-one bias
+        // column at index d (pack_tc)
+        float v0 = (float)((T[g][0] - m0) * s0);
+        float v1 = (float)((T[g][1] - m1) * s1);
+        if (i0 >= d) v0 = i0 == d ? 1.0f : 0.0f;
+        if (i0 + 1 >= d) v1 = i0 + 1 == d ? 1.0f : 0.0f;
+        uint32_t k0, k1;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
+        const long long gi = base + 8 * g + p;
+        // rows cut by the unit cube are never looked at by the emulator
+        if (gi < A.n && (!A.unit || ((cube_bits >> g) & 1u)))
+          *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
+              make_uint2(k0, k1);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      r2n[g] += __shfl_xor_sync(0xffffffffu, r2n[g], 1);
+      r2n[g] += __shfl_xor_sync(0xffffffffu, r2n[g], 2);
+      if (!A.same) {
+        r2m[g] += __shfl_xor_sync(0xffffffffu, r2m[g], 1);
+        r2m[g] += __shfl_xor_sync(0xffffffffu, r2m[g], 2);
+      } else {
+        r2m[g] = r2n[g];
+      }
+    }
+    // ---- disposition of this lane's own proposal (8q + p) -------------------
+    const double r2m_own = q == 0 ? r2m[0] : q == 1 ? r2m[1]
+                                                    : q == 2 ? r2m[2] : r2m[3];
+    const double r2n_own = q == 0 ? r2n[0] : q == 1 ? r2n[1]
+                                                    : q == 2 ? r2n[2] : r2n[3];
+    if (gi_own < A.n) {
+      uint8_t cd = NB200_CODE_IN_SHELL;
+      bool in_ell = false;
+      if (A.unit && !((cube_bits >> q) & 1u)) {
+        cd = NB200_CODE_CUBE_REJECT;                   // union.py:313-314
+      } else {
+        const int nbnd = r2m_own < 1.0 ? 1 : 0;        // union.py:316-317
+        if (!(r_own > 1.0 - 1.0 / (double)nbnd)) {     // union.py:318-319
+          cd = NB200_CODE_OVERLAP_REJECT;
+        } else {
+          in_ell = r2n_own < 1.0;                      // neural.py:117
+          if (!in_ell) cd = NB200_CODE_NN_REJECT;
+        }
+      }
+      code[gi_own] = cd;
+      maskj[gi_own] = in_ell ? 1 : 0;
+      if (A.log_l)
+        A.log_l[gi_own] =
+            cd == NB200_CODE_IN_SHELL
+                ? front_mma_loglike(A.like_id, A.like_p,
+                                    rows + (8 * q + p) * S, d)
+                : nan("");
+    }
+    // ---- the 32 rows leave as one contiguous block --------------------------
+    {
+      const int nrows = (int)min(32ll, A.n - base);
+      double* gdst = points + base * (long long)d;
+      const int total = nrows * d;
+      int r = lane / d, c = lane % d;
+      const int step_r = 32 / d, step_c = 32 % d;
+      for (int e = lane; e < total; e += 32) {
+        gdst[e] = rows[r * S + c];
+        r += step_r; c += step_c;
+        if (c >= d) { c -= d; r += 1; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Host side.
+bool front_mma_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
+                          FrontMmaArgs* args) {
+  const Rec rec = record(meta_h, bound);
+  if (rec.kind() != 1 || rec.J() != 1 || rec.K() != 1) return false;
+  const int32_t* nb = rec.nb(0);
+  if (nb[3] <= 0 || nb[10] < 0 || nb[11] <= 0) return false;
+  const int d = rec.d();
+  if (rec.mix(0)[1] != 0 || rec.mix(0)[0] != d) return false;
+  const int d8 = (d + 7) / 8 * 8;
+  const int S = d8 + 4;
+  const int same = rec.r[10] - 1 == 0;
+  const size_t doubles = (size_t)(same ? 2 : 3) * d8 * d8 + 4 * (size_t)d8 +
+                         (size_t)FM_WARPS * 32 * S;
+  if (doubles * 8 > 200 * 1024) return false;
+  if (smem_out) *smem_out = doubles * 8;
+  if (args) {
+    args->rec_off = (int)(rec.r - meta_h);
+    args->d = d; args->d8 = d8; args->unit = rec.unit();
+    args->k0p = (d + 1 + 7) / 8 * 8; args->S = S;
+    args->lower_b = rec.mix(0)[6]; args->lower_n = nb[2];
+    args->same = same;
+  }
+  return true;
+}
+
+int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
+                     const double* data_d, int bound, int64_t n, uint64_t seed,
+                     uint64_t offset, uint32_t stream_id, double* points,
+                     uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
+                     const double* like_p, double* log_l, cudaStream_t st) {
+  FrontMmaArgs A;
+  size_t smem = 0;
+  NB_CHECK(front_mma_applicable(meta_h, bound, &smem, &A),
+           "DMMA front kernel n/a");
+  A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
+  A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
+  NB_CUDA(cudaFuncSetAttribute(k_front_mma,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  int dev = 0, sms = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = (n + 31) / 32;
+  const int per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
+  int64_t grid = (int64_t)per_sm * sms;
+  const int64_t need = (n_tiles + FM_WARPS - 1) / FM_WARPS;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  ProfScope prof(ST_FUSED, st);
+  k_front_mma<<<(unsigned)grid, FM_THREADS, smem, st>>>(
+      A, meta_d, data_d, points, code, maskj, xs32);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace nb200

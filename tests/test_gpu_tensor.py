@@ -173,3 +173,42 @@ def test_fused_cycle_overlapping_ellipsoids(golden):
     # and with the neural ellipsoid different from every mixture
     spec['neural'][0]['ell']['c'] = spec['neural'][0]['ell']['c'] + 1e-3
     _fused_vs_staged(spec, 1 << 14, likelihoods.Gaussian(4, sigma=0.3), seed=4)
+
+
+def test_fused_cycle_single_ellipsoid_distinct_neural_ellipsoid(golden):
+    # K = 1 with the neural bound's ellipsoid different from the mixture's:
+    # the DMMA front kernel runs two whitenings
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    spec['neural'][0]['ell']['c'] = spec['neural'][0]['ell']['c'] + 1e-3
+    _fused_vs_staged(spec, 1 << 14, likelihoods.Gaussian(30), seed=9)
+    # no unit-cube cut
+    spec['unit'] = False
+    cnt = _fused_vs_staged(spec, 5000, likelihoods.Gaussian(30), seed=10)
+    assert cnt[ops.CNT_CUBE_REJECT] == 0
+
+
+def test_front_kernels_agree(golden, monkeypatch):
+    # the DMMA front kernel (one ellipsoid) against the DFMA front kernel on
+    # the same Philox streams: same proposals up to fp64 rounding (the DMMA
+    # sums in another order and applies the radial factor after the product),
+    # same dispositions
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    like = likelihoods.Gaussian(30)
+    n = 1 << 15
+    outs = []
+    for which in ('mma', 'dfma'):
+        monkeypatch.setenv('NB200_FRONT', which)
+        stack = ops.DeviceStack([spec])
+        out = stack.cycle(0, n, seed=21, offset=5, stream_id=2,
+                          like_id=like.like_id,
+                          like_params=like.device_params('cuda'),
+                          log_l_min=0.0, mode=ops.MLP_TF32)
+        outs.append({k: v.cpu().numpy() for k, v in out.items()})
+    a, b = outs
+    assert np.max(np.abs(a['points'] - b['points'])) < 1e-13
+    assert np.mean(a['code'] != b['code']) < 1e-4
+    same = (a['code'] == 4) & (b['code'] == 4)
+    assert np.max(np.abs(a['log_l'][same] - b['log_l'][same])) < 1e-9
+    assert np.abs(a['counters'] - b['counters']).max() <= 3
