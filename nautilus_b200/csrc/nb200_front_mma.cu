@@ -57,30 +57,35 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
       : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// T[g] = M (rows 8I..8I+7) . (row_g - c) for the four proposal groups
-template <bool SUBTRACT>
-__device__ __forceinline__ void mma_rows(const double* __restrict__ frag,
-                                         int nK, int I, int kb_end,
-                                         const double* rows, int S, int p,
-                                         int q, const double* __restrict__ c,
+// T[g] = M (rows 8I..8I+7) . (row_g - c) for the four proposal groups; all
+// trip counts and strides are compile-time, so the loop unrolls into
+// LDS / DMMA with immediate offsets (the first version spent more issue
+// slots on address arithmetic than on DMMAs)
+template <int D8, bool SUBTRACT>
+__device__ __forceinline__ void mma_rows(const double* __restrict__ frag_lane,
+                                         int I, int kb_end,
+                                         const double* row_lane,
+                                         const double* __restrict__ c_lane,
                                          double (&T)[4][2]) {
+  constexpr int NK = D8 / 4, S = D8 + 4;
 #pragma unroll
   for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
-  const double* f = frag + ((size_t)I * nK) * 32 + (p * 4 + q);
-  const double* a0 = rows + p * S + q;
-#pragma unroll 2
-  for (int Kb = 0; Kb < kb_end; ++Kb) {
-    const double b = f[Kb * 32];
-    const double cq = SUBTRACT ? c[4 * Kb + q] : 0.0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      double a = a0[g * 8 * S + 4 * Kb];
-      if (SUBTRACT) a -= cq;
-      dmma(T[g], a, b);
+  for (int Kb = 0; Kb < NK; ++Kb) {
+    if (Kb < kb_end) {
+      const double b = frag_lane[(I * NK + Kb) * 32];
+      const double cq = SUBTRACT ? c_lane[4 * Kb] : 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        double a = row_lane[g * 8 * S + 4 * Kb];
+        if (SUBTRACT) a -= cq;
+        dmma(T[g], a, b);
+      }
     }
   }
 }
 
+template <int D8>
 __global__ void __launch_bounds__(FM_THREADS, 2)
 k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             const double* __restrict__ data, double* __restrict__ points,
@@ -88,8 +93,8 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             float* __restrict__ xs32) {
   extern __shared__ __align__(16) double sm[];
   const Rec rec{meta + A.rec_off};
-  const int d = A.d, d8 = A.d8, S = A.S;
-  const int nI = d8 >> 3, nK = d8 >> 2;
+  constexpr int d8 = D8, S = D8 + 4, nI = D8 / 8, nK = D8 / 4;
+  const int d = A.d;
   const int fsz = d8 * d8;                 // doubles per staged factor
   double* fB = sm;                         // B        in fragment order
   double* fBinv = fB + fsz;                // B_inv (mixture)
@@ -188,10 +193,15 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     // ---- x = s (B z) + c in place, highest row block first (B is lower
     // triangular: block I needs z[k < 8I + 8], which the blocks below have
     // not overwritten); unit-cube test on the fragments ----------------------
+    // The coordinates also leave for global memory straight from the
+    // fragments: the four lanes of a proposal cover 64 contiguous bytes.
     bool cube[4] = {true, true, true, true};
+    const double* row_lane = rows + p * S + q;
+    const bool pair_ok = (d & 1) == 0;     // 16-byte stores need even offsets
+#pragma unroll
     for (int I = nI - 1; I >= 0; --I) {
       double T[4][2];
-      mma_rows<false>(fB, nK, I, 2 * I + 2, rows, S, p, q, nullptr, T);
+      mma_rows<D8, false>(fB + lane, I, 2 * I + 2, row_lane, nullptr, T);
       __syncwarp();              // every lane has read this block's columns
       const int i0 = 8 * I + 2 * q;
       const double c0 = cM[i0], c1 = cM[i0 + 1];
@@ -203,6 +213,16 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             make_double2(x0, x1);
         if (i0 < d) cube[g] = cube[g] && (x0 >= 0.0) && (x0 < 1.0);
         if (i0 + 1 < d) cube[g] = cube[g] && (x1 >= 0.0) && (x1 < 1.0);
+        const long long gi = base + 8 * g + p;
+        if (gi < A.n) {
+          double* dst = points + gi * (long long)d + i0;
+          if (pair_ok && i0 + 1 < d) {
+            *reinterpret_cast<double2*>(dst) = make_double2(x0, x1);
+          } else {
+            if (i0 < d) dst[0] = x0;
+            if (i0 + 1 < d) dst[1] = x1;
+          }
+        }
       }
     }
     unsigned cube_bits = 0;
@@ -219,20 +239,23 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     double r2m[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the mixture's ellipsoid
     double r2n[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the neural bound's
     if (!A.same) {
+#pragma unroll
       for (int I = 0; I < nI; ++I) {
         double T[4][2];
-        mma_rows<true>(fBinv, nK, I, A.lower_b ? 2 * I + 2 : nK, rows, S, p,
-                       q, cM, T);
+        mma_rows<D8, true>(fBinv + lane, I, A.lower_b ? 2 * I + 2 : nK,
+                           row_lane, cM + q, T);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           r2m[g] = fma(T[g][1], T[g][1], fma(T[g][0], T[g][0], r2m[g]));
       }
     }
-    for (int I = 0; 8 * I < A.k0p; ++I) {
+#pragma unroll
+    for (int I = 0; I < nI + 1; ++I) {
+      if (8 * I >= A.k0p) break;
       double T[4][2];
       if (I < nI) {
-        mma_rows<true>(fNeural, nK, I, lower_n ? 2 * I + 2 : nK, rows, S, p,
-                       q, cN, T);
+        mma_rows<D8, true>(fNeural + lane, I, lower_n ? 2 * I + 2 : nK,
+                           row_lane, cN + q, T);
       } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
@@ -300,19 +323,6 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
                                     rows + (8 * q + p) * S, d)
                 : nan("");
     }
-    // ---- the 32 rows leave as one contiguous block --------------------------
-    {
-      const int nrows = (int)min(32ll, A.n - base);
-      double* gdst = points + base * (long long)d;
-      const int total = nrows * d;
-      int r = lane / d, c = lane % d;
-      const int step_r = 32 / d, step_c = 32 % d;
-      for (int e = lane; e < total; e += 32) {
-        gdst[e] = rows[r * S + c];
-        r += step_r; c += step_c;
-        if (c >= d) { c -= d; r += 1; }
-      }
-    }
     __syncwarp();
   }
 }
@@ -327,6 +337,7 @@ bool front_mma_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   const int d = rec.d();
   if (rec.mix(0)[1] != 0 || rec.mix(0)[0] != d) return false;
   const int d8 = (d + 7) / 8 * 8;
+  if (d8 > 64) return false;
   const int S = d8 + 4;
   const int same = rec.r[10] - 1 == 0;
   const size_t doubles = (size_t)(same ? 2 : 3) * d8 * d8 + 4 * (size_t)d8 +
@@ -354,7 +365,20 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
            "DMMA front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
-  NB_CUDA(cudaFuncSetAttribute(k_front_mma,
+  void (*kern)(const FrontMmaArgs, const int32_t*, const double*, double*,
+               uint8_t*, uint8_t*, float*) = nullptr;
+  switch (A.d8) {
+    case 8: kern = k_front_mma<8>; break;
+    case 16: kern = k_front_mma<16>; break;
+    case 24: kern = k_front_mma<24>; break;
+    case 32: kern = k_front_mma<32>; break;
+    case 40: kern = k_front_mma<40>; break;
+    case 48: kern = k_front_mma<48>; break;
+    case 56: kern = k_front_mma<56>; break;
+    case 64: kern = k_front_mma<64>; break;
+    default: NB_CHECK(false, "DMMA front kernel: n_dim > 64");
+  }
+  NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   int dev = 0, sms = 0;
@@ -367,8 +391,8 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   ProfScope prof(ST_FUSED, st);
-  k_front_mma<<<(unsigned)grid, FM_THREADS, smem, st>>>(
-      A, meta_d, data_d, points, code, maskj, xs32);
+  kern<<<(unsigned)grid, FM_THREADS, smem, st>>>(A, meta_d, data_d, points,
+                                                 code, maskj, xs32);
   NB_LAUNCH_OK();
   return 0;
 }

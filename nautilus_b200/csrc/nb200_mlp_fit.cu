@@ -39,7 +39,10 @@ constexpr int FIT_MAX_LAYERS = 6;   // weight matrices
 // parameter set, and the minibatch gradient is all-reduced through
 // distributed shared memory, in rank order, so that all CTAs apply the same
 // Adam step to bit-identical weights.
-constexpr int FIT_CLUSTER = 4;
+#ifndef NB200_FIT_CLUSTER
+#define NB200_FIT_CLUSTER 4
+#endif
+constexpr int FIT_CLUSTER = NB200_FIT_CLUSTER;
 
 struct FitArgs {
   int n_lay, d, batch, max_epochs, patience;

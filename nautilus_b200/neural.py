@@ -94,6 +94,7 @@ class NeuralNetworkEmulator:
                 off += fo
             emulator.neural_networks.append(
                 FittedNetwork(coefs, intercepts, n_iter[i], loss[i]))
+        emulator.n_train_ = len(x)      # rows the ensemble was fitted on
         emulator._stack = None
         return emulator
 

@@ -58,6 +58,16 @@ def main():
         prof.disable()
         pstats.Stats(prof).sort_stats('cumulative').print_stats(28)
     raw = sum(b.outer_bound.n_sample for b in sampler.bounds[1:])
+    emus = [nb.emulator for b in sampler.bounds[1:] for nb in b.neural_bounds
+            if nb.emulator is not None]
+    fit = dict(n_fits=len(emus),
+               rows_mean=float(np.mean([e.n_train_ for e in emus])),
+               rows_max=int(np.max([e.n_train_ for e in emus])),
+               epochs_mean=float(np.mean([n.n_iter_ for e in emus
+                                          for n in e.neural_networks])),
+               epochs_max=int(np.max([n.n_iter_ for e in emus
+                                      for n in e.neural_networks]))) \
+        if emus else None
     print(json.dumps({
         'config': args.config, 'success': bool(ok), 'wall_s': wall,
         'n_like': int(sampler.n_like), 'n_bounds': len(sampler.bounds),
@@ -66,7 +76,7 @@ def main():
                         abs(float(sampler.log_z) - like.log_z_true)),
         'f_live': None if sampler.explored else float(sampler.f_live),
         'n_eff': float(sampler.n_eff), 'raw_proposals': int(raw),
-        'emulator_arith': args.arith, 'n_batch': sampler.n_batch,
+        'emulator_fits': fit, 'emulator_arith': args.arith, 'n_batch': sampler.n_batch,
         'discard_exploration': not args.keep_exploration}), flush=True)
 
 
