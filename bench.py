@@ -430,6 +430,30 @@ def run_gpu(args):
             'bytes_per_launch': nbytes, 'ms_per_launch': stage_ms[top]}
     roofline['share_of_step'] = stage_ms[top] / total_stage
     roofline['stages_ms'] = stage_ms
+    # the other ceilings of the two hot kernels: the
+    # front kernel's two triangular matrix-vector products on the FP64 tensor
+    # cores (peak measured by tools/peak_dmma.cu) and the emulator's dense
+    # contraction on tcgen05 (kind::tf32, whose peak is half the bf16 one)
+    fp64_peak = 37.0
+    ppath = os.path.join(ROOT, 'profiles', 'r1_peak_dmma.json')
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            fp64_peak = float(json.load(f)['dmma_tflops_w8_16warps'])
+    if 'fused_cycle' in stage_ms:
+        fl = 2.0 * 2 * (D * (D + 1) / 2) * n      # x = Bz + c, t = Binv(x - c)
+        ach = fl / (stage_ms['fused_cycle'] * 1e-3) / 1e12
+        roofline['front_fp64'] = {
+            'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+            'frac': ach / fp64_peak, 'flops_per_launch': fl,
+            'peak_source': 'measured DMMA m8n8k4 (profiles/r1_peak_dmma.json)'}
+    if 'mlp_predict' in stage_ms:
+        fl = MLP_FLOPS_PER_POINT * evaluated
+        ach = fl / (stage_ms['mlp_predict'] * 1e-3) / 1e12
+        roofline['emulator_tensor'] = {
+            'achieved': ach, 'peak': peaks['bf16'], 'unit': 'TFLOP/s',
+            'frac': ach / peaks['bf16'], 'flops_per_launch': fl,
+            'arith': args.mlp,
+            'peak_source': peaks['source'] + ', dense bf16 burst'}
     # whole-step figure against the 8d+9 B/proposal HBM roofline
     roofline['cycle_hbm_frac'] = (value / world * ALGO_BYTES_PER_PROPOSAL /
                                   1e9) / peaks['hbm']

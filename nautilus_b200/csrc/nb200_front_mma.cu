@@ -158,7 +158,12 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
                        A.stream_id, A.seed);
       double acc = 0.0;
       double* zr = rows + (8 * g + p) * S;
-      for (int b = q; b < nK; b += 4) {   // nK blocks cover the padded row
+      // nK blocks cover the padded row; compile-time trip count, so that the
+      // Philox chains of all blocks and groups interleave (ILP)
+#pragma unroll
+      for (int bb = 0; bb < (nK + 3) / 4; ++bb) {
+        const int b = q + 4 * bb;
+        if (b >= nK) continue;
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         if (b < nblk) {
           const uint4 w = rng.block(1 + b);

@@ -28,6 +28,8 @@ for x in "$@"; do
     e2e2) timeout 600 python tools/run_config.py --config 2 --n-batch 1000 --profile > $OUT/e2e_cfg2.log 2>&1
           echo "e2e2 rc=$?" | tee -a $OUT/summary.txt; tail -45 $OUT/e2e_cfg2.log;;
     e2e1) timeout 300 python tools/run_config.py --config 1 > $OUT/e2e_cfg1.log 2>&1; tail -2 $OUT/e2e_cfg1.log;;
+    ncufit) timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mlp_fit -c 1 -f -o $OUT/fit_kernel python tools/bench_fit.py > $OUT/ncu_fit.log 2>&1; echo "ncufit rc=$?" | tee -a $OUT/summary.txt;;
+    fitab) bash tools/fit_ab.sh $TAG;;
     timeline) NB200_EXTRA_FLAGS=-DNB200_TIMELINE timeout 300 python tools/mlp_timeline.py > $OUT/mlp_timeline.txt 2>&1;;
   esac
 done
