@@ -40,7 +40,7 @@ constexpr int FIT_MAX_LAYERS = 6;   // weight matrices
 // distributed shared memory, in rank order, so that all CTAs apply the same
 // Adam step to bit-identical weights.
 #ifndef NB200_FIT_CLUSTER
-#define NB200_FIT_CLUSTER 4
+#define NB200_FIT_CLUSTER 8
 #endif
 constexpr int FIT_CLUSTER = NB200_FIT_CLUSTER;
 
@@ -64,6 +64,10 @@ __device__ __forceinline__ long long gcd_ll(long long a, long long b) {
   return a;
 }
 
+// BIG is a template parameter so that in the usual (small) mode every
+// parameter / gradient / activation access is provably a shared-memory access
+// (LDS/STS instead of generic loads)
+template <bool BIG>
 __global__ void __cluster_dims__(FIT_CLUSTER, 1, 1)
 __launch_bounds__(FIT_THREADS, 1)
 k_mlp_fit(const FitArgs A, const float* __restrict__ x,
@@ -74,13 +78,13 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   // per-CTA parameter storage: shared memory, or global memory in big mode
   // ([W | G | Gq] per CTA, Gq padded to n_params for simple indexing)
   float* big_base = big_store + (size_t)blockIdx.x * 3 * A.n_params;
-  float* W = A.big ? big_base : fs;    // parameters of this network
-  float* G = A.big ? big_base + A.n_params : fs + A.n_params;
-  float* act = A.big ? fs : fs + 2 * A.n_params;   // activations a_0..a_L
+  float* W = BIG ? big_base : fs;    // parameters of this network
+  float* G = BIG ? big_base + A.n_params : fs + A.n_params;
+  float* act = BIG ? fs : fs + 2 * A.n_params;   // activations a_0..a_L
   float* dl0 = fs + A.delta_off;       // delta ping-pong
   float* dl1 = dl0 + A.rows * A.delta_stride;
   // this CTA's reduced quarter of G
-  float* Gq = A.big ? big_base + 2 * A.n_params : fs + A.gsum_off;
+  float* Gq = BIG ? big_base + 2 * A.n_params : fs + A.gsum_off;
   __shared__ float red[FIT_THREADS / 32];
   __shared__ float s_loss;
   __shared__ float s_bsq;              // this CTA's share of sum (y - t)^2
@@ -168,12 +172,41 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               acc[j] = (n0 + j < fo) ? bl[n0 + j] : 0.f;
-            for (int k = 0; k < fi; ++k) {
-              const float a = ok ? in[mrow * si + k] : 0.f;
-              const float* wr = Wl + k * fo + n0;
+            const float* ap = in + mrow * si;
+            if (n0 + 8 <= fo) {
+              // full tile: no per-element predicates; 8-byte weight loads
+              // when the rows of W are 8-byte aligned
+              if (!BIG && ((fo | A.w_off[l]) & 1) == 0) {
+                const float2* wr2 =
+                    reinterpret_cast<const float2*>(Wl + n0);
+                const int ld2 = fo >> 1;
+#pragma unroll 4
+                for (int k = 0; k < fi; ++k) {
+                  const float a = ok ? ap[k] : 0.f;
+                  const float2 w0 = wr2[k * ld2], w1 = wr2[k * ld2 + 1];
+                  const float2 w2 = wr2[k * ld2 + 2], w3 = wr2[k * ld2 + 3];
+                  acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
+                  acc[2] = fmaf(a, w1.x, acc[2]); acc[3] = fmaf(a, w1.y, acc[3]);
+                  acc[4] = fmaf(a, w2.x, acc[4]); acc[5] = fmaf(a, w2.y, acc[5]);
+                  acc[6] = fmaf(a, w3.x, acc[6]); acc[7] = fmaf(a, w3.y, acc[7]);
+                }
+              } else {
+#pragma unroll 4
+                for (int k = 0; k < fi; ++k) {
+                  const float a = ok ? ap[k] : 0.f;
+                  const float* wr = Wl + k * fo + n0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (n0 + j < fo) acc[j] = fmaf(a, wr[j], acc[j]);
+                  for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                }
+              }
+            } else {
+              for (int k = 0; k < fi; ++k) {
+                const float a = ok ? ap[k] : 0.f;
+                const float* wr = Wl + k * fo + n0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n0 + j < fo) acc[j] = fmaf(a, wr[j], acc[j]);
+              }
             }
             if (ok) {
 #pragma unroll
@@ -225,12 +258,23 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
               float acc[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-              for (int mm = 0; mm < R; ++mm) {
-                const float dv = ok ? dcur[mm * A.delta_stride + n] : 0.f;
-                const float* ar = ain + mm * si + k0;
+              const float* dp = dcur + n;
+              if (k0 + 8 <= fi) {
+#pragma unroll 4
+                for (int mm = 0; mm < R; ++mm) {
+                  const float dv = ok ? dp[mm * A.delta_stride] : 0.f;
+                  const float* ar = ain + mm * si + k0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (k0 + j < fi) acc[j] = fmaf(ar[j], dv, acc[j]);
+                  for (int j = 0; j < 8; ++j) acc[j] = fmaf(ar[j], dv, acc[j]);
+                }
+              } else {
+                for (int mm = 0; mm < R; ++mm) {
+                  const float dv = ok ? dp[mm * A.delta_stride] : 0.f;
+                  const float* ar = ain + mm * si + k0;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (k0 + j < fi) acc[j] = fmaf(ar[j], dv, acc[j]);
+                }
               }
               if (ok) {
 #pragma unroll
@@ -255,11 +299,23 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
               float acc[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-              for (int n = 0; n < fo; ++n) {
-                const float dv = ok ? dcur[mrow * A.delta_stride + n] : 0.f;
+              const float* dp = dcur + mrow * A.delta_stride;
+              const float* wk = Wl + k0 * fo;
+              if (k0 + 8 <= fi) {
+#pragma unroll 4
+                for (int n = 0; n < fo; ++n) {
+                  const float dv = ok ? dp[n] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (k0 + j < fi) acc[j] = fmaf(dv, Wl[(k0 + j) * fo + n], acc[j]);
+                  for (int j = 0; j < 8; ++j)
+                    acc[j] = fmaf(dv, wk[j * fo + n], acc[j]);
+                }
+              } else {
+                for (int n = 0; n < fo; ++n) {
+                  const float dv = ok ? dp[n] : 0.f;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (k0 + j < fi) acc[j] = fmaf(dv, wk[j * fo + n], acc[j]);
+                }
               }
               if (ok) {
 #pragma unroll
@@ -276,7 +332,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       }
       // ---- all-reduce of the gradient and the loss over the cluster -----------
       if (tid == 0) s_bsq = batch_sq;
-      if (A.big) __threadfence();      // G lives in global memory
+      if (BIG) __threadfence();      // G lives in global memory
       cluster.sync();
       // reduce-scatter: this CTA sums ITS quarter of the gradient over all
       // ranks (rank order => identical on every CTA) ...
@@ -288,10 +344,10 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
 #pragma unroll
           for (int q = 0; q < FIT_CLUSTER; ++q) {
             const float* Gp =
-                A.big ? big_store + ((size_t)(blockIdx.x - crank + q) * 3 + 1) *
-                                        A.n_params
-                      : cluster.map_shared_rank(G, q);
-            g += A.big ? __ldcg(Gp + e) : Gp[e];
+                BIG ? big_store + ((size_t)(blockIdx.x - crank + q) * 3 + 1) *
+                                      A.n_params
+                    : cluster.map_shared_rank(G, q);
+            g += BIG ? __ldcg(Gp + e) : Gp[e];
           }
           Gq[e - lo] = g;
         }
@@ -301,7 +357,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           t += *cluster.map_shared_rank(&s_bsq, q);
         batch_sq = t;
       }
-      if (A.big) __threadfence();
+      if (BIG) __threadfence();
       cluster.sync();      // ... all-gather happens inside the Adam loop
       // ---- Adam step on the whole minibatch gradient --------------------------
       t_adam += 1;
@@ -311,7 +367,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       for (int e = tid; e < P; e += FIT_THREADS) {
         const int owner = e / A.p_quarter;
         const float gq =
-            A.big ? __ldcg(big_store +
+            BIG ? __ldcg(big_store +
                            ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
                                A.n_params + (e - owner * A.p_quarter))
                   : cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
@@ -441,12 +497,14 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
   NB_LAUNCH_OK();
   k_f64_to_f32<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(y_d, m, y32);
   NB_LAUNCH_OK();
-  NB_CUDA(cudaFuncSetAttribute(k_mlp_fit,
+  auto kern = A.big ? k_mlp_fit<true> : k_mlp_fit<false>;
+  NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  k_mlp_fit<<<n_net * FIT_CLUSTER, FIT_THREADS, smem, st>>>(A, x32, y32, moments,
-                                              weights_out_d, n_iter_out_d,
-                                              loss_out_d, big_store);
+  kern<<<n_net * FIT_CLUSTER, FIT_THREADS, smem, st>>>(A, x32, y32, moments,
+                                                       weights_out_d,
+                                                       n_iter_out_d,
+                                                       loss_out_d, big_store);
   NB_LAUNCH_OK();
   return 0;
 }
