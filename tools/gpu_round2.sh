@@ -30,6 +30,10 @@ for x in "$@"; do
     e2e1) timeout 300 python tools/run_config.py --config 1 > $OUT/e2e_cfg1.log 2>&1; tail -2 $OUT/e2e_cfg1.log;;
     ncufit) timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mlp_fit -c 1 -f -o $OUT/fit_kernel python tools/bench_fit.py > $OUT/ncu_fit.log 2>&1; echo "ncufit rc=$?" | tee -a $OUT/summary.txt;;
     fitab) bash tools/fit_ab.sh $TAG;;
+    mvee) python tools/bench_mvee.py > $OUT/mvee.json 2>&1; cat $OUT/mvee.json
+          timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_mvee -c 1 -f -o $OUT/mvee_kernel python tools/bench_mvee.py > $OUT/ncu_mvee.log 2>&1;;
+    fit) python tools/bench_fit.py --sklearn > $OUT/fit.json 2>&1; cat $OUT/fit.json;;
+    e2e4) timeout 900 python tools/run_config.py --config 4 --n-batch 1000 > $OUT/e2e_cfg4.log 2>&1; tail -2 $OUT/e2e_cfg4.log;;
     timeline) NB200_EXTRA_FLAGS=-DNB200_TIMELINE timeout 300 python tools/mlp_timeline.py > $OUT/mlp_timeline.txt 2>&1;;
   esac
 done
