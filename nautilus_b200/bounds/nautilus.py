@@ -49,14 +49,22 @@ class NautilusBound(_DeviceBound):
             bound_class=Ellipsoid, rng=rng)
         while clusters.split(allow_overlap=False):
             pass
+        # The emulator fits (32 SMs, ~0.1-0.3 s each) are enqueued on a side
+        # stream and collected after the outer union has been built on the
+        # main stream: the two do not depend on each other, and the order in
+        # which `rng` is consumed is that of the sequential code.
         bound.neural_bounds = []
-        for ell in clusters.bounds:
-            member = ell.contains(points)
-            bound.neural_bounds.append(NeuralBound.compute(
-                points[member], log_l[member], log_l_min,
-                enlarge_per_dim=enlarge_per_dim, n_networks=n_networks,
-                neural_network_kwargs=neural_network_kwargs, pool=pool,
-                rng=rng, mode=bound.mode))
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for ell in clusters.bounds:
+                member = ell.contains(points)
+                bound.neural_bounds.append(NeuralBound.compute(
+                    points[member], log_l[member], log_l_min,
+                    enlarge_per_dim=enlarge_per_dim, n_networks=n_networks,
+                    neural_network_kwargs=neural_network_kwargs, pool=pool,
+                    rng=rng, mode=bound.mode, defer=True))
 
         # outer sampling bound, refined until close enough to the target volume
         bound.outer_bound = Union.compute(
@@ -69,6 +77,10 @@ class NautilusBound(_DeviceBound):
         while bound.outer_bound.log_v - log_v_target > slack:
             if not bound.outer_bound.trim():
                 break
+
+        for nb in bound.neural_bounds:
+            nb.finish()
+        main.wait_stream(side)
 
         bound.stream = PhiloxStream(rng)
         bound._clear()

@@ -18,7 +18,10 @@ class NeuralBound(_DeviceBound):
     @classmethod
     def compute(cls, points, log_l, log_l_min, enlarge_per_dim=1.1,
                 n_networks=4, neural_network_kwargs={}, pool=None, rng=None,
-                mode=None):
+                mode=None, defer=False):
+        """``defer=True`` returns as soon as the fit kernel is enqueued;
+        ``finish()`` must be called before the bound is used (the caller may
+        build other bounds in between, on another stream)."""
         bound = cls()
         bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
         points = np.asarray(points, dtype=float)
@@ -46,17 +49,28 @@ class NeuralBound(_DeviceBound):
         score[live] = 0.5 + 0.5 * (rankdata(log_l[live]) - 0.5) / np.sum(live)
         score[~live] = 0.5 * (rankdata(log_l[~live]) - 0.5) / max(
             np.sum(~live), 1)
-        bound.emulator = NeuralNetworkEmulator.train(
+        bound.emulator = NeuralNetworkEmulator.train_async(
             whitened, score, n_networks=n_networks,
             neural_network_kwargs=neural_network_kwargs, pool=pool,
             seed=int(rng.integers(0, 2**63 - 1)))
+        bound._unfinished = (whitened, score, live)
+        return bound if defer else bound.finish()
+
+    def finish(self):
+        """Second half of ``compute``: wait for the fit, set the threshold."""
+        unfinished = getattr(self, '_unfinished', None)
+        if unfinished is None:
+            return self
+        whitened, score, live = unfinished
+        self._unfinished = None
+        self.emulator.wait()
         # threshold: cubic fit of predicted vs true score, evaluated at the
         # lowest live score (neural.py:93-95)
-        bound.emulator.mode = bound.mode
-        predicted = bound.emulator.predict(whitened)
-        bound.score_predict_min = float(np.polyval(
+        self.emulator.mode = self.mode
+        predicted = self.emulator.predict(whitened)
+        self.score_predict_min = float(np.polyval(
             np.polyfit(score, predicted, 3), np.amin(score[live])))
-        return bound
+        return self
 
     def nb_spec(self):
         return dict(ell=self.outer_bound.ell_spec(),

@@ -45,7 +45,19 @@ class NeuralNetworkEmulator:
               seed=0):
         """Standardise ``x`` and fit ``n_networks`` networks
         (nautilus/neural.py:50-98).  ``pool`` is accepted for API
-        compatibility; the networks train concurrently, one CTA each."""
+        compatibility; the networks train concurrently, one CTA cluster
+        each."""
+        return cls.train_async(x, y, n_networks, neural_network_kwargs, pool,
+                               seed).wait()
+
+    @classmethod
+    def train_async(cls, x, y, n_networks=4, neural_network_kwargs={},
+                    pool=None, seed=0):
+        """``train`` without the final synchronisation: the fit kernel is
+        enqueued on the current CUDA stream and ``wait()`` collects the
+        weights.  Lets the caller build the rest of a bound while the
+        networks train (bounds/nautilus.py: the outer union does not depend
+        on them)."""
         emulator = cls()
         x = np.asarray(x, dtype=float)
         y = np.asarray(y, dtype=float)
@@ -81,6 +93,20 @@ class NeuralNetworkEmulator:
             eps=kwargs.get('epsilon', 1e-8), batch_size=batch_size,
             max_epochs=kwargs['max_iter'], tol=kwargs['tol'],
             patience=kwargs['n_iter_no_change'])
+        emulator.n_train_ = len(x)      # rows the ensemble was fitted on
+        emulator._pending = (params, n_iter, loss, sizes, n_networks,
+                             torch.cuda.current_stream())
+        return emulator
+
+    def wait(self):
+        """Collect the result of ``train_async`` (idempotent)."""
+        pending = getattr(self, '_pending', None)
+        if pending is None:
+            return self
+        params, n_iter, loss, sizes, n_networks, stream = pending
+        self._pending = None
+        emulator = self
+        stream.synchronize()
         params = params.cpu().numpy()
         n_iter = n_iter.cpu().numpy()
         loss = loss.cpu().numpy()
@@ -94,7 +120,6 @@ class NeuralNetworkEmulator:
                 off += fo
             emulator.neural_networks.append(
                 FittedNetwork(coefs, intercepts, n_iter[i], loss[i]))
-        emulator.n_train_ = len(x)      # rows the ensemble was fitted on
         emulator._stack = None
         return emulator
 
