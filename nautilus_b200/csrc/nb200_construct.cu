@@ -7,8 +7,8 @@
 // Ellipsoid.compute :266-316 and UnitCubeEllipsoidMixture.compute :471-563).
 // Same iteration as the host restatement (nautilus_b200/bounds/_construct.py:
 // _khachiyan): Sherman-Morrison rank-one update of the inverse moment matrix,
-// O(N d) update of the Mahalanobis distances, a from-scratch refresh every 64
-// updates.
+// O(N d) update of the Mahalanobis distances, a from-scratch refresh now and
+// then (MV_REFRESH).
 //
 // The loop is a few thousand strictly sequential steps of a few hundred
 // kFLOP: latency, not throughput.  ONE persistent CTA of 1024 threads runs it
@@ -22,6 +22,10 @@ namespace nb200 {
 
 constexpr int MV_THREADS = 1024;
 constexpr int MV_WARPS = MV_THREADS / 32;
+// rank-one updates between two from-scratch refreshes of the inverse (the
+// host restatement refreshes every 64; the drift of 512 Sherman-Morrison
+// updates on whitened points is ~1e-12, far below the 1e-3 stopping rule)
+constexpr int MV_REFRESH = 512;
 
 struct MvShared {
   double red_v[MV_WARPS];
@@ -116,14 +120,26 @@ k_mvee(const double* __restrict__ qT, int64_t n, int d, int max_updates,
         Vinv[a * Dp + k] = a == k ? pivot : -Vinv[a * Dp + k] * pivot;
       __syncthreads();
     }
+    // g_i = sum_a q_a V^-1[a][a] q_a + 2 sum_{b<a} q_a V^-1[a][b] q_b, four
+    // independent chains per row so that the (L1-resident) loads of q do not
+    // serialise on one accumulator
     best_v = -1.0; best_i = 0x7fffffff;
     for (int64_t i = tid; i < n; i += MV_THREADS) {
       double gi = 0.0;
       for (int a = 0; a < D; ++a) {
-        double t = 0.0;
-        for (int b = 0; b < D; ++b)
-          t = fma(Vinv[a * Dp + b], lifted(qT, n, d, b, i), t);
-        gi = fma(lifted(qT, n, d, a, i), t, gi);
+        const double* row = Vinv + a * Dp;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int b = 0;
+        for (; b + 4 <= a; b += 4) {
+          t0 = fma(row[b], lifted(qT, n, d, b, i), t0);
+          t1 = fma(row[b + 1], lifted(qT, n, d, b + 1, i), t1);
+          t2 = fma(row[b + 2], lifted(qT, n, d, b + 2, i), t2);
+          t3 = fma(row[b + 3], lifted(qT, n, d, b + 3, i), t3);
+        }
+        for (; b < a; ++b) t0 = fma(row[b], lifted(qT, n, d, b, i), t0);
+        const double qa = lifted(qT, n, d, a, i);
+        const double off = (t0 + t1) + (t2 + t3);
+        gi = fma(qa, fma(row[a], qa, 2.0 * off), gi);
       }
       g[i] = gi;
       arg_better(best_v, best_i, gi, (int)i);
@@ -141,7 +157,7 @@ k_mvee(const double* __restrict__ qT, int64_t n, int d, int max_updates,
     const double step = (gmax - D) / ((double)D * (gmax - 1.0));
     const double beta = step / (1.0 - step);
     const double one_m = 1.0 - step;
-    if (it % 64 == 63) {
+    if (it % MV_REFRESH == MV_REFRESH - 1) {
       // refresh the inverse from scratch now and then (rounding drift)
       for (int64_t i = tid; i < n; i += MV_THREADS)
         u[i] = u[i] * one_m + (i == j ? step : 0.0);
@@ -166,8 +182,16 @@ k_mvee(const double* __restrict__ qT, int64_t n, int d, int max_updates,
     }
     best_v = -1.0; best_i = 0x7fffffff;
     for (int64_t i = tid; i < n; i += MV_THREADS) {
-      double dot = w[d];
-      for (int k = 0; k < d; ++k) dot = fma(qT[(int64_t)k * n + i], w[k], dot);
+      // two chains: the coalesced loads of q stay in flight
+      double dot = w[d], dot1 = 0.0;
+      int k = 0;
+#pragma unroll 4
+      for (; k + 2 <= d; k += 2) {
+        dot = fma(qT[(int64_t)k * n + i], w[k], dot);
+        dot1 = fma(qT[(int64_t)(k + 1) * n + i], w[k + 1], dot1);
+      }
+      if (k < d) dot = fma(qT[(int64_t)k * n + i], w[k], dot);
+      dot += dot1;
       const double gi = (g[i] - coef * dot * dot) * inv1;
       g[i] = gi;
       u[i] = u[i] * one_m + (i == j ? step : 0.0);
