@@ -4,8 +4,14 @@ import numpy as np
 import torch
 
 
+_HAVE_CUDA = None
+
+
 def default_device():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:          # asked thousands of times per run
+        _HAVE_CUDA = bool(torch.cuda.is_available())
+    if not _HAVE_CUDA:
         raise RuntimeError(
             'nautilus_b200 needs a CUDA device (B200); there is no CPU path.')
     return torch.device('cuda', torch.cuda.current_device())
