@@ -244,7 +244,8 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nautilus_b200 import likelihoods, ops
-    from nautilus_b200.pool import exchange_stats_async, merge_gathered
+    from nautilus_b200.pool import (exchange_packed_async, merge_packed,
+                                    packed_stats)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -270,8 +271,11 @@ def run_gpu(args):
 
     out = stack.cycle(0, n, seed=seed, like_id=like.like_id,
                       like_params=like_params, log_l_min=log_l_min, mode=mode)
-    packed = torch.zeros(ops.N_CNT + 4, dtype=torch.float64, device=dev)
-    gathered = torch.zeros((world, ops.N_CNT + 4), dtype=torch.float64,
+    # the kernels write the sums and counters straight into the send buffer
+    # of the one collective
+    words, out['lse'], out['counters'] = packed_stats(dev, ops.N_CNT,
+                                                      ops.N_LSE)
+    gathered = torch.zeros((world, ops.N_LSE + ops.N_CNT), dtype=torch.int64,
                            device=dev)
     state = {'step': 0, 'merged': None}
 
@@ -286,8 +290,7 @@ def run_gpu(args):
         if world > 1:
             # the one exchange step: per-rank counters + LSE partials; like
             # the single-GPU results they stay on the device until read
-            exchange_stats_async(out['counters'], out['lse'],
-                                 gathered=gathered, packed=packed)
+            exchange_packed_async(words, gathered=gathered)
 
     def barrier():
         if world > 1:
@@ -324,7 +327,7 @@ def run_gpu(args):
 
     # result of the last step (also a sanity check on the collective)
     if world > 1:
-        cnt, (m, s1, s2) = merge_gathered(gathered, ops.N_CNT)
+        cnt, (m, s1, s2) = merge_packed(gathered, ops.N_LSE)
         cnt = cnt.astype(float)
     else:
         cnt = out['counters'].cpu().numpy().astype(float)

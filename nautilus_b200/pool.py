@@ -133,6 +133,40 @@ def exchange_stats_async(counters, lse, gathered=None, packed=None,
     return gathered
 
 
+def packed_stats(device, n_cnt=8, n_lse=4):
+    """One 8-byte-word buffer that holds a cycle's LSE partials (float64) and
+    counters (int64) side by side, so that the kernels write straight into
+    the send buffer of the collective: returns (words i64[n_lse + n_cnt],
+    lse f64 view, counters i64 view)."""
+    import torch
+    words = torch.zeros(n_lse + n_cnt, dtype=torch.int64, device=device)
+    return words, words[:n_lse].view(torch.float64), words[n_lse:]
+
+
+def exchange_packed_async(words, gathered=None, group=None):
+    """All-gather the raw words of :func:`packed_stats` (no packing kernels,
+    counters stay exact int64).  Returns the gathered [world, n] int64 tensor
+    on the device; nothing is synchronised."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if gathered is None:
+        gathered = torch.empty((world, words.numel()), dtype=torch.int64,
+                               device=words.device)
+    dist.all_gather_into_tensor(gathered.view(-1), words, group=group)
+    return gathered
+
+
+def merge_packed(gathered, n_lse=4):
+    """(counters int64 ndarray, (m, s1, s2)) from :func:`exchange_packed_async`;
+    every rank gets the same answer (merge in rank order)."""
+    import numpy as np
+    g = np.ascontiguousarray(gathered.cpu().numpy())
+    lse = g[:, :n_lse].copy().view(np.float64)
+    total = g[:, n_lse:].sum(axis=0)
+    return total, merge_lse([tuple(r[:3]) for r in lse])
+
+
 def merge_gathered(gathered, n_cnt=8):
     """(counters int64 ndarray, (m, s1, s2)) from the gathered per-rank rows;
     every rank gets the same answer (merge in rank order)."""

@@ -14,7 +14,9 @@ torch = pytest.importorskip('torch')
 import torch.distributed as dist  # noqa: E402
 import torch.multiprocessing as mp  # noqa: E402
 
-from nautilus_b200.pool import GpuPool, exchange_stats, merge_lse  # noqa: E402
+from nautilus_b200.pool import (GpuPool, exchange_packed_async,  # noqa: E402
+                                exchange_stats, merge_lse, merge_packed,
+                                packed_stats)
 from oracle import nautilus_oracle as orc  # noqa: E402
 from oracle import philox  # noqa: E402
 
@@ -48,6 +50,13 @@ def _rank_main(rank, world, port, n, out):
     total, lse = exchange_stats(torch.from_numpy(cnt),
                                 torch.tensor([m, s1, s2, 0.0],
                                              dtype=torch.float64))
+    # the packed form (what bench.py uses: kernels write into the send
+    # buffer) must give the same answer, with exact int64 counters
+    words, lse_v, cnt_v = packed_stats('cpu')
+    cnt_v.copy_(torch.from_numpy(cnt))
+    lse_v.copy_(torch.tensor([m, s1, s2, 0.0], dtype=torch.float64))
+    total2, lse2 = merge_packed(exchange_packed_async(words))
+    assert total2.tolist() == total.tolist() and lse2 == lse
     if rank == 0:
         out.put((total.tolist(), lse))
     dist.barrier()
