@@ -50,6 +50,10 @@ struct FitArgs {
   int w_off[FIT_MAX_LAYERS], b_off[FIT_MAX_LAYERS];   // float offsets in W
   int a_off[FIT_MAX_LAYERS + 1], a_stride[FIT_MAX_LAYERS + 1];
   int n_params, delta_off, delta_stride, smem_floats, gsum_off;
+  // small mode: transposed copies W^T[n][k] of the layers l >= 1 (row stride
+  // wt_ld[l], a multiple of 8) so that the back-propagation of delta reads
+  // its eight weights per step as two 16-byte loads
+  int wt_base, wt_off[FIT_MAX_LAYERS], wt_ld[FIT_MAX_LAYERS];
   int rows;      // resident chunk (64, 32 or 16: what fits shared memory)
   int big;       // weights / gradient too large for shared memory: they live
                  // in (L2-resident) global memory, activations stay on chip
@@ -85,6 +89,7 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   float* dl1 = dl0 + A.rows * A.delta_stride;
   // this CTA's reduced quarter of G
   float* Gq = BIG ? big_base + 2 * A.n_params : fs + A.gsum_off;
+  float* WT = fs + A.wt_base;          // small mode only
   __shared__ float red[FIT_THREADS / 32];
   __shared__ float s_loss;
   __shared__ float s_bsq;              // this CTA's share of sum (y - t)^2
@@ -117,6 +122,16 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
     G[e] = 0.f; mom_m[e] = 0.f; mom_v[e] = 0.f;
   }
   __syncthreads();
+  if (!BIG) {
+    for (int l = 1; l < A.n_lay; ++l) {
+      const int fi = A.sizes[l], fo = A.sizes[l + 1], ldt = A.wt_ld[l];
+      for (int e = tid; e < fo * ldt; e += FIT_THREADS) {
+        const int n = e / ldt, k = e - n * ldt;
+        WT[A.wt_off[l] + e] = k < fi ? W[A.w_off[l] + k * fo + n] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
 
   const long long M = A.m;
   const int n_batches = (int)((M + A.batch - 1) / A.batch);
@@ -301,7 +316,22 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
               for (int j = 0; j < 8; ++j) acc[j] = 0.f;
               const float* dp = dcur + mrow * A.delta_stride;
               const float* wk = Wl + k0 * fo;
-              if (k0 + 8 <= fi) {
+              if (!BIG) {
+                // W^T[n][k0 .. k0+7]: two 16-byte loads (rows are padded with
+                // zeros, so the last tile needs no predicates)
+                const float4* wt4 = reinterpret_cast<const float4*>(
+                    WT + A.wt_off[l] + k0);
+                const int ld4 = A.wt_ld[l] >> 2;
+#pragma unroll 4
+                for (int n = 0; n < fo; ++n) {
+                  const float dv = ok ? dp[n] : 0.f;
+                  const float4 wa = wt4[n * ld4], wb = wt4[n * ld4 + 1];
+                  acc[0] = fmaf(dv, wa.x, acc[0]); acc[1] = fmaf(dv, wa.y, acc[1]);
+                  acc[2] = fmaf(dv, wa.z, acc[2]); acc[3] = fmaf(dv, wa.w, acc[3]);
+                  acc[4] = fmaf(dv, wb.x, acc[4]); acc[5] = fmaf(dv, wb.y, acc[5]);
+                  acc[6] = fmaf(dv, wb.z, acc[6]); acc[7] = fmaf(dv, wb.w, acc[7]);
+                }
+              } else if (k0 + 8 <= fi) {
 #pragma unroll 4
                 for (int n = 0; n < fo; ++n) {
                   const float dv = ok ? dp[n] : 0.f;
@@ -375,7 +405,18 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
         const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
         mom_m[e] = mq;
         mom_v[e] = vq;
-        W[e] -= lr_t * mq / (sqrtf(vq) + A.eps);
+        const float w_new = W[e] - lr_t * mq / (sqrtf(vq) + A.eps);
+        W[e] = w_new;
+        if (!BIG && e >= A.w_off[1]) {
+          // keep the transposed copy in step (biases have none)
+          int l = 1;
+          while (l + 1 < A.n_lay && e >= A.w_off[l + 1]) ++l;
+          const int r = e - A.w_off[l], fo = A.sizes[l + 1];
+          if (r < A.sizes[l] * fo) {
+            const int k = r / fo, n = r - k * fo;
+            WT[A.wt_off[l] + n * A.wt_ld[l] + k] = w_new;
+          }
+        }
         G[e] = 0.f;
       }
       __syncthreads();
@@ -461,7 +502,14 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
     }
     A.delta_off = 2 * A.n_params + aoff;
     A.gsum_off = A.delta_off + 2 * A.rows * A.delta_stride;
-    A.smem_floats = A.gsum_off + A.p_quarter;
+    A.wt_base = (A.gsum_off + A.p_quarter + 3) / 4 * 4;
+    int wt = 0;
+    for (int l = 1; l < n_lay; ++l) {
+      A.wt_ld[l] = (A.sizes[l] + 7) / 8 * 8;
+      A.wt_off[l] = wt;
+      wt += A.sizes[l + 1] * A.wt_ld[l];
+    }
+    A.smem_floats = A.wt_base + wt;
     if ((size_t)A.smem_floats * 4 <= 220 * 1024) break;
   }
   if ((size_t)A.smem_floats * 4 > 220 * 1024) {
