@@ -54,7 +54,6 @@ struct FitArgs {
   // wt_ld[l], a multiple of 8) so that the back-propagation of delta reads
   // its eight weights per step as two 16-byte loads
   int wt_base, wt_off[FIT_MAX_LAYERS], wt_ld[FIT_MAX_LAYERS];
-  int mom_off;   // small mode: Adam moments of this CTA's parameter slice
   int rows;      // resident chunk (64, 32 or 16: what fits shared memory)
   int big;       // weights / gradient too large for shared memory: they live
                  // in (L2-resident) global memory, activations stay on chip
@@ -124,8 +123,6 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
   }
   __syncthreads();
   if (!BIG) {
-    for (int e = tid; e < 2 * A.p_quarter; e += FIT_THREADS)
-      fs[A.mom_off + e] = 0.f;
     for (int l = 1; l < A.n_lay; ++l) {
       const int fi = A.sizes[l], fo = A.sizes[l + 1], ldt = A.wt_ld[l];
       for (int e = tid; e < fo * ldt; e += FIT_THREADS) {
@@ -390,65 +387,39 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
           t += *cluster.map_shared_rank(&s_bsq, q);
         batch_sq = t;
       }
+      if (BIG) __threadfence();
+      cluster.sync();      // ... all-gather happens inside the Adam loop
       // ---- Adam step on the whole minibatch gradient --------------------------
       t_adam += 1;
       const float b1t = powf(A.beta1, (float)t_adam);
       const float b2t = powf(A.beta2, (float)t_adam);
       const float lr_t = A.lr * sqrtf(1.f - b2t) / (1.f - b1t);
-      if (!BIG) {
-        // Sharded: this CTA owns the moments of ITS slice of the parameters
-        // (shared memory), applies Adam to that slice only and pushes the new
-        // weights into every CTA's copy through distributed shared memory --
-        // 1/C of the arithmetic, no L2 round trips, stores instead of remote
-        // loads.  (Each parameter has one writer, so all copies agree.)
-        const int lo = crank * A.p_quarter;
-        const int hi = min(P, lo + A.p_quarter);
-        float* sm_m = fs + A.mom_off;
-        float* sm_v = sm_m + A.p_quarter;
-        for (int e = lo + tid; e < hi; e += FIT_THREADS) {
-          const float gq = Gq[e - lo];
-          const float mq = A.beta1 * sm_m[e - lo] + (1.f - A.beta1) * gq;
-          const float vq = A.beta2 * sm_v[e - lo] + (1.f - A.beta2) * gq * gq;
-          sm_m[e - lo] = mq;
-          sm_v[e - lo] = vq;
-          const float w_new = W[e] - lr_t * mq / (sqrtf(vq) + A.eps);
-          int t_idx = -1;              // index in the transposed copy, if any
-          if (e >= A.w_off[1]) {
-            int l = 1;
-            while (l + 1 < A.n_lay && e >= A.w_off[l + 1]) ++l;
-            const int r = e - A.w_off[l], fo = A.sizes[l + 1];
-            if (r < A.sizes[l] * fo) {
-              const int k = r / fo, n = r - k * fo;
-              t_idx = A.wt_off[l] + n * A.wt_ld[l] + k;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < FIT_CLUSTER; ++q) {
-            cluster.map_shared_rank(W, q)[e] = w_new;
-            if (t_idx >= 0) cluster.map_shared_rank(WT, q)[t_idx] = w_new;
+      for (int e = tid; e < P; e += FIT_THREADS) {
+        const int owner = e / A.p_quarter;
+        const float gq =
+            BIG ? __ldcg(big_store +
+                           ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
+                               A.n_params + (e - owner * A.p_quarter))
+                  : cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
+        const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
+        const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
+        mom_m[e] = mq;
+        mom_v[e] = vq;
+        const float w_new = W[e] - lr_t * mq / (sqrtf(vq) + A.eps);
+        W[e] = w_new;
+        if (!BIG && e >= A.w_off[1]) {
+          // keep the transposed copy in step (biases have none)
+          int l = 1;
+          while (l + 1 < A.n_lay && e >= A.w_off[l + 1]) ++l;
+          const int r = e - A.w_off[l], fo = A.sizes[l + 1];
+          if (r < A.sizes[l] * fo) {
+            const int k = r / fo, n = r - k * fo;
+            WT[A.wt_off[l] + n * A.wt_ld[l] + k] = w_new;
           }
         }
-        cluster.sync();      // every copy of W is complete; peers are done
-                             // reading this CTA's G
-        for (int e = tid; e < P; e += FIT_THREADS) G[e] = 0.f;
-        __syncthreads();
-      } else {
-        __threadfence();
-        cluster.sync();      // ... all-gather happens inside the Adam loop
-        for (int e = tid; e < P; e += FIT_THREADS) {
-          const int owner = e / A.p_quarter;
-          const float gq = __ldcg(
-              big_store + ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
-                              A.n_params + (e - owner * A.p_quarter));
-          const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
-          const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
-          mom_m[e] = mq;
-          mom_v[e] = vq;
-          W[e] -= lr_t * mq / (sqrtf(vq) + A.eps);
-          G[e] = 0.f;
-        }
-        __syncthreads();
+        G[e] = 0.f;
       }
+      __syncthreads();
       epoch_loss += 0.5f * batch_sq;   // = batch_loss * bn
     }
     last_loss = epoch_loss / (float)M;
@@ -538,8 +509,7 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
       A.wt_off[l] = wt;
       wt += A.sizes[l + 1] * A.wt_ld[l];
     }
-    A.mom_off = A.wt_base + wt;
-    A.smem_floats = A.mom_off + 2 * A.p_quarter;
+    A.smem_floats = A.wt_base + wt;
     if ((size_t)A.smem_floats * 4 <= 220 * 1024) break;
   }
   if ((size_t)A.smem_floats * 4 > 220 * 1024) {
