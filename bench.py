@@ -256,6 +256,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's version banner (printed when
+        # the box sets NCCL_DEBUG) goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     spec = load_spec()
