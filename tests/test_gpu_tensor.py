@@ -212,3 +212,47 @@ def test_front_kernels_agree(golden, monkeypatch):
     same = (a['code'] == 4) & (b['code'] == 4)
     assert np.max(np.abs(a['log_l'][same] - b['log_l'][same])) < 1e-9
     assert np.abs(a['counters'] - b['counters']).max() <= 3
+
+
+@pytest.mark.parametrize('d', [3, 8, 17, 33, 40, 50, 64])
+def test_dmma_front_kernel_all_row_widths(d, monkeypatch):
+    # every instantiation of k_front_mma<D8> (D8 = 8 ... 64): a hand-built
+    # one-ellipsoid bound with a small emulator; decisions against the oracle
+    # on the kernel's own proposals, and agreement with the DFMA kernel
+    from nautilus_b200 import bounds, likelihoods
+    from nautilus_b200.neural import NeuralNetworkEmulator
+    rng = np.random.default_rng(d)
+    z = rng.normal(size=(600, d))
+    z *= (rng.random((600, 1))**(1.0 / d) /
+          np.linalg.norm(z, axis=1)[:, None])
+    mix = np.eye(d) * 0.3 + 0.03 * rng.normal(size=(d, d))
+    live = 0.5 + z @ mix.T
+    ell = bounds.Ellipsoid.compute(live, enlarge_per_dim=1.05,
+                                   rng=np.random.default_rng(0))
+    whitened = ell.transform(live)
+    score = 1.0 - np.linalg.norm(whitened, axis=1)
+    emu = NeuralNetworkEmulator.train(
+        whitened, score, n_networks=2,
+        neural_network_kwargs=dict(hidden_layer_sizes=(16, 8), max_iter=15),
+        seed=1)
+    spec = dict(kind='nautilus', n_dim=d, unit=True,
+                log_v_all=np.array([ell.log_v]),
+                mixtures=[dict(dim_cube=np.zeros(d, dtype=bool),
+                               ell=ell.ell_spec())],
+                neural=[dict(ell=ell.ell_spec(), emulator=emu.emu_spec(),
+                             score_predict_min=float(np.median(
+                                 emu.predict(whitened))))])
+    like = likelihoods.Gaussian(d, sigma=0.2)
+    cnt = _fused_vs_staged(spec, 6000, like, seed=d)
+    assert cnt[ops.CNT_IN_SHELL] > 0 and cnt[ops.CNT_NN_REJECT] > 0
+    outs = []
+    for which in ('mma', 'dfma'):
+        monkeypatch.setenv('NB200_FRONT', which)
+        stack = ops.DeviceStack([spec])
+        out = stack.cycle(0, 4096, seed=3, like_id=like.like_id,
+                          like_params=like.device_params('cuda'),
+                          log_l_min=-1.0, mode=ops.MLP_TF32)
+        outs.append({k: v.cpu().numpy() for k, v in out.items()})
+    a, b = outs
+    assert np.max(np.abs(a['points'] - b['points'])) < 1e-12
+    assert np.mean(a['code'] != b['code']) < 2e-3
