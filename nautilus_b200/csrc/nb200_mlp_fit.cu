@@ -394,30 +394,52 @@ k_mlp_fit(const FitArgs A, const float* __restrict__ x,
       const float b1t = powf(A.beta1, (float)t_adam);
       const float b2t = powf(A.beta2, (float)t_adam);
       const float lr_t = A.lr * sqrtf(1.f - b2t) / (1.f - b1t);
-      for (int e = tid; e < P; e += FIT_THREADS) {
-        const int owner = e / A.p_quarter;
-        const float gq =
-            BIG ? __ldcg(big_store +
-                           ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
-                               A.n_params + (e - owner * A.p_quarter))
-                  : cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
-        const float mq = A.beta1 * mom_m[e] + (1.f - A.beta1) * gq;
-        const float vq = A.beta2 * mom_v[e] + (1.f - A.beta2) * gq * gq;
-        mom_m[e] = mq;
-        mom_v[e] = vq;
-        const float w_new = W[e] - lr_t * mq / (sqrtf(vq) + A.eps);
-        W[e] = w_new;
-        if (!BIG && e >= A.w_off[1]) {
-          // keep the transposed copy in step (biases have none)
-          int l = 1;
-          while (l + 1 < A.n_lay && e >= A.w_off[l + 1]) ++l;
-          const int r = e - A.w_off[l], fo = A.sizes[l + 1];
-          if (r < A.sizes[l] * fo) {
-            const int k = r / fo, n = r - k * fo;
-            WT[A.wt_off[l] + n * A.wt_ld[l] + k] = w_new;
+      // six parameters per thread and pass: all their loads (the reduced
+      // gradient from its owner's shared memory, the two moments from L2) are
+      // issued before the first dependent instruction -- the loop used to pay
+      // one remote round trip per parameter
+      constexpr int AB = 6;
+      for (int base = tid; base < P; base += AB * FIT_THREADS) {
+        float gqv[AB], mv[AB], vv[AB], wv[AB];
+#pragma unroll
+        for (int u = 0; u < AB; ++u) {
+          const int e = base + u * FIT_THREADS;
+          if (e < P) {
+            const int owner = e / A.p_quarter;
+            gqv[u] =
+                BIG ? __ldcg(big_store +
+                             ((size_t)(blockIdx.x - crank + owner) * 3 + 2) *
+                                 A.n_params + (e - owner * A.p_quarter))
+                    : cluster.map_shared_rank(Gq, owner)[e - owner * A.p_quarter];
+            mv[u] = mom_m[e];
+            vv[u] = mom_v[e];
+            wv[u] = W[e];
           }
         }
-        G[e] = 0.f;
+#pragma unroll
+        for (int u = 0; u < AB; ++u) {
+          const int e = base + u * FIT_THREADS;
+          if (e < P) {
+            const float gq = gqv[u];
+            const float mq = A.beta1 * mv[u] + (1.f - A.beta1) * gq;
+            const float vq = A.beta2 * vv[u] + (1.f - A.beta2) * gq * gq;
+            mom_m[e] = mq;
+            mom_v[e] = vq;
+            const float w_new = wv[u] - lr_t * mq / (sqrtf(vq) + A.eps);
+            W[e] = w_new;
+            if (!BIG && e >= A.w_off[1]) {
+              // keep the transposed copy in step (biases have none)
+              int l = 1;
+              while (l + 1 < A.n_lay && e >= A.w_off[l + 1]) ++l;
+              const int r = e - A.w_off[l], fo = A.sizes[l + 1];
+              if (r < A.sizes[l] * fo) {
+                const int k = r / fo, n = r - k * fo;
+                WT[A.wt_off[l] + n * A.wt_ld[l] + k] = w_new;
+              }
+            }
+            G[e] = 0.f;
+          }
+        }
       }
       __syncthreads();
       epoch_loss += 0.5f * batch_sq;   // = batch_loss * bn
