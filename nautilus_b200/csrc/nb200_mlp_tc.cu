@@ -347,13 +347,10 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
         tmem_ld32(d_addr + (uint32_t)c, v);
         tmem_wait_ld();
         // ReLU, then round-half-up to tf32: the MMA reads only the top 19
-        // bits, so adding half an ulp of tf32 is the whole rounding.  On the
-        // bit patterns this is max(x, 0) + 0x1000 == max(x + 0x1000, 0x1000)
-        // in signed integer arithmetic (negative floats are negative
-        // integers): ONE instruction (VIADDMNMX) per value instead of two.
+        // bits, so adding half an ulp of tf32 is the whole rounding
 #pragma unroll
         for (int q = 0; q < 32; ++q)
-          v[q] = (uint32_t)__viaddmax_s32((int)v[q], 0x1000, 0x1000);
+          v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f)) + 0x1000u;
         tmem_st32(d_addr + (uint32_t)c, v);
       }
       tmem_wait_st();
