@@ -221,7 +221,7 @@ k_mvee(const double* __restrict__ qT, int64_t n, int d, int max_updates,
 // ---------------------------------------------------------------------------
 constexpr int MVC_THREADS = 512;
 constexpr int MVC_WARPS = MVC_THREADS / 32;
-constexpr int MVC_MAX_CLUSTER = 8;
+constexpr int MVC_MAX_CLUSTER = 16;   // 16 needs the non-portable opt-in
 
 struct MvcShared {
   double red_v[MVC_WARPS];
@@ -449,7 +449,8 @@ int nb200_mvee_weights(const double* qT_d, int64_t n, int d, int max_updates,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smc));
     NB_CUDA(cudaFuncSetAttribute(
-        k_mvee_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+        k_mvee_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed,
+        C > 8 ? 1 : 0));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(C, 1, 1);
@@ -461,13 +462,23 @@ int nb200_mvee_weights(const double* qT_d, int64_t n, int d, int max_updates,
     attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
+    if (C > 8) {
+      // a 16-CTA cluster is not guaranteed to be schedulable: ask first
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, k_mvee_cluster,
+                                         &cfg) != cudaSuccess ||
+          max_clusters < 1) {
+        cudaGetLastError();
+        break;
+      }
+    }
     ProfScope prof(ST_FIT, (cudaStream_t)stream);
     NB_CUDA(cudaLaunchKernelEx(&cfg, k_mvee_cluster, qT_d, (int)n, d, ld,
                                max_updates, tol, u_d, iters_d));
     NB_LAUNCH_OK();
     return 0;
   }
-  // too many points for eight CTAs: the single-CTA kernel that streams the
+  // too many points for a cluster: the single-CTA kernel that streams the
   // points from L2
   const size_t smem = sizeof(double) * ((size_t)D * (D | 1) + 2 * (size_t)D);
   NB_CUDA(cudaFuncSetAttribute(k_mvee,
