@@ -53,3 +53,20 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_lib.NautilusB200Error):
         _lib.lib()
+
+
+def test_session_fails_loudly_without_gpu(built):
+    # no CPU fallback anywhere: on a box without a CUDA device the host-buffer
+    # session refuses to exist instead of computing something on the host
+    import numpy as np
+    torch = pytest.importorskip('torch')
+    if torch.cuda.is_available():
+        pytest.skip('needs a box without a GPU')
+    from nautilus_b200 import ops
+    spec = dict(kind='cube', n_dim=3)
+    with pytest.raises(_lib.NautilusB200Error, match='CUDA error'):
+        ops.HostSession([spec], n_max=1024)
+    # argument checks come before any CUDA call
+    with pytest.raises(_lib.NautilusB200Error, match='n_max'):
+        ops.HostSession([spec], n_max=0)
+    assert np.isfinite(_lib.lib().nb200_workspace_bytes(1024, 3))
