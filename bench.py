@@ -355,48 +355,72 @@ def run_gpu(args):
     # ---- e2e leg: the C-ABI host-buffer session (include/nautilus_b200.h,
     # nb200_session_*): NumPy in, NumPy out.  Every step uploads the
     # serialised bound + likelihood parameters from pinned host memory and
-    # brings the in-shell points, their log_l, the counters and the
-    # log-sum-exp triple back to host memory; two batches are in flight so the
-    # device->host copy of one runs under the kernels of the next.
-    sess = ops.HostSession([spec], n_max=n, cap=max(n // 4, 1024), n_slots=2,
-                           like_params_max=like_params.numel())
+    # brings back what Sampler.add_samples keeps of the batch
+    # (sampler.py:1135-1141) -- for every in-shell proposal its GLOBAL index
+    # (u64, from which nb200_session_materialize regenerates the row bit for
+    # bit) and its log_l, plus the counters and the log-sum-exp triple; the
+    # rows themselves stay on the device.  Two batches are in flight so the
+    # device->host copy of one runs under the kernels of the next.  The
+    # round-1 form (rows cross PCIe, 8d+8 bytes per in-shell proposal) is
+    # timed as well, on fewer steps, and reported as e2e.rows_mode.
     par_h = like_params.cpu().numpy()
-    bytes_io = {'h2d': 0, 'd2h': 0}
-    host = {'points': 0, 'sum_ll': 0.0}
 
-    def e2e_submit(slot):
-        s = state['step']
-        state['step'] += 1
-        sess.submit(slot, 0, n, seed=seed, offset=(s * world + rank) * n,
-                    like_id=like.like_id, like_params=par_h,
-                    log_l_min=log_l_min, mode=mode, upload_stack=True)
+    def e2e_leg(returns, k_steps):
+        sess = ops.HostSession([spec], n_max=n, cap=max(n // 4, 1024),
+                               n_slots=2, returns=returns,
+                               like_params_max=like_params.numel())
+        io = {'h2d': 0, 'd2h': 0, 'points': 0, 'sum_ll': 0.0, 'last': None}
 
-    def e2e_wait(slot):
-        res = sess.wait(slot)
-        k = len(res['log_l'])
-        host['points'] += k
-        host['sum_ll'] += float(res['log_l'][-1]) if k else 0.0
-        bytes_io['h2d'] = sess.stack_bytes + par_h.nbytes
-        bytes_io['d2h'] = k * (D + 1) * 8 + (ops.N_LSE + ops.N_CNT + 1) * 8
+        def submit(slot):
+            s = state['step']
+            state['step'] += 1
+            sess.submit(slot, 0, n, seed=seed, offset=(s * world + rank) * n,
+                        like_id=like.like_id, like_params=par_h,
+                        log_l_min=log_l_min, mode=mode, upload_stack=True)
 
-    def e2e_run(k_steps):
-        e2e_submit(0)
-        for i in range(k_steps):
-            if i + 1 < k_steps:
-                e2e_submit((i + 1) & 1)
-            e2e_wait(i & 1)
+        def wait(slot):
+            res = sess.wait(slot)
+            k = len(res['log_l'])
+            io['points'] += k
+            io['sum_ll'] += float(res['log_l'][-1]) if k else 0.0
+            io['h2d'] = sess.stack_bytes + par_h.nbytes
+            small = (ops.N_LSE + ops.N_CNT + 1) * 8
+            if returns == 'index':
+                # submit enqueues the copy before the count is known: a
+                # quarter more than the previous batch kept (+1024) is sent
+                io['d2h'] = (k + k // 4 + 1024) * 16 + small
+                io['last'] = np.array(res['index'][:64])
+            else:
+                io['d2h'] = k * (D + 1) * 8 + small
 
-    e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
-    barrier()
-    sess.close()
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        def run(steps):
+            submit(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    submit((i + 1) & 1)
+                wait(i & 1)
+
+        run(3)
+        barrier()
+        t0 = time.perf_counter()
+        run(k_steps)
+        ms_leg = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        if returns == 'index' and io['last'] is not None:
+            # rows on demand (outside the timed region): regenerate a few
+            rows = sess.materialize(0, io['last'], seed=seed, mode=mode)
+            assert rows.shape == (len(io['last']), D) and np.all(
+                (rows >= 0) & (rows < 1))
+        sess.close()
+        if world > 1:
+            t = torch.tensor([ms_leg], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_leg = float(t.item())
+        return ms_leg, io
+
+    e2e_ms, bytes_io = e2e_leg('index', args.steps)
+    rows_steps = max(3, min(args.steps, 100))
+    rows_ms, rows_io = e2e_leg('rows', rows_steps)
 
     if rank != 0:
         if world > 1:
@@ -500,8 +524,20 @@ def run_gpu(args):
                 'h2d_bytes_per_step': bytes_io['h2d'],
                 'd2h_bytes_per_step': bytes_io['d2h'],
                 'ms_per_step': e2e_ms / args.steps,
-                'api': 'nb200_session_submit/_wait (C ABI, host buffers), 2 '
-                       'batches in flight, host wall clock'},
+                'frac_of_device': e2e_value / value,
+                'api': 'nb200_session_submit/_wait_index (C ABI, host '
+                       'buffers): per in-shell proposal the host receives '
+                       '(global index u64, log_l f64); rows stay on the '
+                       'device, nb200_session_materialize regenerates them '
+                       'bit-identically on demand; 2 batches in flight, host '
+                       'wall clock',
+                'rows_mode': {
+                    'value': world * n * rows_steps / (rows_ms * 1e-3),
+                    'ms_per_step': rows_ms / rows_steps,
+                    'steps': rows_steps,
+                    'd2h_bytes_per_step': rows_io['d2h'],
+                    'api': 'nb200_session_submit/_wait: in-shell ROWS cross '
+                           'PCIe (round-1 form)'}},
         'gpu_launches': launches,
         'clocks': clocks.summary() if clocks else None,
         'result': result,

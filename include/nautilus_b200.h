@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NB200_VERSION 100
+#define NB200_VERSION 200
 #define NB200_D_MAX 128
 #define NB200_W_MAX 256
 
@@ -206,6 +206,29 @@ int nb200_compact(const double* points_d, const double* log_l_d,
                   double* out_points_d, double* out_log_l_d, int64_t* n_out_d,
                   void* workspace_d, size_t workspace_bytes, void* stream);
 
+/* Index form of the compaction: for the rows with code==4 the GLOBAL
+ * proposal index offset + i (u64: the Philox counter of the proposal, which
+ * nb200_materialize turns back into the row) and log_l (may be NULL).  What
+ * Sampler.add_samples keeps of a batch (sampler.py:1135-1141) is then 16
+ * bytes per point instead of 8 d + 8; the rows stay on the device. */
+int nb200_compact_index(const double* log_l_d, const uint8_t* code_d,
+                        int64_t n, uint64_t offset, uint64_t* out_index_d,
+                        double* out_log_l_d, int64_t* n_out_d,
+                        void* workspace_d, size_t workspace_bytes,
+                        void* stream);
+
+/* Rows of the proposals with global indices index_d[0..k) of stack record
+ * `bound` (a proposal is a pure function of (bound, seed, stream_id, index)):
+ * re-runs the proposal kernel the cycle used for this bound and `mlp_mode`
+ * on exactly these indices; points_out_d f64[k,d] is BIT-IDENTICAL to the
+ * rows nb200_cycle wrote for them (tests/test_gpu_session.py).  Replaces the
+ * `points[in_shell]` copies of sampler.py:801,1135 by an on-demand gather. */
+int nb200_materialize(const int32_t* meta_h, const int32_t* meta_d,
+                      const double* data_d, int bound, uint64_t seed,
+                      uint32_t stream_id, int mlp_mode,
+                      const uint64_t* index_d, int64_t k, double* points_out_d,
+                      void* stream);
+
 /* ---- the full cycle (sampler.py:1093-1144 over one raw batch) ---------- */
 
 /* n raw proposals from stack record `bound`, filtered by its neural bounds,
@@ -289,6 +312,31 @@ int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
 int nb200_session_wait(nb200_session* s, int slot, const double** points_h,
                        const double** log_l_h, int64_t* n_out, double* lse_h,
                        int64_t* counters_h);
+
+/* Index mode: what crosses PCIe per in-shell proposal is (global index u64,
+ * log_l f64) = 16 bytes instead of the 8 d + 8 of a row; the rows stay on
+ * the device and are regenerated on demand (a row is a pure function of
+ * (bound, seed, stream_id, index)).
+ *   set_returns(NB200_RETURN_INDEX)  batches submitted from now on compact
+ *       indices; their device->host copy is enqueued by submit itself (sized
+ *       from the previous batch, topped up by wait if it fell short), so wait
+ *       costs ONE host synchronisation;
+ *   wait_index(slot, ...)  as wait, with index_h u64[*n_out] instead of rows;
+ *   materialize(...)  rows f64[k,d] (host) of any k indices of `bound`, bit-
+ *       identical to the rows the cycle produced -- posterior(), add_bound and
+ *       the transfer step (sampler.py:541-647, 1007-1089) ask for rows, the
+ *       batch loop never does. */
+#define NB200_RETURN_ROWS 0
+#define NB200_RETURN_INDEX 1
+int nb200_session_set_returns(nb200_session* s, int what);
+int nb200_session_wait_index(nb200_session* s, int slot,
+                             const uint64_t** index_h,
+                             const double** log_l_h, int64_t* n_out,
+                             double* lse_h, int64_t* counters_h);
+int nb200_session_materialize(nb200_session* s, int bound, uint64_t seed,
+                              uint32_t stream_id, int mlp_mode,
+                              const uint64_t* index_h, int64_t k,
+                              double* points_out_h);
 
 #ifdef __cplusplus
 }

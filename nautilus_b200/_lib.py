@@ -92,6 +92,10 @@ PROTOTYPES = {
                              _vp]),
     'nb200_compact': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp,
                              _sz, _vp]),
+    'nb200_compact_index': (_int, [_vp, _vp, _i64, _u64, _vp, _vp, _vp, _vp,
+                                   _sz, _vp]),
+    'nb200_materialize': (_int, [_i32p, _vp, _vp, _int, _u64, _u32, _int,
+                                 _vp, _i64, _vp, _vp]),
     'nb200_cycle': (_int, [_i32p, _vp, _vp, _int, _int, _int, _i64, _u64,
                            _u64, _u32, _int, _vp, _int, _dbl, _int, _vp, _vp,
                            _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -109,6 +113,10 @@ PROTOTYPES = {
                                     _u64, _u64, _u32, _int, _vp, _int, _dbl,
                                     _int]),
     'nb200_session_wait': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    'nb200_session_set_returns': (_int, [_vp, _int]),
+    'nb200_session_wait_index': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    'nb200_session_materialize': (_int, [_vp, _int, _u64, _u32, _int, _vp,
+                                         _i64, _vp]),
 }
 
 

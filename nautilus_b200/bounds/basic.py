@@ -14,7 +14,7 @@ from scipy.special import gammaln
 
 from .. import ops
 from . import _construct
-from ._device import PhiloxStream, default_device, to_device
+from .._device import PhiloxStream, default_device, to_device
 
 
 class _DeviceBound:

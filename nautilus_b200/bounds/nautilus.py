@@ -11,7 +11,7 @@ import torch
 
 from .. import ops
 from ..neural import NeuralNetworkEmulator
-from ._device import PhiloxStream, default_device, to_device
+from .._device import PhiloxStream, default_device, to_device
 from .basic import Ellipsoid, UnitCubeEllipsoidMixture, _DeviceBound
 from .neural import NeuralBound
 from .union import Union
@@ -78,9 +78,23 @@ class NautilusBound(_DeviceBound):
             if not bound.outer_bound.trim():
                 break
 
-        for nb in bound.neural_bounds:
-            nb.finish()
+        with torch.cuda.stream(side):
+            for nb in bound.neural_bounds:
+                nb.finish()
         main.wait_stream(side)
+        # device copies made under the side stream (ellipsoid parameters,
+        # serialised stacks) belong to that stream's allocator pool: drop them
+        # so that whatever the bound uses from now on is created on the
+        # caller's stream (no cross-stream reuse of freed blocks)
+        for nb in bound.neural_bounds:
+            nb._invalidate()
+            nb.outer_bound._invalidate()
+            nb.outer_bound._dev_params = None
+            if nb.emulator is not None:
+                nb.emulator._stack = None
+        for ell in clusters.bounds:
+            ell._invalidate()
+            ell._dev_params = None
 
         bound.stream = PhiloxStream(rng)
         bound._clear()

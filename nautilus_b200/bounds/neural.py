@@ -8,7 +8,7 @@ from scipy.stats import rankdata
 
 from .. import ops
 from ..neural import NeuralNetworkEmulator
-from ._device import default_device, to_device
+from .._device import default_device, to_device
 from .basic import Ellipsoid, _DeviceBound
 
 

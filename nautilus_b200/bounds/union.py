@@ -13,7 +13,7 @@ from scipy.special import logsumexp
 
 from .. import ops
 from . import _construct
-from ._device import PhiloxStream, default_device, to_device
+from .._device import PhiloxStream, default_device, to_device
 from .basic import Ellipsoid, UnitCube, UnitCubeEllipsoidMixture, _DeviceBound
 
 ellipsoids_overlap = _construct.ellipsoids_overlap

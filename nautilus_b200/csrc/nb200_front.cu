@@ -43,7 +43,16 @@ struct FrontArgs {
   int like_id;
   const double* like_p;
   double* log_l;
+  // gather mode (nb200_materialize): proposal i is the GLOBAL proposal index
+  // gather[i]; only the row is written (bit-identical to the cycle's)
+  const unsigned long long* gather;
 };
+
+__device__ __forceinline__ unsigned long long front_index(const FrontArgs& A,
+                                                          long long i) {
+  if (A.gather) return __ldg(A.gather + (i < A.n ? i : A.n - 1));
+  return A.offset + (unsigned long long)i;
+}
 
 // kept out of line so that the four likelihood bodies do not take part in
 // the register allocation of the matrix-vector loops
@@ -157,10 +166,9 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
     {
       double n2[FRONT_PTS];
       double uq[FRONT_PTS];
-      const Philox rng0(A.offset + (unsigned long long)(base + threadIdx.x),
-                        A.stream_id, A.seed);
-      const Philox rng1(A.offset + (unsigned long long)(base + FRONT_THREADS +
-                                                        threadIdx.x),
+      const Philox rng0(front_index(A, base + threadIdx.x), A.stream_id,
+                        A.seed);
+      const Philox rng1(front_index(A, base + FRONT_THREADS + threadIdx.x),
                         A.stream_id, A.seed);
 #pragma unroll
       for (int p = 0; p < FRONT_PTS; ++p) {
@@ -250,7 +258,7 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
     for (int p = 0; p < FRONT_PTS; ++p) {
       cd[p] = NB200_CODE_IN_SHELL;
       if (A.unit && !in_cube[p]) cd[p] = NB200_CODE_CUBE_REJECT;
-      alive[p] = valid[p] && cd[p] == NB200_CODE_IN_SHELL;
+      alive[p] = valid[p] && cd[p] == NB200_CODE_IN_SHELL && !A.gather;
     }
     // whitening w.r.t. the neural bound's ellipsoid: r2 and the standardised,
     // tf32-rounded emulator input row (with the constant-one bias column at
@@ -336,7 +344,7 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
     }
 #pragma unroll
     for (int p = 0; p < FRONT_PTS; ++p) {
-      if (!valid[p]) continue;
+      if (!valid[p] || A.gather) continue;
       bool in_ell = false;
       if (alive[p]) {
         in_ell = r2_nb[p] < 1.0;
@@ -363,7 +371,8 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
                      const double* data_d, int bound, int64_t n, uint64_t seed,
                      uint64_t offset, uint32_t stream_id, double* points,
                      uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
-                     const double* like_p, double* log_l, cudaStream_t st);
+                     const double* like_p, double* log_l,
+                     const unsigned long long* gather, cudaStream_t st);
 
 // NB200_FRONT=dfma forces the DFMA kernel (A/B measurements, tests)
 static bool front_mma_wanted() {
@@ -413,17 +422,19 @@ int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  const double* data_d, int bound, int64_t n, uint64_t seed,
                  uint64_t offset, uint32_t stream_id, double* points,
                  uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
-                 const double* like_p, double* log_l, cudaStream_t st) {
+                 const double* like_p, double* log_l,
+                 const unsigned long long* gather, cudaStream_t st) {
   if (front_mma_wanted() &&
       front_mma_applicable(meta_h, bound, nullptr, nullptr))
     return launch_front_mma(meta_h, meta_d, data_d, bound, n, seed, offset,
                             stream_id, points, code, maskj, xs32, like_id,
-                            like_p, log_l, st);
+                            like_p, log_l, gather, st);
   FrontArgs A;
   size_t smem = 0;
   NB_CHECK(front2_applicable(meta_h, bound, &smem, &A), "front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
+  A.gather = gather;
   NB_CUDA(cudaFuncSetAttribute(k_front,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));

@@ -43,7 +43,19 @@ struct FrontMmaArgs {
   int like_id;
   const double* like_p;
   double* log_l;
+  // gather mode (nb200_materialize): proposal i of the launch is the GLOBAL
+  // proposal index gather[i] instead of offset + i, and only the row is
+  // written -- same instructions in the same order as the cycle's launch, so
+  // the regenerated row is bit-identical to the one the cycle produced
+  const unsigned long long* gather;
 };
+
+// global proposal index (the Philox counter) of local proposal i
+__device__ __forceinline__ unsigned long long fm_index(const FrontMmaArgs& A,
+                                                       long long i) {
+  if (A.gather) return __ldg(A.gather + (i < A.n ? i : A.n - 1));
+  return A.offset + (unsigned long long)i;
+}
 
 __device__ __noinline__ double front_mma_loglike(int like_id, const double* p,
                                                  const double* x, int d) {
@@ -146,16 +158,14 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     // ---- generator ---------------------------------------------------------
     // this lane's own proposal: 8q + p
     const long long gi_own = base + 8 * q + p;
-    const Philox rng_own(A.offset + (unsigned long long)gi_own, A.stream_id,
-                         A.seed);
+    const Philox rng_own(fm_index(A, gi_own), A.stream_id, A.seed);
     const uint4 w0 = rng_own.block(0);
     const double r_own = u01_32(w0.y);     // acceptance uniform (K == 1: the
     const double u_own = u01_53(w0.z, w0.w);   // ellipsoid choice is moot)
     double n2g[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const Philox rng(A.offset + (unsigned long long)(base + 8 * g + p),
-                       A.stream_id, A.seed);
+      const Philox rng(fm_index(A, base + 8 * g + p), A.stream_id, A.seed);
       double acc = 0.0;
       double* zr = rows + (8 * g + p) * S;
       // nK blocks cover the padded row; compile-time trip count, so that the
@@ -239,6 +249,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
       cube_bits |= ok << g;
     }
     __syncwarp();
+    if (A.gather) continue;      // materialize: the row is all that is wanted
 
     // ---- whitening(s): squared radii, emulator input rows -------------------
     double r2m[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the mixture's ellipsoid
@@ -363,13 +374,15 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
                      const double* data_d, int bound, int64_t n, uint64_t seed,
                      uint64_t offset, uint32_t stream_id, double* points,
                      uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
-                     const double* like_p, double* log_l, cudaStream_t st) {
+                     const double* like_p, double* log_l,
+                     const unsigned long long* gather, cudaStream_t st) {
   FrontMmaArgs A;
   size_t smem = 0;
   NB_CHECK(front_mma_applicable(meta_h, bound, &smem, &A),
            "DMMA front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
+  A.gather = gather;
   void (*kern)(const FrontMmaArgs, const int32_t*, const double*, double*,
                uint8_t*, uint8_t*, float*) = nullptr;
   switch (A.d8) {

@@ -192,7 +192,10 @@ __global__ void k_union_propose(
     const double* __restrict__ z_in, const double* __restrict__ cube_u_in,
     const double* __restrict__ u_in, const double* __restrict__ r_in,
     double* __restrict__ points, uint8_t* __restrict__ code,
-    int32_t* __restrict__ n_bound_out) {
+    int32_t* __restrict__ n_bound_out,
+    const unsigned long long* __restrict__ gather) {
+  // gather != nullptr (nb200_materialize): proposal i is the GLOBAL proposal
+  // index gather[i]; only the row is produced (same arithmetic as the cycle's)
   extern __shared__ double sm[];
   const Rec rec{meta + rec_off};
   const int d = rec.d();
@@ -206,7 +209,8 @@ __global__ void k_union_propose(
     const int64_t i = base + threadIdx.x;
     double* x = rowA + threadIdx.x * stride;
     double* z = rowB + threadIdx.x * stride;
-    const Philox rng(offset + (uint64_t)i, stream_id, seed);
+    const Philox rng(gather ? (uint64_t)gather[i] : offset + (uint64_t)i,
+                     stream_id, seed);
     uint8_t cd = NB200_CODE_IN_SHELL;
     int nbnd = 0;
 
@@ -279,7 +283,9 @@ __global__ void k_union_propose(
       }
       // unit-cube filter (union.py:313-314), overlap count (:316-317),
       // accept iff r > 1 - 1/n_bound (:318-319; n_bound == 0 -> -inf -> accept)
-      if (rec.unit() && !cube_ok(x, nullptr, d)) {
+      if (gather) {
+        // row only
+      } else if (rec.unit() && !cube_ok(x, nullptr, d)) {
         cd = NB200_CODE_CUBE_REJECT;
       } else {
         nbnd = union_count(rec, data, x, z);
@@ -287,7 +293,7 @@ __global__ void k_union_propose(
         if (!(r > p)) cd = NB200_CODE_OVERLAP_REJECT;
       }
     }
-    code[i] = cd;
+    if (code) code[i] = cd;
     if (n_bound_out) n_bound_out[i] = nbnd;
   }
   __syncthreads();
@@ -648,6 +654,60 @@ k_compact_scatter(const double* __restrict__ points,
   }
 }
 
+// Index form of the compaction: for every in-shell proposal its GLOBAL proposal
+// index (offset + i, the Philox counter that regenerates the row, see
+// nb200_materialize) and its log_l -- 16 bytes per kept proposal instead of
+// the 8 d + 8 of a row.  Every block derives its own exclusive prefix from the
+// block counts (<= n / 1024 values, L2-resident), so there is no scan launch;
+// the last block also writes the total.
+__global__ void __launch_bounds__(CMP_THREADS)
+k_compact_index(const double* __restrict__ log_l,
+                const uint8_t* __restrict__ code, int64_t n,
+                unsigned long long offset,
+                const long long* __restrict__ block_count,
+                unsigned long long* __restrict__ out_index,
+                double* __restrict__ out_log_l, long long* __restrict__ total) {
+  __shared__ int warp_cnt[CMP_THREADS / 32];
+  __shared__ long long warp_sum_sm[CMP_THREADS / 32];
+  __shared__ long long running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long pre = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += CMP_THREADS)
+    pre += block_count[b];
+  pre = warp_sum(pre);
+  if (lane == 0) warp_sum_sm[warp] = pre;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < CMP_THREADS / 32; ++w) t += warp_sum_sm[w];
+    running = t;
+    if (blockIdx.x == gridDim.x - 1) *total = t + block_count[blockIdx.x];
+  }
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * CMP_ITEMS;
+  for (int p = 0; p < CMP_ITEMS / CMP_THREADS; ++p) {
+    const int64_t i = lo + p * CMP_THREADS + threadIdx.x;
+    const bool keep = i < n && code[i] == NB200_CODE_IN_SHELL;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << lane) - 1u));
+    int all = 0;
+    for (int w = 0; w < CMP_THREADS / 32; ++w) {
+      if (w < warp) before += warp_cnt[w];
+      all += warp_cnt[w];
+    }
+    if (keep) {
+      const long long dst = running + before;
+      out_index[dst] = offset + (unsigned long long)i;
+      if (out_log_l) out_log_l[dst] = log_l[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) running += all;
+    __syncthreads();
+  }
+}
+
 // ==========================================================================
 // host-side launch helpers
 // ==========================================================================
@@ -714,7 +774,8 @@ int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  const double* data_d, int bound, int64_t n, uint64_t seed,
                  uint64_t offset, uint32_t stream_id, double* points,
                  uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
-                 const double* like_p, double* log_l, cudaStream_t st);
+                 const double* like_p, double* log_l,
+                 const unsigned long long* gather, cudaStream_t st);
 
 // emulator of neural bound j on whitened rows; ORs into passf and/or writes
 // the scores.
@@ -949,13 +1010,13 @@ int nb200_union_propose(const int32_t* meta_h, const int32_t* meta_d,
     k_union_propose<true><<<blocks_for(n, threads), threads, smem,
                             (cudaStream_t)stream>>>(
         meta_d, rec_off, data_d, n, seed, offset, stream_id, k_d, z_d,
-        cube_u_d, u_d, r_d, points_d, code_d, n_bound_d);
+        cube_u_d, u_d, r_d, points_d, code_d, n_bound_d, nullptr);
   } else {
     if (opt_in_smem(k_union_propose<false>, smem)) return 2;
     k_union_propose<false><<<blocks_for(n, threads), threads, smem,
                              (cudaStream_t)stream>>>(
         meta_d, rec_off, data_d, n, seed, offset, stream_id, nullptr, nullptr,
-        nullptr, nullptr, nullptr, points_d, code_d, n_bound_d);
+        nullptr, nullptr, nullptr, points_d, code_d, n_bound_d, nullptr);
   }
   NB_LAUNCH_OK();
   return 0;
@@ -1092,6 +1153,65 @@ int nb200_compact(const double* points_d, const double* log_l_d,
   return 0;
 }
 
+int nb200_compact_index(const double* log_l_d, const uint8_t* code_d,
+                        int64_t n, uint64_t offset, uint64_t* out_index_d,
+                        double* out_log_l_d, int64_t* n_out_d,
+                        void* workspace_d, size_t workspace_bytes,
+                        void* stream) {
+  NB_CHECK(n >= 0, "negative n");
+  NB_CHECK(code_d && out_index_d && n_out_d, "null argument");
+  NB_CHECK(workspace_bytes >= nb200_workspace_bytes(n, 1),
+           "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws;
+  workspace_layout(n < 1 ? 1 : n, 1, (char*)workspace_d, &ws);
+  const int nblocks = (int)((n + CMP_ITEMS - 1) / CMP_ITEMS);
+  if (nblocks == 0) {
+    NB_CUDA(cudaMemsetAsync(n_out_d, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  ProfScope prof(ST_COMPACT, st);
+  k_compact_count<<<nblocks, CMP_THREADS, 0, st>>>(code_d, n, ws.block_count);
+  NB_LAUNCH_OK();
+  k_compact_index<<<nblocks, CMP_THREADS, 0, st>>>(
+      log_l_d, code_d, n, (unsigned long long)offset, ws.block_count,
+      (unsigned long long*)out_index_d, out_log_l_d, (long long*)n_out_d);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+int nb200_materialize(const int32_t* meta_h, const int32_t* meta_d,
+                      const double* data_d, int bound, uint64_t seed,
+                      uint32_t stream_id, int mlp_mode,
+                      const uint64_t* index_d, int64_t k, double* points_out_d,
+                      void* stream) {
+  if (check_bound(meta_h, bound)) return 1;
+  NB_CHECK(k >= 0, "negative k");
+  if (k == 0) return 0;
+  NB_CHECK(index_d && points_out_d, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long* gather = (const unsigned long long*)index_d;
+  // the SAME kernel the cycle would run for this bound and emulator
+  // arithmetic (their sums round differently)
+  if (mlp_mode == NB200_MLP_TF32 &&
+      front_applicable(meta_h, bound, nullptr, nullptr))
+    return launch_front(meta_h, meta_d, data_d, bound, k, seed, 0, stream_id,
+                        points_out_d, nullptr, nullptr, nullptr, -1, nullptr,
+                        nullptr, gather, st);
+  const Rec rec = record(meta_h, bound);
+  const int d = rec.d();
+  const int threads = threads_for(d);
+  const size_t smem = smem_rows(threads, d, 2);
+  if (opt_in_smem(k_union_propose<false>, smem)) return 2;
+  ProfScope prof(ST_PROPOSE, st);
+  k_union_propose<false><<<blocks_for(k, threads), threads, smem, st>>>(
+      meta_d, (int)(rec.r - meta_h), data_d, k, seed, 0, stream_id, nullptr,
+      nullptr, nullptr, nullptr, nullptr, points_out_d, nullptr, nullptr,
+      gather);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
 int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
                 const double* data_d, int bound, int first_later, int n_later,
                 int64_t n, uint64_t seed, uint64_t offset, uint32_t stream_id,
@@ -1129,7 +1249,7 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
     rc = launch_front(meta_h, meta_d, data_d, bound, n, seed, offset,
                       stream_id, points_d, code_d, ws.maskj, ws.xs32,
                       fused_tail ? like_id : -1, like_params_d,
-                      fused_tail ? log_l_d : nullptr, st);
+                      fused_tail ? log_l_d : nullptr, nullptr, st);
     if (rc) return rc;
     {
       ProfScope prof(ST_MLP, st);

@@ -42,13 +42,16 @@ __device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) *
          1.1102230246251565e-16;
 }
-// Two standard normals by Box-Muller in fp32 (24-bit uniforms, radius <=
-// 5.9 sigma) on the special-function unit (MUFU lg2 / sqrt / sin / cos).  The
-// normals only fix a direction on the sphere, so ~1e-6 absolute accuracy is
-// ample; everything downstream is fp64.
+// Two standard normals by Box-Muller in fp32 (radius <= 5.7 sigma) on the
+// special-function unit (MUFU lg2 / sqrt / sin / cos).  The normals only fix a
+// direction on the sphere, so ~1e-6 absolute accuracy is ample; everything
+// downstream is fp64.  The radial uniform uses 23 bits: (k + 0.5) * 2^-23 is
+// exact in fp32 for every k < 2^23 and therefore strictly inside (0, 1) -- with
+// 24 bits the largest value rounded to 1.0f, i.e. a radius of exactly 0, and a
+// d <= 2 ellipsoid part would have divided by |z| = 0 once in 2^24 draws.
 __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0,
                                         float& n1) {
-  const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u1 = ((float)(a >> 9) + 0.5f) * 1.1920928955078125e-7f;
   const float ang =
       ((float)(b >> 8) * 5.9604644775390625e-8f - 0.5f) * 6.283185307179586f;
   const float rr = sqrtf(-2.0f * __logf(u1));

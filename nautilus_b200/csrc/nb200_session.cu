@@ -31,8 +31,14 @@ struct Slot {
   double* log_l_h = nullptr;               // pinned
   unsigned long long* small_h = nullptr;   // pinned
   double* like_h = nullptr;                // pinned staging
+  // index mode (nb200_session_set_returns): 16 bytes per in-shell proposal
+  unsigned long long* out_index_d = nullptr;
+  unsigned long long* index_h = nullptr;   // pinned
+  int64_t copied = 0;                      // entries already on their way
   cudaEvent_t done = nullptr;
+  cudaEvent_t copied_ev = nullptr;
   int busy = 0;
+  int mode = 0;                            // returns mode of the batch in flight
 };
 
 }  // namespace nb200
@@ -54,6 +60,13 @@ struct nb200_session {
   uint8_t* code_d = nullptr;
   void* ws = nullptr;
   size_t wsb = 0;
+  int returns = NB200_RETURN_ROWS;
+  int64_t last_k = -1;         // in-shell count of the last finished batch
+  // materialize: grow-only staging
+  cudaStream_t aux = nullptr;
+  unsigned long long* mat_index_d = nullptr;
+  double* mat_points_d = nullptr;
+  int64_t mat_cap = 0;
   nb200::Slot slot[nb200::SESSION_MAX_SLOTS];
 };
 
@@ -67,11 +80,15 @@ static void session_free(nb200_session* s) {
   for (int i = 0; i < SESSION_MAX_SLOTS; ++i) {
     Slot& t = s->slot[i];
     cudaFree(t.out_points_d); cudaFree(t.out_log_l_d); cudaFree(t.small_d);
-    cudaFree(t.like_d);
+    cudaFree(t.like_d); cudaFree(t.out_index_d);
     cudaFreeHost(t.points_h); cudaFreeHost(t.log_l_h);
     cudaFreeHost(t.small_h); cudaFreeHost(t.like_h);
+    cudaFreeHost(t.index_h);
     if (t.done) cudaEventDestroy(t.done);
+    if (t.copied_ev) cudaEventDestroy(t.copied_ev);
   }
+  if (s->aux) { cudaStreamSynchronize(s->aux); cudaStreamDestroy(s->aux); }
+  cudaFree(s->mat_index_d); cudaFree(s->mat_points_d);
   cudaFreeHost(s->meta_h); cudaFreeHost(s->data_h);
   cudaFree(s->meta_d); cudaFree(s->data_d); cudaFree(s->points_d);
   cudaFree(s->log_l_d); cudaFree(s->code_d); cudaFree(s->ws);
@@ -149,8 +166,12 @@ int nb200_session_create(const int32_t* meta_h, int64_t n_meta,
     NB_S(cudaMallocHost(&t.log_l_h, sizeof(double) * cap));
     NB_S(cudaMallocHost(&t.small_h, 8 * SMALL_WORDS));
     NB_S(cudaMallocHost(&t.like_h, sizeof(double) * s->like_cap));
+    NB_S(cudaMalloc(&t.out_index_d, sizeof(unsigned long long) * n_max));
+    NB_S(cudaMallocHost(&t.index_h, sizeof(unsigned long long) * cap));
     NB_S(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+    NB_S(cudaEventCreateWithFlags(&t.copied_ev, cudaEventDisableTiming));
   }
+  NB_S(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
   NB_S(cudaMemcpyAsync(s->meta_d, s->meta_h, sizeof(int32_t) * n_meta,
                        cudaMemcpyHostToDevice, s->compute));
   NB_S(cudaMemcpyAsync(s->data_d, s->data_h, sizeof(double) * n_data,
@@ -217,15 +238,43 @@ int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
                        n_like_params, log_l_min, mlp_mode, s->points_d,
                        s->log_l_d, s->code_d, lse_d, cnt_d, s->ws, s->wsb, st);
   if (rc) return rc;
-  rc = nb200_compact(s->points_d, like_id >= 0 ? s->log_l_d : nullptr,
-                     s->code_d, n, s->d, t.out_points_d,
-                     like_id >= 0 ? t.out_log_l_d : nullptr, n_out_d, s->ws,
-                     s->wsb, st);
+  t.mode = s->returns;
+  if (t.mode == NB200_RETURN_INDEX) {
+    rc = nb200_compact_index(like_id >= 0 ? s->log_l_d : nullptr, s->code_d, n,
+                             offset, (uint64_t*)t.out_index_d,
+                             like_id >= 0 ? t.out_log_l_d : nullptr, n_out_d,
+                             s->ws, s->wsb, st);
+  } else {
+    rc = nb200_compact(s->points_d, like_id >= 0 ? s->log_l_d : nullptr,
+                       s->code_d, n, s->d, t.out_points_d,
+                       like_id >= 0 ? t.out_log_l_d : nullptr, n_out_d, s->ws,
+                       s->wsb, st);
+  }
   if (rc) return rc;
   NB_CUDA(cudaMemcpyAsync(t.small_h, t.small_d, 8 * SMALL_WORDS,
                           cudaMemcpyDeviceToHost, st));
   NB_CUDA(cudaEventRecord(t.done, st));
   t.busy = like_id >= 0 ? 2 : 1;
+  if (t.mode == NB200_RETURN_INDEX) {
+    // the copy does not wait for the host to learn the row count: a little
+    // more than the previous batch kept is sent on its way behind the
+    // kernels (wait tops up the rare shortfall)
+    int64_t guess = s->last_k < 0 ? s->cap : s->last_k + s->last_k / 4 + 1024;
+    if (guess > s->cap) guess = s->cap;
+    if (guess > n) guess = n;
+    t.copied = guess;
+    NB_CUDA(cudaStreamWaitEvent(s->copy, t.done, 0));
+    if (guess > 0) {
+      NB_CUDA(cudaMemcpyAsync(t.index_h, t.out_index_d,
+                              sizeof(unsigned long long) * guess,
+                              cudaMemcpyDeviceToHost, s->copy));
+      if (like_id >= 0)
+        NB_CUDA(cudaMemcpyAsync(t.log_l_h, t.out_log_l_d,
+                                sizeof(double) * guess,
+                                cudaMemcpyDeviceToHost, s->copy));
+    }
+    NB_CUDA(cudaEventRecord(t.copied_ev, s->copy));
+  }
   return 0;
 }
 
@@ -236,11 +285,15 @@ int nb200_session_wait(nb200_session* s, int slot, const double** points_h,
   NB_CHECK(slot >= 0 && slot < s->n_slots, "slot out of range");
   Slot& t = s->slot[slot];
   NB_CHECK(t.busy, "nothing was submitted on this slot");
+  NB_CHECK(t.mode == NB200_RETURN_ROWS,
+           "this batch was submitted in index mode: use "
+           "nb200_session_wait_index");
   NB_CUDA(cudaSetDevice(s->device));
   NB_CUDA(cudaEventSynchronize(t.done));
   const bool with_ll = t.busy == 2;
   t.busy = 0;
   const int64_t k = (int64_t)t.small_h[NB200_N_LSE + NB200_N_CNT];
+  s->last_k = k;
   if (k > s->cap)
     return fail("nautilus_b200: %s (need %lld rows, cap %lld)",
                 "session output capacity too small", k, s->cap);
@@ -261,6 +314,94 @@ int nb200_session_wait(nb200_session* s, int slot, const double** points_h,
   if (counters_h)
     memcpy(counters_h, t.small_h + NB200_N_LSE,
            sizeof(int64_t) * NB200_N_CNT);
+  return 0;
+}
+
+int nb200_session_set_returns(nb200_session* s, int what) {
+  NB_CHECK(s != nullptr, "null session");
+  NB_CHECK(what == NB200_RETURN_ROWS || what == NB200_RETURN_INDEX,
+           "returns must be NB200_RETURN_ROWS or NB200_RETURN_INDEX");
+  s->returns = what;
+  return 0;
+}
+
+int nb200_session_wait_index(nb200_session* s, int slot,
+                             const uint64_t** index_h,
+                             const double** log_l_h, int64_t* n_out,
+                             double* lse_h, int64_t* counters_h) {
+  NB_CHECK(s != nullptr, "null session");
+  NB_CHECK(slot >= 0 && slot < s->n_slots, "slot out of range");
+  Slot& t = s->slot[slot];
+  NB_CHECK(t.busy, "nothing was submitted on this slot");
+  NB_CHECK(t.mode == NB200_RETURN_INDEX,
+           "this batch was submitted in row mode: use nb200_session_wait");
+  NB_CUDA(cudaSetDevice(s->device));
+  NB_CUDA(cudaEventSynchronize(t.copied_ev));
+  const bool with_ll = t.busy == 2;
+  t.busy = 0;
+  const int64_t k = (int64_t)t.small_h[NB200_N_LSE + NB200_N_CNT];
+  s->last_k = k;
+  if (k > s->cap)
+    return fail("nautilus_b200: %s (need %lld rows, cap %lld)",
+                "session output capacity too small", k, s->cap);
+  if (k > t.copied) {      // the guess fell short: fetch the rest
+    const int64_t rest = k - t.copied;
+    NB_CUDA(cudaMemcpyAsync(t.index_h + t.copied, t.out_index_d + t.copied,
+                            sizeof(unsigned long long) * rest,
+                            cudaMemcpyDeviceToHost, s->copy));
+    if (with_ll)
+      NB_CUDA(cudaMemcpyAsync(t.log_l_h + t.copied, t.out_log_l_d + t.copied,
+                              sizeof(double) * rest, cudaMemcpyDeviceToHost,
+                              s->copy));
+    NB_CUDA(cudaStreamSynchronize(s->copy));
+  }
+  if (index_h) *index_h = (const uint64_t*)t.index_h;
+  if (log_l_h) *log_l_h = with_ll ? t.log_l_h : nullptr;
+  if (n_out) *n_out = k;
+  if (lse_h) memcpy(lse_h, t.small_h, sizeof(double) * NB200_N_LSE);
+  if (counters_h)
+    memcpy(counters_h, t.small_h + NB200_N_LSE,
+           sizeof(int64_t) * NB200_N_CNT);
+  return 0;
+}
+
+int nb200_session_materialize(nb200_session* s, int bound, uint64_t seed,
+                              uint32_t stream_id, int mlp_mode,
+                              const uint64_t* index_h, int64_t k,
+                              double* points_out_h) {
+  NB_CHECK(s != nullptr, "null session");
+  NB_CHECK(k >= 0, "negative k");
+  if (k == 0) return 0;
+  NB_CHECK(index_h && points_out_h, "null argument");
+  NB_CUDA(cudaSetDevice(s->device));
+  if (k > s->mat_cap) {
+    NB_CUDA(cudaStreamSynchronize(s->aux));
+    cudaFree(s->mat_index_d); cudaFree(s->mat_points_d);
+    s->mat_index_d = nullptr; s->mat_points_d = nullptr; s->mat_cap = 0;
+    const int64_t cap = k + k / 2;
+    NB_CUDA(cudaMalloc(&s->mat_index_d, sizeof(unsigned long long) * cap));
+    NB_CUDA(cudaMalloc(&s->mat_points_d, sizeof(double) * cap * s->d));
+    s->mat_cap = cap;
+  }
+  // the stack of the batches in flight is the one to regenerate from: order
+  // behind the compute stream's pending uploads
+  cudaEvent_t ev;
+  NB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  NB_CUDA(cudaEventRecord(ev, s->compute));
+  NB_CUDA(cudaStreamWaitEvent(s->aux, ev, 0));
+  NB_CUDA(cudaEventDestroy(ev));
+  NB_CUDA(cudaMemcpyAsync(s->mat_index_d, index_h,
+                          sizeof(unsigned long long) * k,
+                          cudaMemcpyHostToDevice, s->aux));
+  int rc = nb200_materialize(s->meta_h, s->meta_d, s->data_d, bound, seed,
+                             stream_id, mlp_mode,
+                             (const uint64_t*)s->mat_index_d, k,
+                             s->mat_points_d, s->aux);
+  if (rc) return rc;
+  NB_CUDA(cudaMemcpyAsync(points_out_h, s->mat_points_d,
+                          sizeof(double) * k * s->d, cudaMemcpyDeviceToHost,
+                          s->aux));
+  NB_CUDA(cudaStreamSynchronize(s->aux));
   return 0;
 }
 

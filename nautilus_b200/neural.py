@@ -85,7 +85,20 @@ class NeuralNetworkEmulator:
         if batch_size == 'auto':
             batch_size = min(200, len(x))
         dev = default_device()
-        xs = torch.from_numpy((x - emulator.mean) / emulator.scale).to(dev)
+        # The callers hand the rows over sorted by likelihood
+        # (Sampler.add_bound sorts before NautilusBound.compute) and the
+        # trainer walks them in a per-epoch AFFINE order i -> (a i + b) mod M:
+        # on rank-ordered rows a minibatch would be an arithmetic progression
+        # through the likelihood ranks (a few narrow bands when a / M is close
+        # to a simple fraction).  One seeded Fisher-Yates shuffle of the rows
+        # removes the ordering; an arithmetic progression through shuffled
+        # rows is an unstructured subset, like sklearn's per-epoch shuffle
+        # (_multilayer_perceptron.py:708).
+        order = np.random.default_rng(
+            [int(seed) & 0xFFFFFFFFFFFFFFFF, 0x5AFF1E]).permutation(len(x))
+        xs = torch.from_numpy(
+            ((x - emulator.mean) / emulator.scale)[order]).to(dev)
+        y = y[order]
         params, n_iter, loss = ops.mlp_fit(
             xs.contiguous(), torch.from_numpy(y).to(dev), sizes, n_networks,
             seed=seed, lr=kwargs['learning_rate_init'],

@@ -229,6 +229,41 @@ class DeviceStack:
         return out_points, out_log_l, n_out
 
 
+    def compact_index(self, log_l, code, offset=0):
+        """(global index u64[n] as int64 tensor, log_l f64[n], n_out) of the
+        in-shell rows (nb200_compact_index); nothing is synchronised and only
+        the first n_out entries are meaningful."""
+        n = code.numel()
+        index = torch.empty(n, dtype=torch.int64, device=self.device)
+        out_ll = None if log_l is None else torch.empty_like(log_l)
+        n_out = torch.empty(1, dtype=torch.int64, device=self.device)
+        buf, nbytes = self.ws.get(n, self.n_dim)
+        _lib.check(_lib.lib().nb200_compact_index(
+            _ptr(log_l), _ptr(code), n, int(offset), _ptr(index),
+            _ptr(out_ll), _ptr(n_out), _ptr(buf), nbytes, _stream()))
+        return index, out_ll, n_out
+
+    def materialize(self, bound, index, seed=0, stream_id=0, mode=MLP_F64):
+        """Rows f64[k,d] of the proposals with global indices ``index``
+        (int64/uint64 CUDA tensor), bit-identical to what ``cycle`` wrote for
+        them with the same ``mode`` (nb200_materialize)."""
+        if not (index.is_cuda and index.is_contiguous() and
+                index.dtype in (torch.int64, torch.uint64)):
+            raise ValueError('index must be a contiguous CUDA int64 tensor')
+        k = index.numel()
+        out = torch.empty((k, self.n_dim), dtype=torch.float64,
+                          device=self.device)
+        _lib.check(_lib.lib().nb200_materialize(
+            self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound,
+            int(seed), int(stream_id), int(mode), _ptr(index), k, _ptr(out),
+            _stream()))
+        return out
+
+
+RETURN_ROWS = 0
+RETURN_INDEX = 1
+
+
 class HostSession:
     """Host-buffer form of the cycle (``nb200_session_*``): NumPy in, NumPy
     out, no torch tensors.  ``submit`` enqueues one raw batch and returns at
@@ -242,7 +277,9 @@ class HostSession:
     """
 
     def __init__(self, specs, n_max, cap=None, n_slots=2, like_params_max=0,
-                 device=None):
+                 device=None, returns='rows'):
+        if returns not in ('rows', 'index'):
+            raise ValueError("returns must be 'rows' or 'index'")
         if device is not None:
             torch.cuda.set_device(device)
         meta, data = pack_stack(specs)
@@ -258,6 +295,10 @@ class HostSession:
             self.data_h.ctypes.data_as(ctypes.c_void_p), self.data_h.size,
             self.n_max, self.cap, self.n_slots, int(like_params_max),
             ctypes.byref(self._h)))
+        self.returns = returns
+        if returns == 'index':
+            _lib.check(_lib.lib().nb200_session_set_returns(
+                self._h, RETURN_INDEX))
 
     @property
     def stack_bytes(self):
@@ -289,28 +330,47 @@ class HostSession:
 
     def wait(self, slot):
         """dict(points f64[k,d], log_l f64[k] | None, lse f64[4],
-        counters i64[8]) for the batch submitted on ``slot``."""
+        counters i64[8]) for the batch submitted on ``slot``; in index mode
+        ``index`` u64[k] (global proposal indices) replaces ``points``."""
         p_pts, p_ll = ctypes.c_void_p(), ctypes.c_void_p()
         k = ctypes.c_int64()
         lse = np.empty(N_LSE)
         counters = np.empty(N_CNT, dtype=np.int64)
-        _lib.check(_lib.lib().nb200_session_wait(
+        fn = (_lib.lib().nb200_session_wait_index if self.returns == 'index'
+              else _lib.lib().nb200_session_wait)
+        _lib.check(fn(
             self._h, int(slot), ctypes.byref(p_pts), ctypes.byref(p_ll),
             ctypes.byref(k), lse.ctypes.data_as(ctypes.c_void_p),
             counters.ctypes.data_as(ctypes.c_void_p)))
         k = int(k.value)
         d = self.n_dim
 
-        def view(ptr, shape):
+        def view(ptr, shape, dtype=np.float64):
             if not ptr.value or k == 0:
-                return np.empty(shape)
+                return np.empty(shape, dtype=dtype)
             buf = (ctypes.c_double * int(np.prod(shape))).from_address(
                 ptr.value)
-            return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+            return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
-        return dict(points=view(p_pts, (k, d)),
-                    log_l=view(p_ll, (k,)) if p_ll.value else None,
-                    lse=lse, counters=counters)
+        out = dict(log_l=view(p_ll, (k,)) if p_ll.value else None,
+                   lse=lse, counters=counters)
+        if self.returns == 'index':
+            out['index'] = view(p_pts, (k,), np.uint64)
+        else:
+            out['points'] = view(p_pts, (k, d))
+        return out
+
+    def materialize(self, bound, index, seed=0, stream_id=0, mode=MLP_F64):
+        """Rows f64[k,d] (NumPy) of the proposals with global indices
+        ``index`` of stack record ``bound``: bit-identical to the rows the
+        cycle produced for them (nb200_session_materialize)."""
+        index = np.ascontiguousarray(index, dtype=np.uint64)
+        out = np.empty((index.size, self.n_dim))
+        _lib.check(_lib.lib().nb200_session_materialize(
+            self._h, int(bound), int(seed), int(stream_id), int(mode),
+            index.ctypes.data_as(ctypes.c_void_p), index.size,
+            out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     def close(self):
         if self._h:

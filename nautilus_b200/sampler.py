@@ -115,6 +115,15 @@ class Sampler:
             if p is None or isinstance(p, GpuPool) or (
                     isinstance(p, int) and p == 1):
                 pools[i] = p if isinstance(p, GpuPool) else None
+            elif i == 0 and self.device_likelihood:
+                # a device likelihood is evaluated inside the cycle kernels:
+                # worker processes for it would never be used
+                if len(pools) == 1:
+                    raise ValueError(
+                        'A DeviceLikelihood runs on the GPU; a process pool '
+                        'has no use for it. Pass pool=GpuPool(n) to shard '
+                        'the proposal batch over n GPUs.')
+                pools[i] = None
             elif i == 0 and isinstance(p, int):
                 pools[i] = NautilusPool(p, likelihood=self.likelihood)
                 self.likelihood = likelihood_worker
@@ -382,7 +391,9 @@ class Sampler:
             for j in range(n):
                 m[i, j] = int(self._contains(j, pts).sum().item())
         if fractional:
-            m = m / np.maximum(self.shell_n, 1)[:, np.newaxis]
+            # every stored point of shell i lies in bound i: the diagonal
+            # counts the points (sampler.py:1248-1250)
+            m = m / np.maximum(np.diag(m), 1)[:, np.newaxis]
         return m
 
     # ------------------------------------------------------------------

@@ -37,7 +37,7 @@ def test_library_exports_every_symbol(built):
 
 def test_library_loads_and_reports_version(built):
     lib = _lib.lib()
-    assert lib.nb200_version() == 100
+    assert lib.nb200_version() == 200
     assert lib.nb200_workspace_bytes(1 << 20, 30) > (1 << 20) * 30 * 8
 
 

@@ -137,3 +137,104 @@ def test_session_errors(golden):
         ops.HostSession([spec], n_max=0)
     sess.close()
     sess.close()              # idempotent
+
+
+# --------------------------------------------------------------------------
+# index mode: 16 bytes per in-shell proposal cross PCIe, rows are regenerated
+# --------------------------------------------------------------------------
+
+@pytest.mark.parametrize('mode,front', [(ops.MLP_F64, ''), (ops.MLP_TF32, ''),
+                                        (ops.MLP_TF32, 'dfma')])
+def test_index_session_and_materialize_bit_identical(golden, monkeypatch,
+                                                     mode, front):
+    """(index, log_l) of the index-mode session == the row-mode session's
+    rows: log_l equal, materialised rows BIT-identical to the rows the cycle
+    wrote, for each of the three proposal kernels (staged k_union_propose,
+    DMMA front, DFMA front)."""
+    if front:
+        monkeypatch.setenv('NB200_FRONT', front)
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    like = likelihoods.Gaussian(30)
+    n, seed, sid = 1 << 14, 11, 5
+    kw = dict(seed=seed, stream_id=sid, like_id=like.like_id,
+              like_params=like.params(), log_l_min=-30.0, mode=mode)
+    rows = ops.HostSession([spec], n_max=n, n_slots=2,
+                           like_params_max=len(like.params()))
+    idx = ops.HostSession([spec], n_max=n, n_slots=2, returns='index',
+                          like_params_max=len(like.params()))
+    offs = [0, 3 * n, (1 << 40) + 7]       # indices beyond 32 bits too
+    for slot, off in enumerate(offs):
+        rows.submit(slot & 1, 0, n, offset=off, **kw)
+        idx.submit(slot & 1, 0, n, offset=off, **kw)
+        a = {k: np.array(v) for k, v in rows.wait(slot & 1).items()}
+        b = {k: np.array(v) for k, v in idx.wait(slot & 1).items()}
+        assert 'points' not in b and b['index'].dtype == np.uint64
+        assert np.array_equal(a['log_l'], b['log_l'])
+        assert np.array_equal(a['counters'], b['counters'])
+        assert np.array_equal(a['lse'], b['lse'])
+        assert len(b['index']) == a['counters'][ops.CNT_IN_SHELL] > 0
+        assert np.all(np.diff(b['index'].astype(np.int64)) > 0)   # stable
+        assert b['index'][0] >= off and b['index'][-1] < off + n
+        got = idx.materialize(0, b['index'], seed=seed, stream_id=sid,
+                              mode=mode)
+        assert np.array_equal(got, a['points'])
+        # any subset, any order
+        pick = b['index'][::-7][:100]
+        sub = idx.materialize(0, pick, seed=seed, stream_id=sid, mode=mode)
+        assert np.array_equal(sub, a['points'][::-7][:100])
+    # the first batch sized its copy from cap, the later ones from the
+    # previous count: a batch that keeps far more than its predecessor still
+    # comes back complete (top-up path)
+    idx.submit(0, 0, 512, offset=0, **kw)
+    few = idx.wait(0)
+    assert len(few['index']) < 512
+    idx.submit(0, 0, n, offset=0, **kw)
+    many = {k: np.array(v) for k, v in idx.wait(0).items()}
+    rows.submit(0, 0, n, offset=0, **kw)
+    ref = rows.wait(0)
+    assert np.array_equal(many['log_l'], ref['log_l'])
+    assert len(many['index']) > len(few['index']) + len(few['index']) // 4 + \
+        1024
+    # the row-mode wait refuses a batch submitted in index mode
+    idx.submit(0, 0, 100, **kw)
+    with pytest.raises(_lib.NautilusB200Error, match='index mode'):
+        _lib.check(_lib.lib().nb200_session_wait(idx._h, 0, None, None, None,
+                                                 None, None))
+    idx.wait(0)
+    rows.close()
+    idx.close()
+
+
+def test_device_compact_index_and_materialize(golden):
+    """Device-pointer forms: nb200_compact_index / nb200_materialize on a
+    staged-path bound with cube dimensions and several ellipsoids."""
+    spec = flat_to_spec(golden('nautilus_d4'))
+    stack = ops.DeviceStack([spec])
+    like = likelihoods.Gaussian(4, sigma=0.3)
+    n, off = 30000, 123456789012
+    out = stack.cycle(0, n, seed=4, offset=off, stream_id=2,
+                      like_id=like.like_id,
+                      like_params=like.device_params('cuda'))
+    index, ll, n_out = stack.compact_index(out['log_l'], out['code'],
+                                           offset=off)
+    k = int(n_out.item())
+    sel = host(out['code']) == ops.CODE_IN_SHELL
+    assert k == sel.sum() > 0
+    assert np.array_equal(host(index)[:k], off + np.flatnonzero(sel))
+    assert np.array_equal(host(ll)[:k], host(out['log_l'])[sel])
+    rows = stack.materialize(0, index[:k].contiguous(), seed=4, stream_id=2)
+    assert np.array_equal(host(rows), host(out['points'])[sel])
+    # rejected proposals can be regenerated too (rows are written for all)
+    rej = torch.as_tensor(off + np.flatnonzero(~sel)[:50], device='cuda')
+    assert np.array_equal(host(stack.materialize(0, rej, seed=4,
+                                                 stream_id=2)),
+                          host(out['points'])[~sel][:50])
+    # empty
+    e = stack.materialize(0, index[:0].contiguous(), seed=4, stream_id=2)
+    assert e.shape == (0, 4)
+    # the unit cube of shell 0
+    cube = ops.DeviceStack([dict(kind='cube', n_dim=5)])
+    o = cube.cycle(0, 1000, seed=1, offset=17)
+    idx = torch.arange(17, 1017, device='cuda')
+    assert np.array_equal(host(cube.materialize(0, idx, seed=1)),
+                          host(o['points']))

@@ -1,9 +1,10 @@
 """tcgen05 emulator path (NB200_MLP_TF32) against the fp64 parity path.
 
 tf32 x tf32 -> fp32 arithmetic cannot be bit-exact against scikit-learn's
-fp64 forward pass; the bar is stated here: scores within 5e-3 absolute of the
-fp64 kernel, and NeuralBound membership flips only for points whose fp64
-score lies within that band of the threshold.
+fp64 forward pass; the bar is stated here: scores within TOL_SCORE = 2e-3
+absolute of the fp64 kernel (measured 1.1e-3), NeuralBound membership flips
+only for points whose fp64 score lies within that band of the threshold, and
+fewer than TOL_FLIPS = 1e-3 of the proposals flip (measured 2.5e-4).
 """
 
 import numpy as np
@@ -17,7 +18,8 @@ from oracle import c_oracle  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-TOL_SCORE = 5e-3
+TOL_SCORE = 2e-3
+TOL_FLIPS = 1e-3
 
 
 def dev(a):
@@ -54,7 +56,7 @@ def test_tf32_membership_flips_only_at_threshold(golden):
     rate = flips.mean()
     print('tf32 membership flip rate = {:.3e} ({} of {})'.format(
         rate, flips.sum(), n))
-    assert rate < 0.02
+    assert rate < TOL_FLIPS
     # every flip sits within the score tolerance of the threshold
     meta, data = pack_stack([spec])
     idx = np.flatnonzero(flips)
@@ -102,10 +104,10 @@ def test_tf32_cycle_self_consistent(golden):
                         mode=ops.MLP_F64)
     diff = (out['code'] != out64['code']).float().mean().item()
     print('cycle disposition mismatch tf32 vs f64: {:.3e}'.format(diff))
-    assert diff < 0.02
+    assert diff < TOL_FLIPS
 
 
-def _fused_vs_staged(spec, n, like, seed):
+def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS):
     """The fused tf32 cycle (k_front -> k_mlp_tf32 with likelihood and shell
     sums in its tail) against the same decisions rebuilt from staged ops."""
     from oracle import nautilus_oracle as orc
@@ -131,6 +133,18 @@ def _fused_vs_staged(spec, n, like, seed):
     nn = stack.contains(0, pts, which=2, mode=ops.MLP_TF32).cpu().numpy()
     assert np.array_equal(code == 4, acc & nn)
     assert np.array_equal(code == 2, acc & ~nn)
+    # ... and against the fp64 ORACLE (not the same kernel): the dispositions
+    # of orc.classify differ only where the oracle's own fp64 score lies
+    # within TOL_SCORE of the threshold
+    ref_code, _, _ = orc.classify(spec, [], p, r, None)
+    bad = np.flatnonzero(ref_code != code)
+    assert len(bad) <= max(2, flip_tol * n), (len(bad), n)
+    if len(bad):
+        assert set(ref_code[bad]) | set(code[bad]) <= {2, 4}
+        nbs = spec['neural'][0]
+        _, score = orc.neural_contains(nbs, p[bad], return_score=True)
+        thr = nbs['score_predict_min'] - 1e-9
+        assert np.nanmax(np.abs(score - thr)) < TOL_SCORE
     sel = code == 4
     ref_ll = like(p[sel])
     assert np.all(np.isnan(log_l[~sel]))
@@ -243,7 +257,9 @@ def test_dmma_front_kernel_all_row_widths(d, monkeypatch):
                              score_predict_min=float(np.median(
                                  emu.predict(whitened))))])
     like = likelihoods.Gaussian(d, sigma=0.2)
-    cnt = _fused_vs_staged(spec, 6000, like, seed=d)
+    # (a 15-epoch toy network thresholded at its median score: many points
+    # sit at the threshold, hence the wider flip allowance)
+    cnt = _fused_vs_staged(spec, 6000, like, seed=d, flip_tol=5e-3)
     assert cnt[ops.CNT_IN_SHELL] > 0 and cnt[ops.CNT_NN_REJECT] > 0
     outs = []
     for which in ('mma', 'dfma'):
