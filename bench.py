@@ -35,6 +35,15 @@ WORKLOAD = ('cfg2: 30-D isotropic Gaussian (sigma=0.1), n_live=2000, bound '
             'batch=2^20 raw proposals per GPU per step')
 
 
+def workload_config(batch):
+    """The `config` object: identical for both arms (same workload)."""
+    return {'workload': WORKLOAD, 'batch_per_gpu': batch,
+            'l2': 'GPU arm: each step writes {:.0f} MB of proposals (> 126 MB '
+                  'L2), no flush needed; bound parameters (~520 KB) are meant '
+                  'to stay cache-resident'.format(
+                      batch * ALGO_BYTES_PER_PROPOSAL / 1e6)}
+
+
 _SPEC = None
 
 
@@ -64,18 +73,48 @@ def measured_peaks():
 # CPU baseline: the oracle port of the reference loop, on host cores
 # --------------------------------------------------------------------------
 
+REF_N_BATCH = 1000      # n_batch of the reference Sampler in the CPU arm
+
+
+def cpu_kind():
+    """'reference' when the unmodified reference travelled with the snapshot
+    (oracle/_ref, placed by oracle/make_ref.sh), else the oracle port."""
+    from oracle import ref_arm
+    return 'reference' if ref_arm.available() else 'port'
+
+
+def _log_l_min():
+    like_norm = -0.5 * D * np.log(2 * np.pi * 0.1**2)
+    with np.load(os.path.join(ROOT, 'tests', 'golden',
+                              'cfg2_bound_d30.npz')) as f:
+        return float(f['log_l_min']) + like_norm
+
+
 def _cpu_worker(args):
-    """NautilusBound.sample + likelihood + update_shell_info for
-    ~n_raw raw proposals, exactly the reference's loop structure (1000 raw
-    draws per iteration, bounds/union.py:305-323, bounds/nautilus.py:213-222,
-    sampler.py:925-943), single-threaded BLAS like the reference
-    (sampler.py:789)."""
-    seed, n_raw = args
+    """One host core's share of the CPU arm, single-threaded BLAS like the
+    reference (sampler.py:789).
+
+    kind 'reference': the UNMODIFIED reference (oracle/_ref/nautilus): its own
+    ``Sampler.add_samples`` (sampler.py:1093-1144) on the config-2 bound until
+    the outer union has consumed ~n_raw raw proposals (oracle/ref_arm.py).
+    kind 'port': the oracle's restatement of the same loop
+    (NautilusBound.sample + likelihood + update_shell_info; 1000 raw draws per
+    iteration, bounds/union.py:305-323, bounds/nautilus.py:213-222,
+    sampler.py:925-943)."""
+    seed, n_raw, kind = args
     from threadpoolctl import threadpool_limits
-    from oracle import nautilus_oracle as orc
     from nautilus_b200 import likelihoods
     spec = load_spec()
     like = likelihoods.Gaussian(D)
+    if kind == 'reference':
+        from oracle import ref_arm
+        ref_arm._import_reference()          # not part of the timed loop
+        with threadpool_limits(limits=1):
+            n, dt, _ = ref_arm.run_reference_cycles(
+                spec, like, _log_l_min(), n_raw, seed=seed,
+                n_batch=REF_N_BATCH)
+        return n, dt
+    from oracle import nautilus_oracle as orc
     rng = np.random.default_rng(seed)
     with threadpool_limits(limits=1):
         t0 = time.perf_counter()
@@ -96,18 +135,20 @@ def _cpu_worker(args):
 
 
 class CpuPool:
-    """Persistent worker pool (what the reference's `pool=` keeps alive,
-    sampler.py:283-298): forked once, reused for every step."""
+    """Persistent worker processes, one per host core, each running its own
+    replica of the CPU loop (forked once, reused for every step)."""
 
-    def __init__(self, cores):
+    def __init__(self, cores, kind=None):
         import multiprocessing as mp
         self.cores = cores
+        self.kind = kind or cpu_kind()
         self.pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
 
     def run(self, n_raw_per_core, seed=0):
-        """One pass of the oracle loop on every core; returns (raw proposals,
+        """One pass of the CPU loop on every core; returns (raw proposals,
         seconds) with seconds = the slowest worker's loop time."""
-        jobs = [(seed + i, n_raw_per_core) for i in range(self.cores)]
+        jobs = [(seed + i, n_raw_per_core, self.kind)
+                for i in range(self.cores)]
         if self.pool is None:
             res = [_cpu_worker(jobs[0])]
         else:
@@ -120,13 +161,28 @@ class CpuPool:
             self.pool.join()
 
 
-def cpu_pass(cores, n_raw_per_core, seed=0):
-    """Run the oracle loop on `cores` processes; returns (raw proposals, s)."""
-    pool = CpuPool(cores)
+def cpu_pass(cores, n_raw_per_core, seed=0, kind=None):
+    """Run the CPU loop on `cores` processes; returns (raw proposals, s)."""
+    pool = CpuPool(cores, kind)
     try:
         return pool.run(n_raw_per_core, seed)
     finally:
         pool.close()
+
+
+def cpu_sample_text(kind, steps, cores, per_core):
+    if kind == 'reference':
+        return ('{} step(s) x {} processes x ~{} raw proposals each through '
+                'the UNMODIFIED reference (oracle/_ref/nautilus v1.0.6): '
+                'Sampler.add_samples(n_batch={}) -> NautilusBound.sample -> '
+                'Union.sample -> NeuralBound.contains (scikit-learn predict) '
+                '-> likelihood -> update_shell_info on the config-2 bound; '
+                'BLAS pinned to 1 thread per process as the reference does'
+                .format(steps, cores, per_core, REF_N_BATCH))
+    return ('{} step(s) x {} processes x {} raw proposals through the oracle '
+            'port of Union.sample/NautilusBound.sample/likelihood/'
+            'update_shell_info (oracle/_ref missing on this box)'
+            .format(steps, cores, per_core))
 
 
 def host_cores():
@@ -137,16 +193,19 @@ def host_cores():
 
 
 def run_reference(args):
-    """--impl reference: the CPU path on all host cores, bounded samples."""
+    """--impl reference: the reference's own CPU implementation of the path
+    on all host cores, bounded samples."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = host_cores()
+    kind = cpu_kind()
     # bounded sample: about CPU_BUDGET_S seconds of loop time for the whole
-    # run whatever --steps is (one core does ~2e5 raw proposals/s)
-    per_core = int(CPU_BUDGET_S * 2.0e5 / max(args.steps, 1))
+    # run whatever --steps is
+    rate = 6.0e4 if kind == 'reference' else 2.0e5     # raw/s on one core
+    per_core = int(CPU_BUDGET_S * rate / max(args.steps, 1))
     per_core = max(2000, min(400000, per_core // 1000 * 1000))
-    pool = CpuPool(cores)
+    pool = CpuPool(cores, kind)
     for _ in range(min(args.warmup, 3)):
         pool.run(2000)
     total, wall = 0, 0.0
@@ -156,9 +215,7 @@ def run_reference(args):
         wall += dt
     pool.close()
     value = total / wall
-    sample = ('{} steps x {} processes x {} raw proposals through the oracle '
-              'port of Union.sample/NautilusBound.sample/likelihood/'
-              'update_shell_info'.format(args.steps, cores, per_core))
+    sample = cpu_sample_text(kind, args.steps, cores, per_core)
     line = {
         'impl': 'reference', 'metric': 'raw_proposals_per_sec',
         'value': value, 'unit': 'proposals/s', 'n_gpus': args.gpus,
@@ -166,10 +223,12 @@ def run_reference(args):
         'ms_per_step': 1e3 * wall / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'impl': 'oracle port (NumPy/SciPy), '
-                   'the reference is pure Python and cannot travel'},
+        'config': workload_config(args.batch),
+        'notes': {'emulator_arith': 'f64 (scikit-learn)',
+                  'parallelism': '{} independent host processes'.format(
+                      cores)},
         'cpu_baseline': {'value': value, 'unit': 'proposals/s',
-                         'cores': cores, 'kind': 'port', 'sample': sample},
+                         'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'proposals/s',
                 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -268,9 +327,7 @@ def run_gpu(args):
     n = args.batch
     mode = ops.MLP_TF32 if args.mlp == 'tf32' else ops.MLP_F64
     seed = 0
-    log_l_min = float(np.load(os.path.join(
-        ROOT, 'tests', 'golden', 'cfg2_bound_d30.npz'))['log_l_min']) + \
-        like.norm
+    log_l_min = _log_l_min()
 
     out = stack.cycle(0, n, seed=seed, like_id=like.like_id,
                       like_params=like_params, log_l_min=log_l_min, mode=mode)
@@ -491,16 +548,18 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        per_core = 200000
-        n_cpu, wall = cpu_pass(cores, per_core)
-        n1, wall1 = cpu_pass(1, per_core)
+        kind = cpu_kind()
+        per_core = 100000 if kind == 'reference' else 200000
+        n_cpu, wall = cpu_pass(cores, per_core, kind=kind)
+        n1, wall1 = cpu_pass(1, per_core, kind=kind)
         cpu = {'value': n_cpu / wall, 'unit': 'proposals/s', 'cores': cores,
-               'kind': 'port',
-               'sample': '{} processes x {} raw proposals through the oracle '
-                         'port of the reference loop (NumPy/SciPy, BLAS '
-                         'pinned to 1 thread per process as the reference '
-                         'does)'.format(cores, per_core),
+               'kind': kind,
+               'sample': cpu_sample_text(kind, 1, cores, per_core),
                'single_core_value': n1 / wall1}
+        if kind == 'reference':
+            # cross-check: the oracle port of the same loop on one core
+            np_, wp = cpu_pass(1, 200000, kind='port')
+            cpu['port_single_core_value'] = np_ / wp
 
     line = {
         'metric': 'raw_proposals_per_sec', 'value': value,
@@ -508,16 +567,11 @@ def run_gpu(args):
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_gpu': n,
-                   'emulator_arith': args.mlp,
-                   'l2': 'each step writes {:.0f} MB of proposals (> 126 MB '
-                         'L2); bound parameters ({:.0f} KB) are meant to stay '
-                         'cache-resident'.format(
-                             n * ALGO_BYTES_PER_PROPOSAL / 1e6,
-                             stack.data_d.numel() * 8 / 1e3),
-                   'parallelism': 'proposal batch sharded over {} GPU(s), one '
-                                  'all-gather of 12 doubles per step'.format(
-                                      world)},
+        'config': workload_config(n),
+        'notes': {'emulator_arith': args.mlp,
+                  'parallelism': 'proposal batch sharded over {} GPU(s), one '
+                                 'all-gather of 12 doubles per step'.format(
+                                     world)},
         'roofline': roofline,
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': 'proposals/s',

@@ -50,11 +50,18 @@ struct nb200_session {
   int64_t n_max = 0, cap = 0;
   int64_t n_meta = 0, n_data = 0;
   int like_cap = 0;
-  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, upload = nullptr;
   int32_t* meta_h = nullptr;   // pinned copy of the stack (launch shapes + H2D)
   double* data_h = nullptr;    // pinned
-  int32_t* meta_d = nullptr;
-  double* data_d = nullptr;
+  // the device copy of the stack is double-buffered: a batch's upload runs on
+  // the `upload` stream under the kernels of the batch before it
+  int32_t* meta_buf[2] = {nullptr, nullptr};
+  double* data_buf[2] = {nullptr, nullptr};
+  cudaEvent_t buf_free[2] = {nullptr, nullptr};  // last reader of buffer done
+  cudaEvent_t uploaded = nullptr;
+  int cur = 0;
+  int32_t* meta_d = nullptr;   // == meta_buf[cur]
+  double* data_d = nullptr;    // == data_buf[cur]
   double* points_d = nullptr;  // raw batch, shared by the slots
   double* log_l_d = nullptr;
   uint8_t* code_d = nullptr;
@@ -90,7 +97,14 @@ static void session_free(nb200_session* s) {
   if (s->aux) { cudaStreamSynchronize(s->aux); cudaStreamDestroy(s->aux); }
   cudaFree(s->mat_index_d); cudaFree(s->mat_points_d);
   cudaFreeHost(s->meta_h); cudaFreeHost(s->data_h);
-  cudaFree(s->meta_d); cudaFree(s->data_d); cudaFree(s->points_d);
+  if (s->upload) cudaStreamSynchronize(s->upload);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(s->meta_buf[b]); cudaFree(s->data_buf[b]);
+    if (s->buf_free[b]) cudaEventDestroy(s->buf_free[b]);
+  }
+  if (s->uploaded) cudaEventDestroy(s->uploaded);
+  if (s->upload) cudaStreamDestroy(s->upload);
+  cudaFree(s->points_d);
   cudaFree(s->log_l_d); cudaFree(s->code_d); cudaFree(s->ws);
   if (s->compute) cudaStreamDestroy(s->compute);
   if (s->copy) cudaStreamDestroy(s->copy);
@@ -148,8 +162,16 @@ int nb200_session_create(const int32_t* meta_h, int64_t n_meta,
   NB_S(cudaMallocHost(&s->data_h, sizeof(double) * (n_data + 1)));
   memcpy(s->meta_h, meta_h, sizeof(int32_t) * n_meta);
   if (n_data) memcpy(s->data_h, data_h, sizeof(double) * n_data);
-  NB_S(cudaMalloc(&s->meta_d, sizeof(int32_t) * n_meta));
-  NB_S(cudaMalloc(&s->data_d, sizeof(double) * (n_data + 1)));
+  NB_S(cudaStreamCreateWithFlags(&s->upload, cudaStreamNonBlocking));
+  NB_S(cudaEventCreateWithFlags(&s->uploaded, cudaEventDisableTiming));
+  for (int b = 0; b < 2; ++b) {
+    NB_S(cudaMalloc(&s->meta_buf[b], sizeof(int32_t) * n_meta));
+    NB_S(cudaMalloc(&s->data_buf[b], sizeof(double) * (n_data + 1)));
+    NB_S(cudaEventCreateWithFlags(&s->buf_free[b], cudaEventDisableTiming));
+  }
+  s->cur = 0;
+  s->meta_d = s->meta_buf[0];
+  s->data_d = s->data_buf[0];
   NB_S(cudaMalloc(&s->points_d, sizeof(double) * n_max * d));
   NB_S(cudaMalloc(&s->log_l_d, sizeof(double) * n_max));
   NB_S(cudaMalloc(&s->code_d, (size_t)n_max));
@@ -195,6 +217,7 @@ int nb200_session_set_stack(nb200_session* s, const int32_t* meta_h,
   if (stack_shape_ok(meta_h, n_meta, s->d)) return 1;
   NB_CUDA(cudaSetDevice(s->device));
   // earlier batches may still read the staged copy: drain them first
+  NB_CUDA(cudaStreamSynchronize(s->upload));
   NB_CUDA(cudaStreamSynchronize(s->compute));
   memcpy(s->meta_h, meta_h, sizeof(int32_t) * n_meta);
   if (n_data) memcpy(s->data_h, data_h, sizeof(double) * n_data);
@@ -219,16 +242,33 @@ int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
            "too many likelihood parameters for this session");
   NB_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = s->compute;
-  if (upload_stack) {   // this step's inputs: the serialised bound(s)
-    NB_CUDA(cudaMemcpyAsync(s->meta_d, s->meta_h, sizeof(int32_t) * s->n_meta,
-                            cudaMemcpyHostToDevice, st));
-    NB_CUDA(cudaMemcpyAsync(s->data_d, s->data_h, sizeof(double) * s->n_data,
-                            cudaMemcpyHostToDevice, st));
+  // this step's inputs -- the serialised bound(s) and the likelihood
+  // parameters -- go up on the `upload` stream, into the stack buffer the
+  // batch in flight is NOT reading, so the copies run under its kernels
+  bool uploads = false;
+  if (upload_stack) {
+    const int nxt = s->cur ^ 1;
+    NB_CUDA(cudaStreamWaitEvent(s->upload, s->buf_free[nxt], 0));
+    NB_CUDA(cudaMemcpyAsync(s->meta_buf[nxt], s->meta_h,
+                            sizeof(int32_t) * s->n_meta,
+                            cudaMemcpyHostToDevice, s->upload));
+    NB_CUDA(cudaMemcpyAsync(s->data_buf[nxt], s->data_h,
+                            sizeof(double) * s->n_data,
+                            cudaMemcpyHostToDevice, s->upload));
+    s->cur = nxt;
+    s->meta_d = s->meta_buf[nxt];
+    s->data_d = s->data_buf[nxt];
+    uploads = true;
   }
   if (n_like_params > 0) {
     memcpy(t.like_h, like_params_h, sizeof(double) * n_like_params);
     NB_CUDA(cudaMemcpyAsync(t.like_d, t.like_h, sizeof(double) * n_like_params,
-                            cudaMemcpyHostToDevice, st));
+                            cudaMemcpyHostToDevice, s->upload));
+    uploads = true;
+  }
+  if (uploads) {
+    NB_CUDA(cudaEventRecord(s->uploaded, s->upload));
+    NB_CUDA(cudaStreamWaitEvent(st, s->uploaded, 0));
   }
   double* lse_d = (double*)t.small_d;
   int64_t* cnt_d = (int64_t*)(t.small_d + NB200_N_LSE);
@@ -238,6 +278,7 @@ int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
                        n_like_params, log_l_min, mlp_mode, s->points_d,
                        s->log_l_d, s->code_d, lse_d, cnt_d, s->ws, s->wsb, st);
   if (rc) return rc;
+  NB_CUDA(cudaEventRecord(s->buf_free[s->cur], st));
   t.mode = s->returns;
   if (t.mode == NB200_RETURN_INDEX) {
     rc = nb200_compact_index(like_id >= 0 ? s->log_l_d : nullptr, s->code_d, n,

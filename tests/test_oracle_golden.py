@@ -175,3 +175,26 @@ def test_philox_known_answer():
     u = philox.u01_53(np.array([0xffffffff], np.uint32),
                       np.array([0xffffffff], np.uint32))
     assert u[0] < 1.0 and u[0] == 1 - 2.0**-53
+
+
+def test_reference_arm_objects_reproduce_the_golden_bound(golden):
+    """oracle/ref_arm.py rebuilds reference objects from the exported
+    parameters (for the timed CPU arm): the rebuilt reference bound answers
+    contains() exactly as the reference did when the fixture was made, and
+    its own add_samples loop runs."""
+    from oracle import ref_arm
+    if not ref_arm.available():
+        pytest.skip('oracle/_ref missing (run oracle/make_ref.sh)')
+    from nautilus_b200._pack import flat_to_spec
+    from nautilus_b200 import likelihoods
+    g = golden('cfg2_bound_d30')
+    spec = flat_to_spec(g)
+    bound = ref_arm.reference_bound(spec, np.random.default_rng(0))
+    assert np.array_equal(bound.contains(g['points']), g['contains'])
+    like = likelihoods.Gaussian(30)
+    n, dt, info = ref_arm.run_reference_cycles(
+        spec, like, float(g['log_l_min']) + like.norm, 3000, seed=1,
+        n_batch=100)
+    assert n >= 3000 and info['shell_n'] >= 100 and info['n_like'] == \
+        info['shell_n']
+    assert np.isfinite(info['shell_log_l']) and info['shell_log_v'] < 0
