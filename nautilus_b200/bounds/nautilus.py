@@ -34,14 +34,21 @@ class NautilusBound(_DeviceBound):
             raise NotImplementedError(
                 'periodic parameters (PhaseShift) are outside the scope of '
                 'nautilus_b200.')
-        points = np.asarray(points, dtype=float)
-        log_l = np.asarray(log_l, dtype=float)
+        # `points` / `log_l` may be CUDA tensors (the Sampler keeps every
+        # evaluated point on the device): only the live points and the
+        # training subsets are brought to the host, never the whole set
+        on_device = isinstance(points, torch.Tensor)
+        if not on_device:
+            points = np.asarray(points, dtype=float)
+            log_l = np.asarray(log_l, dtype=float)
         bound = cls()
         bound.n_dim = points.shape[1]
         bound.shift = None
         bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
         bound.rng = np.random.default_rng() if rng is None else rng
         live = points[log_l >= log_l_min]
+        if on_device:
+            live = live.cpu().numpy()
 
         # one neural bound per non-overlapping live-point ellipsoid
         clusters = Union.compute(

@@ -4,6 +4,7 @@ Host-side mirror of ``nautilus/bounds/neural.py``.
 """
 
 import numpy as np
+import torch
 from scipy.stats import rankdata
 
 from .. import ops
@@ -24,15 +25,20 @@ class NeuralBound(_DeviceBound):
         build other bounds in between, on another stream)."""
         bound = cls()
         bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
-        points = np.asarray(points, dtype=float)
-        log_l = np.asarray(log_l, dtype=float)
+        on_device = isinstance(points, torch.Tensor)
+        if not on_device:
+            points = np.asarray(points, dtype=float)
+            log_l = np.asarray(log_l, dtype=float)
         bound.n_dim = points.shape[1]
         if rng is None:
             rng = np.random.default_rng()
 
         live = log_l >= log_l_min
+        live_points = points[live]
+        if on_device:
+            live_points = live_points.cpu().numpy()
         bound.outer_bound = Ellipsoid.compute(
-            points[live], enlarge_per_dim=enlarge_per_dim, rng=rng)
+            live_points, enlarge_per_dim=enlarge_per_dim, rng=rng)
         if n_networks == 0:
             bound.emulator = None
             bound.score_predict_min = 0
@@ -44,6 +50,9 @@ class NeuralBound(_DeviceBound):
         inside = bound.outer_bound.contains(points)
         points, log_l = points[inside], log_l[inside]
         whitened = bound.outer_bound.transform(points)
+        if on_device:        # the training subset (~2 n_live rows) only
+            whitened = whitened.cpu().numpy()
+            log_l = log_l.cpu().numpy()
         live = log_l >= log_l_min
         score = np.empty(len(points))
         score[live] = 0.5 + 0.5 * (rankdata(log_l[live]) - 0.5) / np.sum(live)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._pack import pack_stack
+from ._pack import _Data, pack_record, pack_stack
 
 MLP_F64 = 0
 MLP_TF32 = 1
@@ -110,12 +110,51 @@ class DeviceStack:
     def __init__(self, specs, device='cuda'):
         self.device = torch.device(device)
         self.n_dim = int(specs[0]['n_dim'])
-        meta, data = pack_stack(specs)
-        self.meta_h = np.ascontiguousarray(meta, dtype=np.int32)
-        self.n_bounds = int(self.meta_h[0])
-        self.meta_d = torch.from_numpy(self.meta_h).to(self.device)
-        self.data_d = torch.from_numpy(data).to(self.device)
+        self._data = _Data()
+        self._recs = []
+        self._n_chunks = 0          # data chunks already on the device
+        self._n_data = 0            # doubles already on the device
+        self.data_d = None
         self.ws = Workspace(self.device)
+        for spec in specs:
+            self._recs.append(pack_record(spec, self._data))
+        self._sync()
+
+    def append(self, spec):
+        """Add one more bound at the end of the stack (a new bound was
+        accepted, sampler.py:1023-1039): only ITS parameters are serialised
+        and uploaded, the records already on the device stay where they are
+        (data offsets are absolute and do not move)."""
+        self._recs.append(pack_record(spec, self._data))
+        self._sync()
+
+    def _sync(self):
+        # new data chunks -> the tail of the device array (grow by doubling)
+        new = self._data.chunks[self._n_chunks:]
+        total = self._data.n
+        if self.data_d is None or self.data_d.numel() < max(total, 2):
+            grown = torch.empty(max(2 * total, 1024), dtype=torch.float64,
+                                device=self.device)
+            if self.data_d is not None and self._n_data:
+                grown[:self._n_data] = self.data_d[:self._n_data]
+            self.data_d = grown
+        if new:
+            chunk = torch.from_numpy(np.concatenate(new))
+            self.data_d[self._n_data:self._n_data + chunk.numel()] = chunk.to(
+                self.device)
+        self._n_chunks = len(self._data.chunks)
+        self._n_data = total
+        L = len(self._recs)
+        table = np.zeros(1 + L, dtype=np.int32)
+        table[0] = L
+        off = 1 + L
+        for i, r in enumerate(self._recs):
+            table[1 + i] = off
+            off += len(r)
+        self.meta_h = np.ascontiguousarray(
+            np.concatenate([table] + self._recs), dtype=np.int32)
+        self.n_bounds = L
+        self.meta_d = torch.from_numpy(self.meta_h).to(self.device)
 
     @property
     def _meta_h_ptr(self):
@@ -442,6 +481,15 @@ def loglike(points, like_id, params, code=None):
         _ptr(points), _ptr(code), n, d, like_id, _ptr(params),
         params.numel(), _ptr(out), _stream()))
     return out
+
+
+def top_k(values, k):
+    """Indices (int64 CUDA tensor, unordered) of the k largest entries of the
+    CUDA float64 vector ``values`` -- the live set of sampler.py:1007-1009,
+    1160-1164 without a host argsort."""
+    if k >= values.numel():
+        return torch.arange(values.numel(), device=values.device)
+    return torch.topk(values, int(k), sorted=False).indices
 
 
 def mvee_weights(q_t, max_updates=3000, tol=1e-3):

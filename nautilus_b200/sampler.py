@@ -5,16 +5,28 @@ Drop-in for ``nautilus.Sampler`` (nautilus/sampler.py): same constructor and
 ``log_l``, ``shell_*``), same control flow between shells -- with the
 per-shell proposal -> neural filter -> exclusion -> likelihood ->
 importance-weight cycle executed by the CUDA kernels behind
-``include/nautilus_b200.h``.  The control plane (this file) is host Python
-like the reference's; stored samples are NumPy arrays on the host so user
-code that reads ``sampler.points`` keeps working.
+``include/nautilus_b200.h``.
+
+Where things live.  The control plane (this file) is host Python like the
+reference's.  Every evaluated point stays ON THE DEVICE in one arena (rows,
+``log_l`` and a shell tag per point); ``sampler.points`` / ``sampler.log_l``
+are lazy host views for user code.  With a ``DeviceLikelihood`` one step of
+``add_samples`` is ONE ``nb200_cycle`` call per raw batch (proposal, neural
+filter, exclusion by all later bounds, likelihood, log-sum-exp / counters) and
+ONE 96-byte device->host read; shell sums are merged incrementally
+(``update_shell_info`` never re-reads a shell's ``log_l`` from the host); the
+live set (``f_live``, ``log_v_live``, the threshold of a new bound) and the
+transfer of old points into a new bound are computed on the device.
 
 Differences that are deliberate and documented in DESIGN.md:
   * random numbers come from Philox streams seeded by ``seed`` (the reference
     threads one PCG64 generator through everything), so runs are reproducible
     but not draw-for-draw identical to the reference;
   * ``likelihood`` may be a ``nautilus_b200.likelihoods.DeviceLikelihood``;
-    it is then evaluated on the GPU on unit-cube points;
+    it is then evaluated on the GPU inside the cycle.  On that path a step
+    consumes WHOLE raw batches: ``n_batch`` is the least number of likelihood
+    evaluations of a step, not the exact number (the bookkeeping --
+    ``shell_n``, ``shell_n_sample``, the bound counters -- is exact);
   * HDF5 checkpointing and periodic parameters are out of scope and raise.
 """
 
@@ -30,7 +42,60 @@ from . import ops
 from .bounds import NautilusBound, UnitCube
 from ._device import default_device
 from .likelihoods import DeviceLikelihood
-from .pool import GpuPool, NautilusPool, likelihood_worker
+from .pool import GpuPool, NautilusPool, likelihood_worker, merge_lse
+
+TAG_DROPPED = -1          # arena tag of a point that belongs to no shell
+
+
+class _Arena:
+    """Every evaluated point, on the device: rows f64[n, d], ``log_l`` f64[n]
+    and an int32 tag per point -- the index of its shell, ``TAG_DROPPED``, or
+    ``-(2 + s)`` for a transfer candidate that came out of shell s
+    (sampler.py:1059-1089).  Positions are chronological; nothing is ever
+    moved, shells are told apart by the tag."""
+
+    def __init__(self, n_dim, device, capacity=1 << 15):
+        self.n_dim = n_dim
+        self.device = device
+        self.n = 0
+        self.version = 0
+        self.points = torch.empty((capacity, n_dim), dtype=torch.float64,
+                                  device=device)
+        self.log_l = torch.empty(capacity, dtype=torch.float64, device=device)
+        self.tag = torch.empty(capacity, dtype=torch.int32, device=device)
+
+    def reserve(self, extra):
+        need = self.n + int(extra)
+        cap = self.points.shape[0]
+        if need <= cap:
+            return
+        while cap < need:
+            cap *= 2
+        for name in ('points', 'log_l', 'tag'):
+            old = getattr(self, name)
+            new = torch.empty((cap, ) + tuple(old.shape[1:]), dtype=old.dtype,
+                              device=self.device)
+            new[:self.n] = old[:self.n]
+            setattr(self, name, new)
+
+    def commit(self, k, shell):
+        """k rows were written at [n, n + k): tag them, make them count."""
+        self.tag[self.n:self.n + k] = shell
+        self.n += int(k)
+        self.version += 1
+
+    def append(self, points, log_l, shell):
+        points = torch.as_tensor(np.ascontiguousarray(points),
+                                 device=self.device)
+        k = points.shape[0]
+        self.reserve(k)
+        self.points[self.n:self.n + k] = points
+        self.log_l[self.n:self.n + k] = torch.as_tensor(
+            np.ascontiguousarray(log_l, dtype=np.float64), device=self.device)
+        self.commit(k, shell)
+
+    def view(self):
+        return (self.points[:self.n], self.log_l[:self.n], self.tag[:self.n])
 
 
 class Sampler:
@@ -43,7 +108,7 @@ class Sampler:
                  likelihood_args=[], likelihood_kwargs={}, n_batch=None,
                  n_like_new_bound=None, vectorized=False, pass_dict=None,
                  pool=None, seed=None, blobs_dtype=None, filepath=None,
-                 resume=True, emulator_arith='auto'):
+                 resume=True, emulator_arith='auto', device_cycle=True):
         if filepath is not None:
             raise NotImplementedError(
                 'HDF5 checkpointing is outside the scope of nautilus_b200.')
@@ -52,6 +117,10 @@ class Sampler:
                 'periodic parameters are outside the scope of nautilus_b200.')
 
         self.device_likelihood = isinstance(likelihood, DeviceLikelihood)
+        # device_cycle=False keeps a DeviceLikelihood on the staged path of a
+        # host likelihood (exactly n_batch evaluations per step, one op at a
+        # time); tests use it as the reference semantics
+        self.device_cycle = bool(device_cycle) and self.device_likelihood
         if callable(prior):
             self.prior = partial(prior, *prior_args, **prior_kwargs)
             if n_dim is None:
@@ -135,6 +204,10 @@ class Sampler:
         if n_batch is None:
             s = 1 if self.pool_l is None else self.pool_l.size
             n_batch = -(-100 // s) * s
+            if self.device_cycle:
+                # a step is whole raw GPU batches: ask for
+                # enough points per step to fill one
+                n_batch = max(n_batch, n_live // 2)
         self.n_batch = n_batch
 
         self.rng = np.random.default_rng(seed)
@@ -142,9 +215,6 @@ class Sampler:
         self.n_like = 0
         self.explored = False
         self.bounds = []
-        self.points = []
-        self.log_l = []
-        self.blobs = None
         self.blobs_dtype = blobs_dtype
         self._discard_exploration = False
         self.shell_n = np.zeros(0, dtype=int)
@@ -155,13 +225,20 @@ class Sampler:
         self.shell_log_v = np.zeros(0, dtype=float)
         self.shell_n_sample_exp = np.zeros(0, dtype=int)
         self.shell_end_exp = np.zeros(0, dtype=int)
-        self.points_t = np.zeros((0, self.n_dim))
-        self.shell_t = np.zeros(0, dtype=int)
-        self.log_l_t = np.zeros(0)
-        self.blobs_t = None
         self.filepath = None
-        self._stack = None       # all bounds serialised on the device
+        self._arena = None          # created with the first bound
+        self._blobs_all = None      # host, aligned with arena positions
+        self._host_cache = (None, None)
+        self._sums = []             # per shell: running (m, s1, s2) or None
+        self._explore_end = 0       # arena position where exploration ended
+        self._t_pos = np.zeros(0, dtype=np.int64)   # transfer candidates:
+        self._t_shell = np.zeros(0, dtype=int)      # arena position, donor
+        self._p_shell = {}          # per bound: (in-shell, raw) so far
+        self._stack = None          # all bounds serialised on the device
+        self._stack_len = 0
         self._like_params = None
+        self._cycle_buf = None
+        self.cycle_stats = dict(calls=0, raw=0, d2h_bytes=0)
 
     # ------------------------------------------------------------------
     # scheduler (sampler.py:373-505)
@@ -195,8 +272,9 @@ class Sampler:
                     self.add_bound(verbose=verbose)
                     self.n_update_iter = 0
                     self.n_like_iter = 0
+                n_like_before = self.n_like
                 self.n_update_iter += self.add_samples(-1, verbose=verbose)
-                self.n_like_iter += self.n_batch
+                self.n_like_iter += self.n_like - n_like_before
                 if self.f_live <= f_live:
                     self._finish_exploration(discard_exploration)
             elif np.any(self.shell_n < n_shell):
@@ -216,16 +294,30 @@ class Sampler:
     def _finish_exploration(self, discard_exploration):
         """Drop empty shells and freeze the exploration bookkeeping
         (sampler.py:455-480)."""
-        for shell in np.flatnonzero(self.shell_n == 0)[::-1]:
-            del self.bounds[shell], self.points[shell], self.log_l[shell]
-            if self.blobs is not None:
-                del self.blobs[shell]
+        _, _, tag = self._arena.view()
+        # whatever is still waiting for a transfer belongs to no shell
+        tag[tag <= -2] = TAG_DROPPED
+        self._t_pos = np.zeros(0, dtype=np.int64)
+        self._t_shell = np.zeros(0, dtype=int)
+        empty = np.flatnonzero(self.shell_n == 0)
+        if len(empty):
+            keep = np.setdiff1d(np.arange(len(self.bounds)), empty)
+            remap = np.full(len(self.bounds), TAG_DROPPED, dtype=np.int32)
+            remap[keep] = np.arange(len(keep), dtype=np.int32)
+            lut = torch.as_tensor(remap, device=tag.device)
+            inside = tag >= 0
+            tag[inside] = lut[tag[inside].long()]
+            self.bounds = [self.bounds[i] for i in keep]
+            self._sums = [self._sums[i] for i in keep]
             for key in ('shell_n', 'shell_n_sample', 'shell_n_eff',
                         'shell_log_l_min', 'shell_log_l', 'shell_log_v'):
-                setattr(self, key, np.delete(getattr(self, key), shell))
+                setattr(self, key, getattr(self, key)[keep])
             self._stack = None
+        self._arena.version += 1
+        self._p_shell = {}
         self.shell_n_sample_exp = np.copy(self.shell_n_sample)
-        self.shell_end_exp = np.array([len(p) for p in self.points])
+        self.shell_end_exp = np.copy(self.shell_n)
+        self._explore_end = self._arena.n
         self.explored = True
         self.discard_exploration = discard_exploration
 
@@ -238,33 +330,89 @@ class Sampler:
         if not isinstance(value, bool):
             raise ValueError("'discard_exploration' must be a bool.")
         self._discard_exploration = value
-        for index in range(len(self.log_l)):
+        for index in range(len(self.bounds)):
+            self._sums[index] = None
             self.update_shell_info(index)
+
+    # ------------------------------------------------------------------
+    # stored points: device arena, lazy host views
+    # ------------------------------------------------------------------
+    def _discarding(self):
+        return bool(self._discard_exploration and self.explored)
+
+    def _start(self):
+        """First arena position that counts (discard_exploration drops what
+        was drawn while exploring, sampler.py:917-923)."""
+        return self._explore_end if self._discarding() else 0
+
+    def _host(self):
+        """(points, log_l, tag) of the arena as NumPy arrays (cached until
+        the arena changes)."""
+        if self._arena is None:
+            return (np.zeros((0, self.n_dim)), np.zeros(0),
+                    np.zeros(0, dtype=np.int32))
+        version, cached = self._host_cache
+        if version != self._arena.version:
+            pts, ll, tag = self._arena.view()
+            cached = (pts.cpu().numpy(), ll.cpu().numpy(), tag.cpu().numpy())
+            self._host_cache = (self._arena.version, cached)
+        return cached
+
+    def _by_shell(self, values, tag):
+        return [values[tag == i] for i in range(len(self.bounds))]
+
+    @property
+    def points(self):
+        """List (one entry per shell) of the stored points, as in the
+        reference; materialised from the device arena on demand."""
+        pts, _, tag = self._host()
+        return self._by_shell(pts, tag)
+
+    @property
+    def log_l(self):
+        _, ll, tag = self._host()
+        return self._by_shell(ll, tag)
+
+    @property
+    def blobs(self):
+        if self._blobs_all is None:
+            return None
+        _, _, tag = self._host()
+        return self._by_shell(self._blobs_all[:len(tag)], tag)
+
+    @property
+    def points_t(self):
+        return self._host()[0][self._t_pos]
+
+    @property
+    def log_l_t(self):
+        return self._host()[1][self._t_pos]
+
+    @property
+    def shell_t(self):
+        return self._t_shell
 
     # ------------------------------------------------------------------
     # read-outs (sampler.py:541-730, 1147-1190)
     # ------------------------------------------------------------------
-    def _starts(self):
-        if self._discard_exploration and self.explored:
-            return self.shell_end_exp
-        return np.zeros(len(self.points), dtype=int)
-
     def posterior(self, return_as_dict=None, equal_weight=False,
                   equal_weight_boost=1.0, return_blobs=False):
         """Posterior sample: points, log weights, log likelihoods[, blobs]."""
         if return_as_dict is None:
             return_as_dict = bool(callable(self.prior) and self.pass_dict)
-        start = self._starts()
-        points = np.concatenate([p[s:] for p, s in zip(self.points, start)])
-        log_l = np.concatenate([v[s:] for v, s in zip(self.log_l, start)])
+        pts, ll, tag = self._host()
+        use = np.flatnonzero((tag >= 0) &
+                             (np.arange(len(tag)) >= self._start()))
+        # shell by shell, chronological inside a shell (the reference's order)
+        use = use[np.argsort(tag[use], kind='stable')]
+        points, log_l = pts[use], ll[use]
         log_w = np.repeat(self.shell_log_v - np.log(np.maximum(
             self.shell_n, 1)), self.shell_n) + log_l
         blobs = None
         if return_blobs:
-            if self.blobs is None:
+            if self._blobs_all is None:
                 raise ValueError('No blobs have been calculated.')
-            blobs = np.concatenate(
-                [b[s:] for b, s in zip(self.blobs, start)])
+            blobs = self._blobs_all[use]
 
         if equal_weight:
             expect = np.exp(log_w - np.amax(log_w)) * equal_weight_boost
@@ -323,12 +471,21 @@ class Sampler:
         return np.exp(2 * logsumexp(log_z) -
                       2 * logsumexp(log_z - 0.5 * np.log(eff)))
 
-    def _live_weights(self):
-        log_v = np.repeat(self.shell_log_v - np.log(np.maximum(
-            self.shell_n, 1)), self.shell_n)
-        log_l = np.concatenate(self.log_l)
-        order = np.argsort(log_l)[-self.n_live:]
-        return log_v, log_l, order
+    def _live_set(self):
+        """Device side of ``f_live`` / ``log_v_live`` / the threshold of a new
+        bound (sampler.py:1007-1009, 1146-1190): over the m stored points
+        that belong to a shell, CUDA tensors (position int64[m], log volume
+        weight f64[m], log_l f64[m], live int64[<= n_live]) with ``live`` the
+        indices of the n_live points of highest likelihood (device top-k)."""
+        _, ll, tag = self._arena.view()
+        pos = torch.nonzero(tag >= 0).squeeze(1)
+        per_shell = torch.as_tensor(
+            self.shell_log_v - np.log(np.maximum(self.shell_n, 1)),
+            device=ll.device)
+        log_l = ll[pos]
+        log_v = per_shell[tag[pos].long()]
+        live = ops.top_k(log_l, min(self.n_live, log_l.numel()))
+        return pos, log_v, log_l, live
 
     @property
     def f_live(self):
@@ -337,59 +494,74 @@ class Sampler:
             return None
         if np.sum(self.shell_n) == 0:
             return 1.0
-        log_v, log_l, live = self._live_weights()
+        _, log_v, log_l, live = self._live_set()
         log_w = log_v + log_l
-        return np.exp(logsumexp(log_w[live]) - logsumexp(log_w))
+        return float(torch.exp(torch.logsumexp(log_w[live], 0) -
+                               torch.logsumexp(log_w, 0)).item())
 
     @property
     def log_v_live(self):
         """log volume of the live set (sampler.py:1171-1190)."""
         if len(self.bounds) == 0:
             return 1.0
-        log_v, _, live = self._live_weights()
-        return logsumexp(log_v[live])
+        _, log_v, _, live = self._live_set()
+        return float(torch.logsumexp(log_v[live], 0).item())
 
     # ------------------------------------------------------------------
     # device plumbing
     # ------------------------------------------------------------------
     def _device_stack(self):
+        """All bounds serialised on the device; a new bound is APPENDED (only
+        its own parameters are packed and uploaded)."""
         if self._stack is None:
             self._stack = ops.DeviceStack([b.spec() for b in self.bounds],
                                           device=default_device())
+            self._stack_len = len(self.bounds)
+        while self._stack_len < len(self.bounds):
+            self._stack.append(self.bounds[self._stack_len].spec())
+            self._stack_len += 1
         return self._stack
 
     def _contains(self, index, points_dev, mask=None):
         return self._device_stack().contains(index, points_dev, mask=mask,
                                              mode=self.mlp_mode)
 
-    def shell_association(self, points, n_max=None):
-        """Index of the last bound (< n_max) containing each point
-        (sampler.py:1192-1221)."""
-        if n_max is None:
-            n_max = len(self.bounds)
-        dev = default_device()
-        pts = torch.as_tensor(np.ascontiguousarray(points), device=dev)
-        shell = torch.full((len(points), ), -1, dtype=torch.int64, device=dev)
+    def _association(self, pts, n_max):
+        """Device tensor: index of the last bound (< n_max) containing each
+        row of the CUDA tensor ``pts`` (sampler.py:1213-1221)."""
+        shell = torch.full((pts.shape[0], ), -1, dtype=torch.int64,
+                           device=pts.device)
         for i in range(n_max - 1, -1, -1):
             undecided = shell < 0
             if not bool(undecided.any()):
                 break
             inside = self._contains(i, pts, mask=undecided)
             shell[undecided & inside] = i
-        return shell.cpu().numpy()
+        return shell
+
+    def shell_association(self, points, n_max=None):
+        """Index of the last bound (< n_max) containing each point
+        (sampler.py:1192-1221)."""
+        if n_max is None:
+            n_max = len(self.bounds)
+        pts = torch.as_tensor(np.ascontiguousarray(points),
+                              device=default_device())
+        return self._association(pts, n_max).cpu().numpy()
 
     def shell_bound_occupation(self, fractional=True):
         """m[i, j] = how many points of shell i lie in bound j
         (sampler.py:1223-1251)."""
         n = len(self.bounds)
         m = np.zeros((n, n), dtype=int)
-        dev = default_device()
-        for i, points in enumerate(self.points):
-            if len(points) == 0:
-                continue
-            pts = torch.as_tensor(np.ascontiguousarray(points), device=dev)
+        pts, _, tag = self._arena.view()
+        pos = torch.nonzero(tag >= 0).squeeze(1)
+        if pos.numel():
+            rows = pts[pos].contiguous()
+            shell = tag[pos].long()
             for j in range(n):
-                m[i, j] = int(self._contains(j, pts).sum().item())
+                inside = self._contains(j, rows)
+                m[:, j] = torch.bincount(shell[inside],
+                                         minlength=n).cpu().numpy()
         if fractional:
             # every stored point of shell i lies in bound i: the diagonal
             # counts the points (sampler.py:1248-1250)
@@ -397,7 +569,156 @@ class Sampler:
         return m
 
     # ------------------------------------------------------------------
-    # the cycle (sampler.py:751-943, 1093-1144)
+    # the cycle on the device (sampler.py:751-943, 1093-1144 in one call)
+    # ------------------------------------------------------------------
+    def _raw_batch_size(self, index, want):
+        """Raw proposals to draw so that about ``want`` end up in the shell,
+        from the shell's own acceptance so far."""
+        got, raw = self._p_shell.get(index, (0, 0))
+        if raw > 0:
+            p = max(got, 1) / raw
+        else:
+            bound = self.bounds[index]
+            p = 1.0
+            if isinstance(bound, NautilusBound) and bound.n_sample > 0 and \
+                    bound.outer_bound.n_sample > 0:
+                p = ((1 - bound.outer_bound.n_reject /
+                      bound.outer_bound.n_sample) *
+                     (1 - bound.n_reject / bound.n_sample))
+            if index + 1 < len(self.bounds):
+                p *= 0.5
+        n_raw = int(1.15 * want / max(p, 1e-5)) + 256
+        return int(min(max(n_raw, 4096), 1 << 22))
+
+    def _cycle_buffers(self, n_raw):
+        buf = self._cycle_buf
+        if buf is None or buf['code'].numel() < n_raw:
+            dev = default_device()
+            cap = max(n_raw, 1 << 16)
+            buf = dict(
+                points=torch.empty((cap, self.n_dim), dtype=torch.float64,
+                                   device=dev),
+                log_l=torch.empty(cap, dtype=torch.float64, device=dev),
+                code=torch.empty(cap, dtype=torch.uint8, device=dev),
+                lse=torch.empty(ops.N_LSE, dtype=torch.float64, device=dev),
+                counters=torch.empty(ops.N_CNT, dtype=torch.int64,
+                                     device=dev))
+            self._cycle_buf = buf
+        return buf
+
+    def _run_cycle(self, index, n_raw, offset, out_points, out_log_l):
+        """ONE nb200_cycle call: raw proposals [offset, offset + n_raw) of
+        bound ``index`` -> neural filter -> exclusion by every later bound ->
+        likelihood -> sums; the in-shell rows are compacted straight into
+        ``out_points`` / ``out_log_l`` (views of the arena).  Returns the
+        CUDA tensors (counters i64[8], lse f64[4]); nothing is synchronised.
+        """
+        stack = self._device_stack()
+        if self._like_params is None:
+            self._like_params = self.likelihood.device_params(stack.device)
+        bound = self.bounds[index]
+        buf = self._cycle_buffers(n_raw)
+        out = stack.cycle(
+            index, n_raw, later=(index + 1, len(self.bounds) - index - 1),
+            seed=bound.stream.seed, offset=offset,
+            stream_id=bound.stream.stream_id,
+            like_id=self.likelihood.like_id, like_params=self._like_params,
+            log_l_min=float(self.shell_log_l_min[index]), mode=self.mlp_mode,
+            out=buf)
+        stack.compact(out['points'][:n_raw], out['log_l'][:n_raw],
+                      out['code'][:n_raw], out_points=out_points,
+                      out_log_l=out_log_l)
+        return out['counters'], out['lse']
+
+    def _add_samples_device(self, index):
+        """``add_samples`` with a device likelihood: whole raw batches
+        through ``nb200_cycle`` until at least ``n_batch`` new points are in
+        the shell.  Per raw batch the host reads 96 bytes."""
+        bound = self.bounds[index]
+        arena = self._arena
+        last = index == len(self.bounds) - 1
+        n_new, n_update = 0, 0
+        while n_new < self.n_batch:
+            n_raw = self._raw_batch_size(index, self.n_batch - n_new)
+            offset = bound.stream.take(n_raw)
+            arena.reserve(n_raw)
+            a0 = arena.n
+            counters, lse = self._run_cycle(
+                index, n_raw, offset, arena.points[a0:a0 + n_raw],
+                arena.log_l[a0:a0 + n_raw])
+            # the one device->host read of the batch: 8 counters + the
+            # log-sum-exp triple
+            small = torch.cat([counters.double(), lse]).cpu().numpy()
+            self.cycle_stats['calls'] += 1
+            self.cycle_stats['raw'] += n_raw
+            self.cycle_stats['d2h_bytes'] += small.nbytes
+            cnt = small[:ops.N_CNT].round().astype(np.int64)
+            triple = tuple(small[ops.N_CNT:ops.N_CNT + 3])
+            k = int(cnt[ops.CNT_IN_SHELL])
+            arena.commit(k, index)
+            got, raw = self._p_shell.get(index, (0, 0))
+            self._p_shell[index] = (got + k, raw + n_raw)
+            # the bound's own counters (union.py:322-323, nautilus.py:221-222)
+            if isinstance(bound, NautilusBound):
+                rej_u = int(cnt[ops.CNT_CUBE_REJECT] +
+                            cnt[ops.CNT_OVERLAP_REJECT])
+                bound.outer_bound.n_sample += n_raw
+                bound.outer_bound.n_reject += rej_u
+                bound.n_sample += n_raw - rej_u
+                bound.n_reject += int(cnt[ops.CNT_NN_REJECT])
+            # draws of the bound this batch consumed (sampler.py:793, 1133)
+            self.shell_n_sample[index] += k + int(cnt[ops.CNT_EXCLUDED])
+
+            kept, upd = k, int(cnt[ops.CNT_UPDATE])
+            if last and len(self._t_pos) > 0 and k > 0:
+                kept, upd = self._swap_in_transfers(index, a0, k)
+                self._sums[index] = None        # the set changed: re-reduce
+            elif self._sums[index] is not None:
+                self._sums[index] = merge_lse([self._sums[index], triple])
+                self.shell_n[index] += k
+            self.n_like += kept
+            n_new += kept
+            n_update += upd
+            self.update_shell_info(index)
+        return n_update
+
+    def _swap_in_transfers(self, index, a0, k):
+        """Exploration only (sampler.py:803-819): fresh draws that fall into
+        an earlier shell s are replaced, one for one, by transfer candidates
+        that came out of shell s.  Works on arena tags; returns (fresh points
+        kept, how many of them reach the shell's threshold)."""
+        arena = self._arena
+        fresh = arena.points[a0:a0 + k]
+        shell_p = self._association(fresh, len(self.bounds) - 1).cpu().numpy()
+        drop, take = [], []
+        for s in range(len(self.bounds) - 1):
+            donors = np.flatnonzero(self._t_shell == s)
+            cand = np.flatnonzero(shell_p == s)
+            n = min(len(donors), len(cand))
+            if n > 0:
+                chosen = self.rng.choice(donors, size=n, replace=False)
+                take.append(chosen)
+                self._t_shell[chosen] = -1
+                drop.append(self.rng.choice(cand, size=n, replace=False))
+        if take:
+            take = np.concatenate(take)
+            drop = np.concatenate(drop)
+            dev = arena.tag.device
+            arena.tag[torch.as_tensor(self._t_pos[take], device=dev)] = index
+            arena.tag[torch.as_tensor(a0 + drop, device=dev)] = TAG_DROPPED
+            arena.version += 1
+            still = self._t_shell >= 0
+            self._t_pos = self._t_pos[still]
+            self._t_shell = self._t_shell[still]
+        fresh_in = arena.tag[a0:a0 + k] == index
+        kept = int(fresh_in.sum().item())
+        upd = int((fresh_in & (arena.log_l[a0:a0 + k] >=
+                               float(self.shell_log_l_min[index]))
+                   ).sum().item())
+        return kept, upd
+
+    # ------------------------------------------------------------------
+    # the cycle with a host likelihood (sampler.py:751-908)
     # ------------------------------------------------------------------
     def sample_shell(self, index, shell_t=None):
         """Exactly ``n_batch`` points uniform in shell ``index``
@@ -421,12 +742,12 @@ class Sampler:
             alive = torch.ones(want, dtype=torch.bool, device=pts.device)
             for later in range(index + 1, len(self.bounds)):
                 alive &= ~self._contains(later, pts, mask=alive)
-            pts = pts[alive].cpu().numpy()
+            pts = pts[alive].contiguous()
 
-            replace = np.zeros(len(pts), dtype=bool)
+            replace = np.zeros(pts.shape[0], dtype=bool)
             if shell_t is not None and len(shell_t) > 0 and len(pts) > 0:
-                shell_p = self.shell_association(pts,
-                                                 n_max=len(self.bounds) - 1)
+                shell_p = self._association(
+                    pts, len(self.bounds) - 1).cpu().numpy()
                 for shell in range(len(self.bounds) - 1):
                     donors = np.flatnonzero(shell_t == shell)
                     fresh = np.flatnonzero(shell_p == shell)
@@ -437,7 +758,7 @@ class Sampler:
                         shell_t[idx_t] = -1
                         replace[self.rng.choice(fresh, size=n,
                                                 replace=False)] = True
-            pts = pts[~replace]
+            pts = pts.cpu().numpy()[~replace]
             if len(pts) > 0:
                 kept.append(pts)
                 n_have += len(pts)
@@ -493,17 +814,61 @@ class Sampler:
         self.n_like += len(log_l)
         return log_l, blobs
 
+    def _add_samples_host(self, index):
+        """``add_samples`` with a Python likelihood: exactly ``n_batch``
+        evaluations (sampler.py:1093-1144); the new points are uploaded into
+        the arena."""
+        arena = self._arena
+        last = index == len(self.bounds) - 1
+        if last and len(self._t_pos) > 0:
+            shell_t = self._t_shell.copy()
+            points, n_bound, idx_t = self.sample_shell(index, shell_t)
+            assert len(points) + len(idx_t) == n_bound
+            if len(idx_t) > 0:
+                arena.tag[torch.as_tensor(self._t_pos[idx_t],
+                                          device=arena.device)] = index
+                arena.version += 1
+                still = np.ones(len(self._t_pos), dtype=bool)
+                still[idx_t] = False
+                self._t_pos = self._t_pos[still]
+                self._t_shell = self._t_shell[still]
+        else:
+            points, n_bound = self.sample_shell(index)
+
+        self.shell_n_sample[index] += n_bound
+        log_l, blobs = self.evaluate_likelihood(points)
+        if blobs is not None:
+            blobs = np.atleast_1d(blobs)
+            if self._blobs_all is None:
+                self._blobs_all = np.zeros(arena.n, dtype=blobs.dtype)
+            self._blobs_all = np.concatenate([self._blobs_all, blobs])
+        arena.append(points, log_l, index)
+        self._sums[index] = None
+        self.update_shell_info(index)
+        return int(np.sum(log_l >= self.shell_log_l_min[index]))
+
+    # ------------------------------------------------------------------
     def update_shell_info(self, index):
-        """Volume, mean likelihood and ESS of one shell from its stored log_l
-        (sampler.py:910-943); the sums run on the GPU (nb200_stats)."""
+        """Volume, mean likelihood and ESS of one shell (sampler.py:910-943).
+
+        The log-sum-exp triple of a shell is the running merge of the triples
+        ``nb200_cycle`` returns batch by batch (``self._sums``, with
+        ``shell_n`` counted along); when the shell's membership changed in
+        another way (transfers, discard_exploration, a host likelihood) it is
+        re-reduced on the device from the arena (``nb200_stats``) -- the
+        shell's ``log_l`` is never uploaded again."""
         n_sample = self.shell_n_sample[index]
-        start = 0
-        if self._discard_exploration and self.explored:
-            start = self.shell_end_exp[index]
+        if self._discarding():
             n_sample = n_sample - self.shell_n_sample_exp[index]
-        log_l = self.log_l[index][start:]
-        n = len(log_l)
-        self.shell_n[index] = n
+        if self._sums[index] is None:
+            _, ll, tag = self._arena.view()
+            start = self._start()
+            code = (tag[start:] == index).to(torch.uint8) * ops.CODE_IN_SHELL
+            lse, cnt = ops.stats(ll[start:], code=code)
+            small = torch.cat([cnt.double(), lse]).cpu().numpy()
+            self.shell_n[index] = int(round(small[ops.CNT_IN_SHELL]))
+            self._sums[index] = tuple(small[ops.N_CNT:ops.N_CNT + 3])
+        n = int(self.shell_n[index])
         if n == 0:
             self.shell_log_v[index] = -np.inf
             self.shell_log_l[index] = np.nan
@@ -511,9 +876,7 @@ class Sampler:
             return
         self.shell_log_v[index] = self.bounds[index].log_v + np.log(
             n / n_sample)
-        lse, _ = ops.stats(torch.as_tensor(np.ascontiguousarray(log_l),
-                                           device=default_device()))
-        m, s1, s2 = lse.cpu().numpy()[:3]
+        m, s1, s2 = self._sums[index]
         if s1 > 0:
             self.shell_log_l[index] = m + np.log(s1) - np.log(n)
             self.shell_n_eff[index] = s1 * s1 / s2
@@ -522,38 +885,15 @@ class Sampler:
             self.shell_n_eff[index] = n
 
     def add_samples(self, shell, verbose=False):
-        """One batch of ``n_batch`` likelihood evaluations in ``shell``
-        (sampler.py:1093-1144).  Returns how many reach the shell's likelihood
-        threshold."""
+        """One batch of likelihood evaluations in ``shell``
+        (sampler.py:1093-1144).  Returns how many reach the shell's
+        likelihood threshold."""
         if verbose:
             self.print_status('Sampling', end='\r')
-        if shell == -1 and len(self.shell_t) > 0:
-            points, n_bound, idx_t = self.sample_shell(-1, self.shell_t)
-            assert len(points) + len(idx_t) == n_bound
-            if len(idx_t) > 0:
-                self.points[-1] = np.concatenate(
-                    (self.points[-1], self.points_t[idx_t]))
-                self.log_l[-1] = np.concatenate(
-                    (self.log_l[-1], self.log_l_t[idx_t]))
-                if self.blobs is not None:
-                    self.blobs[-1] = np.concatenate(
-                        (self.blobs[-1], self.blobs_t[idx_t]))
-        else:
-            points, n_bound = self.sample_shell(shell)
-        if verbose:
-            self.print_status('Computing', end='\r')
-
-        self.shell_n_sample[shell] += n_bound
-        log_l, blobs = self.evaluate_likelihood(points)
-        self.points[shell] = np.append(self.points[shell], points, axis=0)
-        self.log_l[shell] = np.append(self.log_l[shell], log_l, axis=0)
-        if blobs is not None:
-            if self.blobs is None:
-                self.blobs = [blobs]
-            else:
-                self.blobs[shell] = np.append(self.blobs[shell], blobs, axis=0)
-        self.update_shell_info(shell)
-        return int(np.sum(log_l >= self.shell_log_l_min[shell]))
+        index = shell % len(self.bounds)
+        if self.device_cycle and not isinstance(self.pool_s, GpuPool):
+            return self._add_samples_device(index)
+        return self._add_samples_host(index)
 
     # ------------------------------------------------------------------
     # new bounds (sampler.py:982-1091)
@@ -563,23 +903,28 @@ class Sampler:
         if len(self.bounds) == 0:
             log_l_min = -np.inf
             new_bound = UnitCube.compute(self.n_dim, rng=self.rng)
+            self._arena = _Arena(self.n_dim, default_device())
         else:
             if verbose:
                 self.print_status('Bounding', end='\r')
-            log_l = np.concatenate(self.log_l)
-            order = np.argsort(log_l)
-            points = np.concatenate(self.points)[order]
-            log_l = log_l[order]
-            log_l_min = log_l[-self.n_live]
-            # step over a likelihood plateau if enough points lie above it
+            # live threshold and plateau rule (sampler.py:1007-1016), on the
+            # device: the n_live-th largest stored log_l
+            pts, _, _ = self._arena.view()
+            pos, log_v, log_l, live = self._live_set()
+            log_l_min = float(log_l[live].min().item())
             above = log_l > log_l_min
-            if (np.sum(log_l == log_l_min) > 1 and
-                    np.sum(above) >= self.n_points_min):
-                log_l_min = np.amin(log_l[above])
+            if int((log_l == log_l_min).sum().item()) > 1 and \
+                    int(above.sum().item()) >= self.n_points_min:
+                log_l_min = float(log_l[above].min().item())
             new_bound = None
-            if not np.all(log_l >= log_l_min):
+            if not bool((log_l >= log_l_min).all().item()):
+                # rows ordered by likelihood, as the reference hands them
+                # over; they stay on the device (NautilusBound.compute pulls
+                # the live points and the training subsets only)
+                order = torch.argsort(log_l, stable=True)
                 cand = NautilusBound.compute(
-                    points, log_l, log_l_min, self.log_v_live,
+                    pts[pos[order]], log_l[order], log_l_min,
+                    float(torch.logsumexp(log_v[live], 0).item()),
                     enlarge_per_dim=self.enlarge_per_dim,
                     n_points_min=self.n_points_min,
                     split_threshold=self.split_threshold, periodic=None,
@@ -594,43 +939,40 @@ class Sampler:
                 return False
 
         self.bounds.append(new_bound)
-        self._stack = None
         self.shell_n = np.append(self.shell_n, 0)
         self.shell_n_sample = np.append(self.shell_n_sample, 0)
         self.shell_n_eff = np.append(self.shell_n_eff, 0)
         self.shell_log_l = np.append(self.shell_log_l, np.nan)
         self.shell_log_v = np.append(self.shell_log_v, np.nan)
         self.shell_log_l_min = np.append(self.shell_log_l_min, log_l_min)
-        self.points.append(np.zeros((0, self.n_dim)))
-        self.log_l.append(np.zeros(0))
-        if self.blobs is not None:
-            self.blobs.append(np.zeros(self.blobs[-1][:0].shape,
-                                       dtype=self.blobs_dtype))
+        self._sums.append((-np.inf, 0.0, 0.0))
 
         # earlier points inside the new bound become transfer candidates
+        # (sampler.py:1059-1089), found with ONE contains() over all stored
+        # points on the device; candidates of the previous bound that were
+        # never used belong to no shell any more
         if len(self.bounds) > 1:
-            moved = dict(shell=[], points=[], log_l=[], blobs=[])
+            pts, _, tag = self._arena.view()
+            tag[tag <= -2] = TAG_DROPPED
+            pos = torch.nonzero(tag >= 0).squeeze(1)
+            gone = np.zeros(len(self.bounds), dtype=int)
+            self._t_pos = np.zeros(0, dtype=np.int64)
+            self._t_shell = np.zeros(0, dtype=int)
+            if pos.numel():
+                inside = self._contains(len(self.bounds) - 1,
+                                        pts[pos].contiguous())
+                moved = pos[inside]
+                donors = tag[moved].long()
+                tag[moved] = (-2 - donors).to(torch.int32)
+                gone = torch.bincount(
+                    donors, minlength=len(self.bounds)).cpu().numpy()
+                self._t_pos = moved.cpu().numpy()
+                self._t_shell = donors.cpu().numpy().astype(int)
+            self._arena.version += 1
             for shell in range(len(self.bounds) - 1):
-                if len(self.points[shell]):
-                    inside = self.bounds[-1].contains(
-                        self.points[shell], mode=self.mlp_mode)
-                else:
-                    inside = np.zeros(0, dtype=bool)
-                moved['shell'].append(np.repeat(shell, np.sum(inside)))
-                moved['points'].append(self.points[shell][inside])
-                moved['log_l'].append(self.log_l[shell][inside])
-                self.points[shell] = self.points[shell][~inside]
-                self.log_l[shell] = self.log_l[shell][~inside]
-                if self.blobs is not None:
-                    moved['blobs'].append(self.blobs[shell][inside])
-                    self.blobs[shell] = self.blobs[shell][~inside]
-                self.shell_n[shell] -= np.sum(inside)
-                self.update_shell_info(shell)
-            self.shell_t = np.concatenate(moved['shell'])
-            self.points_t = np.concatenate(moved['points'])
-            self.log_l_t = np.concatenate(moved['log_l'])
-            if self.blobs is not None:
-                self.blobs_t = np.concatenate(moved['blobs'])
+                if gone[shell] > 0:
+                    self._sums[shell] = None
+                    self.update_shell_info(shell)
         return True
 
     # ------------------------------------------------------------------

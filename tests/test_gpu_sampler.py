@@ -43,8 +43,11 @@ def test_sampler_accuracy():
 
 
 def test_sampler_device_likelihood_matches_host_likelihood():
+    # device_cycle=False: the device likelihood evaluated op by op with the
+    # step semantics of a host likelihood (exactly n_batch evaluations)
     like = likelihoods.Gaussian(3, mu=[0.4, 0.5, 0.6], sigma=0.1)
-    s_dev = Sampler(lambda x: x, like, n_dim=3, n_live=500, seed=1)
+    s_dev = Sampler(lambda x: x, like, n_dim=3, n_live=500, seed=1,
+                    device_cycle=False)
     s_dev.run(n_eff=3000)
     assert abs(s_dev.log_z - like.log_z_true) < 0.05
     s_host = Sampler(lambda x: x, like.__call__, n_dim=3, n_live=500,
@@ -53,6 +56,87 @@ def test_sampler_device_likelihood_matches_host_likelihood():
     # same seed, same arithmetic for log L up to summation order
     assert abs(s_host.log_z - s_dev.log_z) < 1e-9
     assert s_host.n_like == s_dev.n_like
+
+
+class _StagedCycleSampler(Sampler):
+    """The device cycle rebuilt from separate operations: raw draws, neural
+    filter, one contains() per later bound, likelihood, and the ORACLE's
+    reductions on the host -- everything nb200_cycle fuses into one call."""
+
+    def _run_cycle(self, index, n_raw, offset, out_points, out_log_l):
+        from nautilus_b200 import ops
+        from oracle import nautilus_oracle as orc
+        stack = self._device_stack()
+        bound = self.bounds[index]
+        pts, code, _ = stack.propose(index, n_raw, seed=bound.stream.seed,
+                                     offset=offset,
+                                     stream_id=bound.stream.stream_id)
+        code = code.clone()
+        alive = code == ops.CODE_IN_SHELL
+        if index > 0 and len(bound.neural_bounds) > 0:
+            nn = stack.contains(index, pts, which=2, mask=alive,
+                                mode=self.mlp_mode)
+            code[alive & ~nn] = ops.CODE_NN_REJECT
+            alive = alive & nn
+        for later in range(index + 1, len(self.bounds)):
+            # every later bound is consulted (no short-circuit)
+            inside = stack.contains(later, pts, mask=alive,
+                                    mode=self.mlp_mode)
+            code[alive & inside] = ops.CODE_EXCLUDED
+        sel = code == ops.CODE_IN_SHELL
+        par = self.likelihood.device_params(pts.device)
+        log_l = ops.loglike(pts, self.likelihood.like_id, par, code=code)
+        k = int(sel.sum().item())
+        out_points[:k] = pts[sel]
+        out_log_l[:k] = log_l[sel]
+        ll = log_l[sel].cpu().numpy()
+        cnt = np.zeros(ops.N_CNT, dtype=np.int64)
+        cnt[ops.CNT_RAW] = n_raw
+        c = code.cpu().numpy()
+        for q in range(4):
+            cnt[1 + q] = np.sum(c == q)
+        cnt[ops.CNT_IN_SHELL] = k
+        cnt[ops.CNT_UPDATE] = np.sum(ll >= self.shell_log_l_min[index])
+        m, s1, s2 = orc.lse_triple(ll)
+        return (torch.as_tensor(cnt, device=pts.device),
+                torch.as_tensor(np.array([m, s1, s2, 0.0]),
+                                device=pts.device))
+
+
+def test_device_cycle_equals_staged_operations():
+    """add_samples through ONE nb200_cycle call per raw batch (later-bound
+    exclusion, likelihood and sums fused) reproduces, shell by shell, the
+    run assembled from separate operations and host reductions: identical
+    counters and points, log-sum-exp triples to 1e-12."""
+    like = likelihoods.Gaussian(4, mu=[0.4, 0.5, 0.6, 0.5], sigma=0.08)
+    kw = dict(n_dim=4, n_live=400, seed=3, n_batch=300, emulator_arith='f64')
+    a = Sampler(lambda x: x, like, **kw)
+    b = _StagedCycleSampler(lambda x: x, like, **kw)
+    for s in (a, b):
+        assert s.device_cycle
+        assert s.run(n_eff=4000, discard_exploration=True)
+    assert len(a.bounds) == len(b.bounds) > 3
+    assert a.n_like == b.n_like
+    assert np.array_equal(a.shell_n, b.shell_n)
+    assert np.array_equal(a.shell_n_sample, b.shell_n_sample)
+    assert np.allclose(a.shell_log_l, b.shell_log_l, rtol=0, atol=1e-11)
+    assert np.allclose(a.shell_n_eff, b.shell_n_eff, rtol=1e-11)
+    assert np.allclose(a.shell_log_v, b.shell_log_v, rtol=0, atol=1e-12)
+    assert abs(a.log_z - b.log_z) < 1e-11
+    for pa, pb in zip(a.points, b.points):
+        assert np.array_equal(pa, pb)
+    # later-bound exclusion happened inside the cycle, and the host read 96
+    # bytes per raw batch
+    assert a.cycle_stats['d2h_bytes'] == 96 * a.cycle_stats['calls']
+    assert abs(a.log_z - like.log_z_true) < 0.05
+    # read-outs from the arena
+    pts, log_w, log_l = a.posterior()
+    assert len(pts) == np.sum(a.shell_n) and np.isclose(
+        np.sum(np.exp(log_w)), 1)
+    assert np.allclose(np.average(pts, weights=np.exp(log_w), axis=0),
+                       like.mu, atol=0.01)
+    assert [len(p) for p in a.points] == list(
+        a.shell_n + a.shell_end_exp)
 
 
 def test_sampler_enlarge_per_dim():
