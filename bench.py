@@ -561,6 +561,29 @@ def run_gpu(args):
             np_, wp = cpu_pass(1, 200000, kind='port')
             cpu['port_single_core_value'] = np_ / wp
 
+    # |delta log Z| of BASELINE's metric: config 2 end to end through the
+    # drop-in Sampler (outside every timed region), against the analytic
+    # evidence of the 30-D Gaussian; N_eff >= 4e4 puts the statistical error
+    # (1/sqrt(N_eff) = 0.005) well inside north_star's 0.01
+    logz = None
+    if world == 1 and not args.no_logz:
+        from nautilus_b200 import Sampler
+        t0 = time.perf_counter()
+        smp = Sampler(lambda x: x, like, n_dim=D, n_live=2000, seed=0,
+                      emulator_arith=args.mlp)
+        ok = smp.run(n_eff=40000, discard_exploration=True, timeout=600)
+        raw_total = sum(b.outer_bound.n_sample for b in smp.bounds[1:])
+        logz = {'log_z': float(smp.log_z), 'log_z_true': like.log_z_true,
+                'delta_log_z': abs(float(smp.log_z) - like.log_z_true),
+                'target': 0.01, 'n_eff': float(smp.n_eff),
+                'stat_error': float(1 / np.sqrt(smp.n_eff)),
+                'converged': bool(ok), 'wall_s': time.perf_counter() - t0,
+                'n_like': int(smp.n_like), 'n_bounds': len(smp.bounds),
+                'raw_proposals': int(raw_total),
+                'run': 'Sampler(prior=identity, Gaussian(30, sigma=0.1), '
+                       'n_live=2000, seed=0).run(n_eff=40000, '
+                       'discard_exploration=True)'}
+
     line = {
         'metric': 'raw_proposals_per_sec', 'value': value,
         'unit': 'proposals/s', 'n_gpus': world, 'steps': args.steps,
@@ -593,6 +616,8 @@ def run_gpu(args):
                     'api': 'nb200_session_submit/_wait: in-shell ROWS cross '
                            'PCIe (round-1 form)'}},
         'gpu_launches': launches,
+        'delta_log_z': None if logz is None else logz['delta_log_z'],
+        'log_z_run': logz,
         'clocks': clocks.summary() if clocks else None,
         'result': result,
     }
@@ -610,6 +635,8 @@ def main():
     ap.add_argument('--batch', type=int, default=1 << 20)
     ap.add_argument('--mlp', default='tf32', choices=['f64', 'tf32'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-logz', action='store_true',
+                    help='skip the end-to-end config-2 run (delta_log_z)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -196,3 +196,33 @@ def test_config3_like_wide_network_training():
     assert rmse < 0.3 * np.std(y)
     p32 = emu.predict(x, mode=ops.MLP_TF32)
     assert np.max(np.abs(p32 - pred)) < 5e-3
+
+
+def test_config2_delta_log_z_and_posterior_moments():
+    """BASELINE config 2 end to end through the drop-in Sampler: 30-D
+    N(0.5, 0.1^2 I), n_live = 2000, tensor-core emulator, device cycle.  Run to
+    N_eff >= 4e4 (statistical error 1/sqrt(N_eff) = 0.005) and
+    assert north_star's |delta log Z| <= 0.01 against the analytic evidence,
+    plus the posterior mean and covariance (the reference's own tolerances,
+    tests/test_sampler.py:167-215: 0.01 on the mean, 0.001 on the
+    covariance)."""
+    d = 30
+    like = likelihoods.Gaussian(d, sigma=0.1)
+    sampler = Sampler(lambda x: x, like, n_dim=d, n_live=2000, seed=0)
+    assert sampler.device_cycle and sampler.mlp_mode == ops.MLP_TF32
+    assert sampler.run(n_eff=40000, discard_exploration=True, timeout=600)
+    assert sampler.n_eff >= 40000
+    delta = abs(sampler.log_z - like.log_z_true)
+    print('config 2: log Z = {:+.5f} (truth {:+.1e}), |delta| = {:.5f}, '
+          'N_eff = {:.0f}, {} bounds, {} likelihood calls'.format(
+              sampler.log_z, like.log_z_true, delta, sampler.n_eff,
+              len(sampler.bounds), sampler.n_like))
+    assert delta <= 0.01
+    pts, log_w, _ = sampler.posterior()
+    w = np.exp(log_w)
+    assert np.isclose(np.sum(w), 1)
+    assert np.allclose(np.average(pts, weights=w, axis=0), 0.5, atol=0.01)
+    cov = np.cov(pts, aweights=w, rowvar=False)
+    assert np.allclose(cov, np.eye(d) * 0.01, atol=0.001)
+    # the batch loop read 96 bytes per raw batch from the device
+    assert sampler.cycle_stats['d2h_bytes'] == 96 * sampler.cycle_stats['calls']
