@@ -26,13 +26,45 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-D = 30
 CPU_BUDGET_S = 60.0      # CPU loop time the reference arm may spend
+
+# BASELINE.json configurations with a fixed, reference-built bound.  Config 2
+# is the headline (the driver's default run); config 5 is the strong-scaling
+# workload (fixed global batch split over the GPUs).
+CONFIGS = {
+    2: dict(d=30, golden='cfg2_bound_d30', like='Gaussian', batch=1 << 20,
+            scaling='weak', steps=1000,
+            workload='cfg2: 30-D isotropic Gaussian (sigma=0.1), '
+                     'n_live=2000, bound built by the reference (K=1 '
+                     'ellipsoid, 4 nets 100-50-20), batch=2^20 raw '
+                     'proposals per GPU per step'),
+    5: dict(d=100, golden='cfg5_bound_d100', like='EquicorrelatedGaussian',
+            batch=1 << 24, scaling='strong', steps=20,
+            workload='cfg5: 100-D correlated Gaussian (sigma=0.05, rho=0.5), '
+                     'n_live=10000, bound built by the reference from 40000 '
+                     'target draws (4 nets 100-50-20), batch=2^24 raw '
+                     'proposals per step IN TOTAL, split over the GPUs'),
+}
+CONFIG = 2
+D = 30
 ALGO_BYTES_PER_PROPOSAL = 8 * D + 8 + 1      # row + log_l + disposition
 MLP_FLOPS_PER_POINT = 4 * 2 * (30 * 100 + 100 * 50 + 50 * 20 + 20 * 1)
-WORKLOAD = ('cfg2: 30-D isotropic Gaussian (sigma=0.1), n_live=2000, bound '
-            'built by the reference (K=1 ellipsoid, 4 nets 100-50-20), '
-            'batch=2^20 raw proposals per GPU per step')
+WORKLOAD = CONFIGS[2]['workload']
+
+
+def select_config(c):
+    global CONFIG, D, ALGO_BYTES_PER_PROPOSAL, MLP_FLOPS_PER_POINT, WORKLOAD
+    global _SPEC
+    cfg = CONFIGS[c]
+    CONFIG, D, WORKLOAD = c, cfg['d'], cfg['workload']
+    ALGO_BYTES_PER_PROPOSAL = 8 * D + 8 + 1
+    MLP_FLOPS_PER_POINT = 4 * 2 * (D * 100 + 100 * 50 + 50 * 20 + 20 * 1)
+    _SPEC = None
+
+
+def make_like():
+    from nautilus_b200 import likelihoods
+    return getattr(likelihoods, CONFIGS[CONFIG]['like'])(D)
 
 
 def workload_config(batch):
@@ -52,7 +84,7 @@ def load_spec():
     if _SPEC is None:
         from nautilus_b200._pack import flat_to_spec
         with np.load(os.path.join(ROOT, 'tests', 'golden',
-                                  'cfg2_bound_d30.npz')) as f:
+                                  CONFIGS[CONFIG]['golden'] + '.npz')) as f:
             _SPEC = flat_to_spec({k: f[k] for k in f.files})
     return _SPEC
 
@@ -84,10 +116,11 @@ def cpu_kind():
 
 
 def _log_l_min():
-    like_norm = -0.5 * D * np.log(2 * np.pi * 0.1**2)
+    # (the config-2 fixture stores the threshold without the normalisation)
+    norm = make_like().norm if CONFIG == 2 else 0.0
     with np.load(os.path.join(ROOT, 'tests', 'golden',
-                              'cfg2_bound_d30.npz')) as f:
-        return float(f['log_l_min']) + like_norm
+                              CONFIGS[CONFIG]['golden'] + '.npz')) as f:
+        return float(f['log_l_min']) + norm
 
 
 def _cpu_worker(args):
@@ -103,9 +136,8 @@ def _cpu_worker(args):
     sampler.py:925-943)."""
     seed, n_raw, kind = args
     from threadpoolctl import threadpool_limits
-    from nautilus_b200 import likelihoods
     spec = load_spec()
-    like = likelihoods.Gaussian(D)
+    like = make_like()
     if kind == 'reference':
         from oracle import ref_arm
         ref_arm._import_reference()          # not part of the timed loop
@@ -221,8 +253,8 @@ def run_reference(args):
         'value': value, 'unit': 'proposals/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * wall / max(args.steps, 1),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': CONFIGS[CONFIG]['scaling'],
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.batch),
         'notes': {'emulator_arith': 'f64 (scikit-learn)',
                   'parallelism': '{} independent host processes'.format(
@@ -321,38 +353,62 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
 
     spec = load_spec()
-    like = likelihoods.Gaussian(D)
+    like = make_like()
     stack = ops.DeviceStack([spec], device=dev)
     like_params = like.device_params(dev)
-    n = args.batch
+    strong = CONFIGS[CONFIG]['scaling'] == 'strong'
+    # weak scaling: args.batch per GPU; strong: args.batch in total
+    n = args.batch // world if strong else args.batch
     mode = ops.MLP_TF32 if args.mlp == 'tf32' else ops.MLP_F64
     seed = 0
     log_l_min = _log_l_min()
 
     out = stack.cycle(0, n, seed=seed, like_id=like.like_id,
                       like_params=like_params, log_l_min=log_l_min, mode=mode)
-    # the kernels write the sums and counters straight into the send buffer
-    # of the one collective
-    words, out['lse'], out['counters'] = packed_stats(dev, ops.N_CNT,
-                                                      ops.N_LSE)
-    gathered = torch.zeros((world, ops.N_LSE + ops.N_CNT), dtype=torch.int64,
-                           device=dev)
+    # The kernels write the sums and counters straight into the send buffer
+    # of the one collective.  Send buffers are double-buffered and the
+    # all-gather of step s is asynchronous (NCCL's stream, behind the kernels
+    # of step s): the compute stream goes straight on to step s + 1 and only
+    # waits for the gather of step s when step s + 2 is about to overwrite its
+    # send buffer -- by then it finished long ago, so the exchange is off the
+    # critical path.
+    outs, words, gathered, works = [], [], [], [None, None]
+    for b in range(2):
+        w, lse_b, cnt_b = packed_stats(dev, ops.N_CNT, ops.N_LSE)
+        o = dict(out)
+        o['lse'], o['counters'] = lse_b, cnt_b
+        outs.append(o)
+        words.append(w)
+        gathered.append(torch.zeros((world, ops.N_LSE + ops.N_CNT),
+                                    dtype=torch.int64, device=dev))
     state = {'step': 0, 'merged': None}
 
     def step():
         # every rank draws its own slice of the global proposal index space
         s = state['step']
         state['step'] += 1
+        b = s & 1
+        if works[b] is not None:
+            works[b].wait()          # send buffer b is free again
+            works[b] = None
         offset = (s * world + rank) * n
         stack.cycle(0, n, seed=seed, offset=offset, like_id=like.like_id,
                     like_params=like_params, log_l_min=log_l_min, mode=mode,
-                    out=out)
+                    out=outs[b])
         if world > 1:
             # the one exchange step: per-rank counters + LSE partials; like
             # the single-GPU results they stay on the device until read
-            exchange_packed_async(words, gathered=gathered)
+            works[b] = exchange_packed_async(words[b], gathered=gathered[b],
+                                             async_op=True)
+
+    def drain():
+        for b in range(2):
+            if works[b] is not None:
+                works[b].wait()
+                works[b] = None
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -374,6 +430,7 @@ def run_gpu(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -386,12 +443,13 @@ def run_gpu(args):
         clocks.stop()
 
     # result of the last step (also a sanity check on the collective)
+    last = (state['step'] - 1) & 1
     if world > 1:
-        cnt, (m, s1, s2) = merge_packed(gathered, ops.N_LSE)
+        cnt, (m, s1, s2) = merge_packed(gathered[last], ops.N_LSE)
         cnt = cnt.astype(float)
     else:
-        cnt = out['counters'].cpu().numpy().astype(float)
-        m, s1, s2 = out['lse'].cpu().numpy()[:3]
+        cnt = outs[last]['counters'].cpu().numpy().astype(float)
+        m, s1, s2 = outs[last]['lse'].cpu().numpy()[:3]
     n_shell = cnt[ops.CNT_IN_SHELL]
     result = {
         'raw': int(cnt[ops.CNT_RAW]), 'in_shell': int(n_shell),
@@ -566,7 +624,7 @@ def run_gpu(args):
     # evidence of the 30-D Gaussian; N_eff >= 4e4 puts the statistical error
     # (1/sqrt(N_eff) = 0.005) well inside north_star's 0.01
     logz = None
-    if world == 1 and not args.no_logz:
+    if world == 1 and not args.no_logz and CONFIG == 2:
         from nautilus_b200 import Sampler
         t0 = time.perf_counter()
         smp = Sampler(lambda x: x, like, n_dim=D, n_live=2000, seed=0,
@@ -588,13 +646,13 @@ def run_gpu(args):
         'metric': 'raw_proposals_per_sec', 'value': value,
         'unit': 'proposals/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': CONFIGS[CONFIG]['scaling'],
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(n),
         'notes': {'emulator_arith': args.mlp,
                   'parallelism': 'proposal batch sharded over {} GPU(s), one '
-                                 'all-gather of 12 doubles per step'.format(
-                                     world)},
+                                 'asynchronous, double-buffered all-gather '
+                                 'of 12 words per step'.format(world)},
         'roofline': roofline,
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': 'proposals/s',
@@ -629,15 +687,23 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS),
+                    help='2: headline, weak scaling (default); 5: 100-D, '
+                         'fixed global batch, strong scaling')
+    ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=1 << 20)
+    ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--mlp', default='tf32', choices=['f64', 'tf32'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-logz', action='store_true',
                     help='skip the end-to-end config-2 run (delta_log_z)')
     args = ap.parse_args()
+    select_config(args.config)
+    if args.steps is None:
+        args.steps = CONFIGS[CONFIG]['steps']
+    if args.batch is None:
+        args.batch = CONFIGS[CONFIG]['batch']
     if args.impl == 'reference':
         run_reference(args)
     else:

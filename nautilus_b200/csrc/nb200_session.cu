@@ -179,12 +179,12 @@ int nb200_session_create(const int32_t* meta_h, int64_t n_meta,
   NB_S(cudaMalloc(&s->ws, s->wsb));
   for (int i = 0; i < n_slots; ++i) {
     Slot& t = s->slot[i];
-    // compaction may write up to n rows before the capacity check can run
-    NB_S(cudaMalloc(&t.out_points_d, sizeof(double) * n_max * d));
+    // (out_points_d, n_max rows, is allocated by the first row-mode submit:
+    // an index-mode session never needs it)
     NB_S(cudaMalloc(&t.out_log_l_d, sizeof(double) * n_max));
     NB_S(cudaMalloc(&t.small_d, 8 * SMALL_WORDS));
     NB_S(cudaMalloc(&t.like_d, sizeof(double) * s->like_cap));
-    NB_S(cudaMallocHost(&t.points_h, sizeof(double) * cap * d));
+    // (points_h likewise)
     NB_S(cudaMallocHost(&t.log_l_h, sizeof(double) * cap));
     NB_S(cudaMallocHost(&t.small_h, 8 * SMALL_WORDS));
     NB_S(cudaMallocHost(&t.like_h, sizeof(double) * s->like_cap));
@@ -286,6 +286,11 @@ int nb200_session_submit(nb200_session* s, int slot, int upload_stack,
                              like_id >= 0 ? t.out_log_l_d : nullptr, n_out_d,
                              s->ws, s->wsb, st);
   } else {
+    if (!t.out_points_d) {
+      // compaction may write up to n rows before the capacity check can run
+      NB_CUDA(cudaMalloc(&t.out_points_d,
+                         sizeof(double) * s->n_max * s->d));
+    }
     rc = nb200_compact(s->points_d, like_id >= 0 ? s->log_l_d : nullptr,
                        s->code_d, n, s->d, t.out_points_d,
                        like_id >= 0 ? t.out_log_l_d : nullptr, n_out_d, s->ws,
@@ -339,6 +344,8 @@ int nb200_session_wait(nb200_session* s, int slot, const double** points_h,
     return fail("nautilus_b200: %s (need %lld rows, cap %lld)",
                 "session output capacity too small", k, s->cap);
   if (k > 0) {
+    if (!t.points_h)
+      NB_CUDA(cudaMallocHost(&t.points_h, sizeof(double) * s->cap * s->d));
     // the kernels of the next batch keep running on `compute` meanwhile
     NB_CUDA(cudaMemcpyAsync(t.points_h, t.out_points_d,
                             sizeof(double) * k * s->d, cudaMemcpyDeviceToHost,

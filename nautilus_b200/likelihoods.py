@@ -27,6 +27,45 @@ class DeviceLikelihood:
             self.params(), dtype=np.float64)).to(device)
 
 
+class TorchLikelihood(DeviceLikelihood):
+    """Plug-in device likelihood: any callable on CUDA tensors.
+
+    ``fn`` receives what the reference hands a vectorised likelihood
+    (nautilus/sampler.py:856-873) -- the prior-transformed points as a CUDA
+    float64 tensor ``[n, d]`` (or a dict of CUDA tensors per parameter when
+    the sampler passes dictionaries) -- and returns ``log L`` as a CUDA
+    float64 tensor ``[n]``.  The sampler then keeps the whole batch loop on
+    the device: proposal, neural filter and later-bound exclusion in
+    ``nb200_cycle`` (no built-in likelihood), ``fn`` on the compacted rows in
+    the arena, log-sum-exp / counters by ``nb200_stats``; the host reads the
+    row count and 96 bytes of sums per raw batch.  The prior transform runs
+    on the device too (``Prior.unit_to_*_device`` or a torch-compatible prior
+    callable)."""
+    like_id = -1
+
+    def __init__(self, fn, n_dim=None, log_z_true=None):
+        self.fn = fn
+        self.n_dim = n_dim
+        self.log_z_true = log_z_true
+
+    def torch_call(self, args):
+        import torch
+        out = self.fn(args)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda):
+            raise TypeError('a TorchLikelihood must return a CUDA tensor')
+        return out.to(torch.float64).reshape(-1).contiguous()
+
+    def __call__(self, x):
+        """NumPy face (tests, CPU comparisons): upload, evaluate, download."""
+        import torch
+        t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64),
+                            device='cuda')
+        return self.torch_call(t).cpu().numpy()
+
+    def params(self):
+        return np.zeros(0)
+
+
 class Gaussian(DeviceLikelihood):
     """N(mu, sigma^2 I), normalised: log Z = sum_i log(Phi-mass in [0,1])."""
     like_id = ops.LIKE_GAUSSIAN

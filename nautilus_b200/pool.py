@@ -143,18 +143,25 @@ def packed_stats(device, n_cnt=8, n_lse=4):
     return words, words[:n_lse].view(torch.float64), words[n_lse:]
 
 
-def exchange_packed_async(words, gathered=None, group=None):
+def exchange_packed_async(words, gathered=None, group=None, async_op=False):
     """All-gather the raw words of :func:`packed_stats` (no packing kernels,
     counters stay exact int64).  Returns the gathered [world, n] int64 tensor
-    on the device; nothing is synchronised."""
+    on the device; nothing is synchronised.
+
+    ``async_op=True`` returns the work handle instead: the collective runs
+    on the backend's own stream behind whatever the current stream has
+    enqueued so far, and the current stream does NOT wait for it -- call
+    ``handle.wait()`` before reusing ``words`` or reading ``gathered`` (with
+    two send buffers that is two steps later, i.e. never a stall)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     if gathered is None:
         gathered = torch.empty((world, words.numel()), dtype=torch.int64,
                                device=words.device)
-    dist.all_gather_into_tensor(gathered.view(-1), words, group=group)
-    return gathered
+    work = dist.all_gather_into_tensor(gathered.view(-1), words, group=group,
+                                       async_op=async_op)
+    return work if async_op else gathered
 
 
 def merge_packed(gathered, n_lse=4):

@@ -606,6 +606,47 @@ class Sampler:
             self._cycle_buf = buf
         return buf
 
+    def _device_args(self, pts):
+        """What the likelihood is called with (sampler.py:856-862), for rows
+        that live on the device."""
+        if callable(self.prior):
+            return self.prior(pts)
+        if self.pass_dict:
+            return self.prior.unit_to_dictionary_device(pts)
+        return self.prior.unit_to_physical_device(pts)
+
+    def _run_cycle_plugin(self, index, n_raw, offset, out_points, out_log_l):
+        """The cycle with a plug-in (torch-callable) likelihood: nb200_cycle
+        without a built-in likelihood, the callable on the compacted rows,
+        nb200_stats.  One extra 8-byte read (the row count)."""
+        stack = self._device_stack()
+        bound = self.bounds[index]
+        buf = self._cycle_buffers(n_raw)
+        out = stack.cycle(
+            index, n_raw, later=(index + 1, len(self.bounds) - index - 1),
+            seed=bound.stream.seed, offset=offset,
+            stream_id=bound.stream.stream_id, like_id=-1, mode=self.mlp_mode,
+            out=buf)
+        _, _, n_out = stack.compact(out['points'][:n_raw], None,
+                                    out['code'][:n_raw],
+                                    out_points=out_points)
+        k = int(n_out.item())
+        counters = out['counters'].clone()
+        if k == 0:
+            lse = torch.tensor([-np.inf, 0.0, 0.0, 0.0], dtype=torch.float64,
+                               device=stack.device)
+            return counters, lse
+        log_l = self.likelihood.torch_call(
+            self._device_args(out_points[:k]))
+        if log_l.numel() != k:
+            raise ValueError('the likelihood returned {} values for {} '
+                             'points'.format(log_l.numel(), k))
+        out_log_l[:k] = log_l
+        lse, cnt = ops.stats(log_l, log_l_min=float(
+            self.shell_log_l_min[index]))
+        counters[ops.CNT_UPDATE] = cnt[ops.CNT_UPDATE]
+        return counters, lse
+
     def _run_cycle(self, index, n_raw, offset, out_points, out_log_l):
         """ONE nb200_cycle call: raw proposals [offset, offset + n_raw) of
         bound ``index`` -> neural filter -> exclusion by every later bound ->
@@ -613,6 +654,9 @@ class Sampler:
         ``out_points`` / ``out_log_l`` (views of the arena).  Returns the
         CUDA tensors (counters i64[8], lse f64[4]); nothing is synchronised.
         """
+        if self.likelihood.like_id < 0:
+            return self._run_cycle_plugin(index, n_raw, offset, out_points,
+                                          out_log_l)
         stack = self._device_stack()
         if self._like_params is None:
             self._like_params = self.likelihood.device_params(stack.device)
@@ -771,11 +815,15 @@ class Sampler:
         """log L (and blobs) of unit-cube ``points`` (sampler.py:832-908)."""
         if self.device_likelihood:
             dev = default_device()
-            if self._like_params is None:
-                self._like_params = self.likelihood.device_params(dev)
             pts = torch.as_tensor(np.ascontiguousarray(points), device=dev)
-            log_l = ops.loglike(pts, self.likelihood.like_id,
-                                self._like_params).cpu().numpy()
+            if self.likelihood.like_id < 0:
+                log_l = self.likelihood.torch_call(
+                    self._device_args(pts)).cpu().numpy()
+            else:
+                if self._like_params is None:
+                    self._like_params = self.likelihood.device_params(dev)
+                log_l = ops.loglike(pts, self.likelihood.like_id,
+                                    self._like_params).cpu().numpy()
             self.n_like += len(log_l)
             return log_l, None
 

@@ -271,6 +271,53 @@ def make_cfg2():
          **spec_to_flat(spec))
 
 
+# ---- 5b. the config-5 bound: 100-D correlated Gaussian --------------------
+
+def make_cfg5():
+    """d = 100, N(0.5, sigma^2 [(1-rho) I + rho 11^T]),
+    sigma = 0.05, rho = 0.5, n_live = 10 000; the fixed bound the reference
+    builds from 40 000 seeded points drawn from the target (minutes of CPU:
+    `python tests/golden/make_golden.py cfg5`)."""
+    from scipy.special import gammaln
+    from scipy.stats import chi2
+    from nautilus_b200 import likelihoods
+    d, m, n_live = 100, 40000, 10000
+    like = likelihoods.EquicorrelatedGaussian(d)
+    rng = np.random.default_rng(0)
+    sigma, rho = like.sigma, like.rho
+    # x = mu + sigma (sqrt(1-rho) e + sqrt(rho) g 1), e ~ N(0, I), g ~ N(0, 1)
+    pts = 0.5 + sigma * (np.sqrt(1 - rho) * rng.normal(size=(m, d)) +
+                         np.sqrt(rho) * rng.normal(size=(m, 1)))
+    assert np.all((pts > 0) & (pts < 1))
+    log_l = like(pts)
+    log_l_min = np.sort(log_l)[-n_live]
+    # volume of the likelihood contour holding n_live / m of the mass
+    r2 = chi2.ppf(n_live / m, d)
+    log_det = (d * np.log(sigma**2) + (d - 1) * np.log(1 - rho) +
+               np.log(1 + (d - 1) * rho))
+    log_v_target = (0.5 * log_det + 0.5 * d * np.log(r2) +
+                    0.5 * d * np.log(np.pi) - gammaln(d / 2 + 1))
+    bound = rb.NautilusBound.compute(
+        pts, log_l, log_l_min, log_v_target, n_networks=4,
+        rng=np.random.default_rng(1))
+    spec = nautilus_spec(bound)
+    bound.sample(2000, return_points=False)
+    test = np.vstack([bound.points[:512], pts[:512]])
+    nb = bound.neural_bounds[0]
+    t = nb.outer_bound.transform(test)
+    save('cfg5_bound_d100', points=test, contains=bound.contains(test),
+         union_contains=bound.outer_bound.contains(test),
+         neural_contains=nb.contains(test),
+         ell_contains=nb.outer_bound.contains(test),
+         predict=nb.emulator.predict(t),
+         log_l_min=log_l_min, log_v_target=log_v_target,
+         ref_log_v=bound.log_v, ref_n_sample=bound.n_sample,
+         ref_n_reject=bound.n_reject,
+         ref_u_n_sample=bound.outer_bound.n_sample,
+         ref_u_n_reject=bound.outer_bound.n_reject,
+         **spec_to_flat(spec))
+
+
 # ---- 6. shell bookkeeping from a real (small) reference run -----------------
 
 def make_shells():
@@ -321,6 +368,9 @@ def make_emulator():
 
 
 if __name__ == '__main__':
+    if sys.argv[1:] == ['cfg5']:
+        make_cfg5()
+        sys.exit(0)
     make_ellipsoids()
     make_mixture()
     make_union()

@@ -57,6 +57,25 @@ def _rank_main(rank, world, port, n, out):
     lse_v.copy_(torch.tensor([m, s1, s2, 0.0], dtype=torch.float64))
     total2, lse2 = merge_packed(exchange_packed_async(words))
     assert total2.tolist() == total.tolist() and lse2 == lse
+    # the asynchronous, double-buffered form of bench.py: the handle of step
+    # s is waited for only when step s + 2 reuses the send buffer
+    bufs = [packed_stats('cpu') for _ in range(2)]
+    gath = [torch.zeros((world, 12), dtype=torch.int64) for _ in range(2)]
+    works = [None, None]
+    for s in range(5):
+        b = s & 1
+        if works[b] is not None:
+            works[b].wait()
+            t3, l3 = merge_packed(gath[b])
+            assert t3.tolist() == (total * (s - 1)).tolist()
+        bufs[b][2].copy_(torch.from_numpy(cnt * (s + 1)))
+        bufs[b][1].copy_(torch.tensor([m, s1, s2, 0.0], dtype=torch.float64))
+        works[b] = exchange_packed_async(bufs[b][0], gathered=gath[b],
+                                         async_op=True)
+    for b in range(2):
+        works[b].wait()
+    t4, l4 = merge_packed(gath[0])         # step 4 used buffer 0
+    assert t4.tolist() == (total * 5).tolist() and l4 == lse
     if rank == 0:
         out.put((total.tolist(), lse))
     dist.barrier()

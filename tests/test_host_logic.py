@@ -241,3 +241,35 @@ def test_batched_gmm_matches_sequential():
     b = _construct.two_gaussians_batched(x, np.random.default_rng(1),
                                          device='cpu')
     assert np.array_equal(a, b)
+
+
+def test_prior_device_transforms_match_scipy():
+    """Prior.unit_to_*_device (torch) == the SciPy isf path of the reference
+    (nautilus/prior.py:85-181); torch CPU tensors exercise the same code the
+    CUDA tensors take."""
+    import torch
+    from scipy import stats
+    from nautilus_b200 import Prior
+    prior = Prior()
+    prior.add_parameter('a', (-1.0, 2.0))
+    prior.add_parameter('fixed', 0.25)
+    prior.add_parameter('b', stats.norm(loc=2.0, scale=0.5))
+    prior.add_parameter('c', stats.expon(scale=3.0))
+    prior.add_parameter('d', stats.lognorm(0.4, loc=1.0, scale=2.0))
+    prior.add_parameter('tied', 'b')
+    u = np.random.default_rng(0).random((257, 4))
+    ref = prior.unit_to_physical(u)
+    got = prior.unit_to_physical_device(torch.from_numpy(u)).numpy()
+    assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref))) < 1e-12
+    ref_d = prior.unit_to_dictionary(u)
+    got_d = prior.unit_to_dictionary_device(torch.from_numpy(u))
+    assert set(ref_d) == set(got_d)
+    for key in ref_d:
+        assert np.allclose(got_d[key].numpy(), ref_d[key], rtol=1e-12)
+    with pytest.raises(ValueError):
+        prior.unit_to_physical_device(torch.zeros((3, 5), dtype=torch.float64))
+    other = Prior()
+    other.add_parameter('x', stats.beta(2, 3))
+    with pytest.raises(NotImplementedError):
+        other.unit_to_physical_device(torch.zeros((3, 1),
+                                                  dtype=torch.float64))
