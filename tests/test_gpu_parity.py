@@ -178,7 +178,8 @@ def test_union_golden(golden):
 # a11, a12, a16 NeuralBound / emulator / NautilusBound
 # --------------------------------------------------------------------------
 
-@pytest.mark.parametrize('name', ['nautilus_d4', 'cfg2_bound_d30'])
+@pytest.mark.parametrize('name', ['nautilus_d4', 'cfg2_bound_d30',
+                                  'cfg5_bound_d100'])
 def test_nautilus_bound_golden(golden, name):
     g = golden(name)
     spec = flat_to_spec(g)

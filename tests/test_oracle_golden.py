@@ -90,7 +90,8 @@ def test_union_matches_reference(golden):
         g['log_v']
 
 
-@pytest.mark.parametrize('name', ['nautilus_d4', 'cfg2_bound_d30'])
+@pytest.mark.parametrize('name', ['nautilus_d4', 'cfg2_bound_d30',
+                                  'cfg5_bound_d100'])
 def test_nautilus_bound_matches_reference(golden, name):
     g = golden(name)
     spec = flat_to_spec(g)
