@@ -183,6 +183,12 @@ int nb200_bound_contains(const int32_t* meta_h, const int32_t* meta_d,
 
 /* bytes of scratch the bound-level entry points need for n points in d dims */
 size_t nb200_workspace_bytes(int64_t n, int d);
+/* ... and what nb200_cycle would like when `n_pairs` (later bound, neural
+ * bound) pairs exclude proposals (sum of J over the later bounds): with this
+ * much the exclusion of sampler.py:796-801 runs as ONE grouped pass per 2^18
+ * candidates whatever the number of later bounds; with less (but at least
+ * nb200_workspace_bytes) it runs in more passes, or one bound at a time. */
+size_t nb200_cycle_workspace_bytes(int64_t n, int d, int n_pairs);
 
 /* ---- shell reductions (sampler.py:925-943, 1144) ----------------------- */
 

@@ -70,6 +70,7 @@ PROTOTYPES = {
     'nb200_profile_collect': (_int, [_vp, _vp]),
     'nb200_profile_stage_name': (ctypes.c_char_p, [_int]),
     'nb200_workspace_bytes': (_sz, [_i64, _int]),
+    'nb200_cycle_workspace_bytes': (_sz, [_i64, _int, _int]),
     'nb200_ell_transform': (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     'nb200_ell_contains': (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     'nb200_ell_sample_from': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp,

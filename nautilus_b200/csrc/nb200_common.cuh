@@ -87,6 +87,21 @@ __host__ __device__ inline Rec record(const int32_t* meta, int bound) {
   return Rec{meta + meta[1 + bound]};
 }
 
+// ---- grouped later-bound exclusion (csrc/nb200_exclude.cu, nb200_mlp_tc.cu) --
+struct PairRec { int rec_off, j, blob_off, thr_off; };   // data offsets: doubles
+struct TcGroupArgs {
+  int n_pairs;
+  long long chunk_lo;                    // first candidate of this chunk
+  long long seg_stride;                  // rows reserved per segment
+  const PairRec* pairs;                  // [n_pairs]
+  const unsigned int* seg_count;         // [n_pairs] rows appended
+  const unsigned long long* n_cand;      // candidates in total
+  const unsigned int* cid;               // [n_pairs][seg_stride] candidate ids
+  const double* data;                    // the stack's parameter array
+  uint8_t* excl;                         // [n_cand] out
+};
+
+
 // ---- small device utilities ----------------------------------------------
 __device__ __forceinline__ int row_stride(int d) { return d | 1; }
 

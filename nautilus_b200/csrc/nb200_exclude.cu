@@ -1,0 +1,198 @@
+// Later-bound exclusion as ONE grouped pass (HOT LOOP D of the reference,
+// nautilus/sampler.py:796-801: a proposal of shell i is dropped if ANY later
+// bound contains it; 70 % of the reference's sampling-phase time).
+//
+// The reference calls bound.contains(points) once per later bound
+// (bounds/nautilus.py:146-169 -> union.py:269-289 + neural.py:99-126).  Here:
+//   1. the proposals that are still in the shell are compacted to a candidate
+//      list (the exclusion never looks at the other ~85 % of the raw batch);
+//   2. k_excl_prep: ONE launch tests every candidate against every later
+//      bound in fp64 -- union membership (all mixtures + unit cube), then each
+//      neural bound's ellipsoid -- with the candidate's row loaded into shared
+//      memory once for all bounds.  A (candidate, later bound, neural bound)
+//      triple that still needs the emulator's verdict is appended, already
+//      whitened, standardised and tf32-rounded, to the segment of its
+//      (bound, neural bound) pair;
+//   3. k_mlp_tf32<GROUPED>: ONE launch runs all segments through the tcgen05
+//      emulator, each with its pair's weights streamed out of L2 and its
+//      pair's threshold, and marks the candidates that a later bound contains;
+//   4. k_excl_apply writes NB200_CODE_EXCLUDED back into the dispositions.
+// The launch count does not depend on the number of later bounds.  The fp64
+// arithmetic is that of k_union_count / k_neural_prep / k_standardise_tf32
+// (same device functions, same expressions), so the result is bit-identical
+// to the per-bound loop it replaces (tests/test_gpu_exclusion.py).
+#include "nb200_device.cuh"
+
+namespace nb200 {
+
+constexpr int EX_THREADS = 128;
+
+// pair tables: pair_base[l] = first pair of later bound l; one pair per
+// (later bound, neural bound), with or without an emulator
+__global__ void k_excl_pairs(const int32_t* __restrict__ meta, int first_later,
+                             int n_later, PairRec* __restrict__ pairs,
+                             int* __restrict__ pair_base) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int p = 0;
+  for (int l = 0; l < n_later; ++l) {
+    const Rec rec = record(meta, first_later + l);
+    pair_base[l] = p;
+    const int J = rec.kind() == 1 ? rec.J() : 0;
+    for (int j = 0; j < J; ++j) {
+      const int32_t* nb = rec.nb(j);
+      PairRec pr;
+      pr.rec_off = (int)(rec.r - meta);
+      pr.j = j;
+      pr.blob_off = nb[3] > 0 ? nb[10] : -1;
+      pr.thr_off = nb[3] > 0 ? nb[7] : -1;
+      pairs[p++] = pr;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+k_excl_prep(const int32_t* __restrict__ meta, const double* __restrict__ data,
+            int first_later, int n_later, int d, int k0p,
+            const double* __restrict__ points,
+            const unsigned long long* __restrict__ cand_idx,
+            const unsigned long long* __restrict__ n_cand, long long chunk_lo,
+            long long chunk_cap, const int* __restrict__ pair_base,
+            unsigned int* __restrict__ seg_count, float* __restrict__ xs,
+            unsigned int* __restrict__ cid, long long seg_stride,
+            uint8_t* __restrict__ excl) {
+  extern __shared__ double sm[];
+  const int stride = row_stride(d);
+  double* rowX = sm;                                      // the candidate
+  double* rowS = rowX + (size_t)EX_THREADS * stride;      // x - c (scratch)
+  float* rowF = reinterpret_cast<float*>(rowS + (size_t)EX_THREADS * stride);
+  const long long m = (long long)*n_cand;
+  const long long hi = min(m, chunk_lo + chunk_cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long t0 = chunk_lo + (long long)blockIdx.x * EX_THREADS; t0 < hi;
+       t0 += (long long)gridDim.x * EX_THREADS) {
+    const int nrows = (int)min((long long)EX_THREADS, hi - t0);
+    // gather the candidates' rows: one warp per row, coalesced
+    for (int r = warp; r < nrows; r += EX_THREADS / 32) {
+      const double* src = points + cand_idx[t0 + r] * (unsigned long long)d;
+      for (int j = lane; j < d; j += 32) rowX[r * stride + j] = src[j];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nrows) {
+      const long long c = t0 + threadIdx.x;
+      const double* x = rowX + threadIdx.x * stride;
+      double* s = rowS + threadIdx.x * stride;
+      float* f = rowF + threadIdx.x * k0p;
+      bool out = false;
+      for (int l = 0; l < n_later && !out; ++l) {
+        const Rec rec = record(meta, first_later + l);
+        // Union.contains (union.py:285-289); a cube record is the unit cube
+        bool in;
+        if (rec.kind() == 0) {
+          in = cube_ok(x, nullptr, d);
+        } else {
+          in = union_count(rec, data, x, s) > 0;
+          if (in && rec.unit()) in = cube_ok(x, nullptr, d);
+        }
+        if (!in) continue;
+        const int J = rec.kind() == 1 ? rec.J() : 0;
+        if (J == 0) { out = true; break; }
+        for (int j = 0; j < J; ++j) {
+          const int32_t* nb = rec.nb(j);
+          const bool has_emu = nb[3] > 0;
+          const double* cN = data + nb[0];
+          const double* mean = data + nb[5];
+          const double* scale = data + nb[6];
+          // NeuralBound.contains (neural.py:115-119): ellipsoid test and the
+          // whitened coordinates, standardised for the emulator
+          // (nautilus/neural.py:115) exactly as k_standardise_tf32 does
+          for (int q = 0; q < d; ++q) s[q] = x[q] - __ldg(cN + q);
+          double r2 = 0.0;
+          matvec_rows(data + nb[1], d, nb[2], s, [&](int i, double v) {
+            r2 = fma(v, v, r2);
+            if (has_emu)
+              f[i] = (float)((v - __ldg(mean + i)) * (1.0 / __ldg(scale + i)));
+          });
+          if (!(r2 < 1.0)) continue;
+          if (!has_emu) { out = true; break; }
+          const int p = pair_base[l] + j;
+          const unsigned int slot = atomicAdd(seg_count + p, 1u);
+          const long long row = (long long)p * seg_stride + slot;
+          float* dst = xs + row * (long long)k0p;
+          for (int q = 0; q < k0p; ++q) {
+            const float v = q < d ? f[q] : (q == d ? 1.0f : 0.0f);
+            uint32_t rr;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
+            dst[q] = __uint_as_float(rr);
+          }
+          cid[row] = (unsigned int)(c);
+        }
+      }
+      if (out) excl[c] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_excl_apply(const unsigned long long* __restrict__ cand_idx,
+                             const unsigned long long* __restrict__ n_cand,
+                             const uint8_t* __restrict__ excl,
+                             uint8_t* __restrict__ code) {
+  const long long m = (long long)*n_cand;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < m;
+       c += (long long)gridDim.x * blockDim.x)
+    if (excl[c]) code[cand_idx[c]] = NB200_CODE_EXCLUDED;
+}
+
+// ---- host wrappers ----------------------------------------------------------
+
+int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
+                      PairRec* pairs, int* pair_base, cudaStream_t st) {
+  k_excl_pairs<<<1, 32, 0, st>>>(meta_d, first_later, n_later, pairs,
+                                 pair_base);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+size_t excl_prep_smem(int d, int k0p) {
+  return (size_t)EX_THREADS * (2 * (size_t)(d | 1) * sizeof(double) +
+                               (size_t)k0p * sizeof(float));
+}
+
+int launch_excl_prep(const int32_t* meta_d, const double* data_d,
+                     int first_later, int n_later, int d, int k0p,
+                     const double* points, const unsigned long long* cand_idx,
+                     const unsigned long long* n_cand, long long chunk_lo,
+                     long long chunk_cap, const int* pair_base,
+                     unsigned int* seg_count, float* xs, unsigned int* cid,
+                     long long seg_stride, uint8_t* excl, cudaStream_t st) {
+  const size_t smem = excl_prep_smem(d, k0p);
+  NB_CHECK(smem <= 227 * 1024, "exclusion prep: rows do not fit shared memory");
+  NB_CUDA(cudaFuncSetAttribute(k_excl_prep,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  int dev = 0, sms = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (chunk_cap + EX_THREADS - 1) / EX_THREADS;
+  const long long resident = (long long)sms * (smem * 2 <= 220 * 1024 ? 2 : 1);
+  if (grid > 4 * resident) grid = 4 * resident;
+  if (grid < 1) grid = 1;
+  k_excl_prep<<<(unsigned)grid, EX_THREADS, smem, st>>>(
+      meta_d, data_d, first_later, n_later, d, k0p, points, cand_idx, n_cand,
+      chunk_lo, chunk_cap, pair_base, seg_count, xs, cid, seg_stride, excl);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+int launch_excl_apply(const unsigned long long* cand_idx,
+                      const unsigned long long* n_cand, const uint8_t* excl,
+                      uint8_t* code, int64_t n, cudaStream_t st) {
+  long long grid = (n + 255) / 256;
+  if (grid > 2048) grid = 2048;
+  if (grid < 1) grid = 1;
+  k_excl_apply<<<(unsigned)grid, 256, 0, st>>>(cand_idx, n_cand, excl, code);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace nb200

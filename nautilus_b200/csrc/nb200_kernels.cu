@@ -7,6 +7,7 @@
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace nb200 {
@@ -861,6 +862,100 @@ static int union_contains_launch(const int32_t* meta_h, const int32_t* meta_d,
   return 0;
 }
 
+// ---- grouped later-bound exclusion (csrc/nb200_exclude.cu) ------------------
+int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
+                      PairRec* pairs, int* pair_base, cudaStream_t st);
+size_t excl_prep_smem(int d, int k0p);
+int launch_excl_prep(const int32_t* meta_d, const double* data_d,
+                     int first_later, int n_later, int d, int k0p,
+                     const double* points, const unsigned long long* cand_idx,
+                     const unsigned long long* n_cand, long long chunk_lo,
+                     long long chunk_cap, const int* pair_base,
+                     unsigned int* seg_count, float* xs, unsigned int* cid,
+                     long long seg_stride, uint8_t* excl, cudaStream_t st);
+int launch_excl_apply(const unsigned long long* cand_idx,
+                      const unsigned long long* n_cand, const uint8_t* excl,
+                      uint8_t* code, int64_t n, cudaStream_t st);
+int run_mlp_tf32_grouped(const int32_t* hdr32, const float* xs_segments,
+                         const TcGroupArgs& G, cudaStream_t st);
+
+constexpr int64_t EXCL_CHUNK = 1 << 18;   // candidates per pass (recommended)
+
+static inline int k0p_of(int d) { return (d + 1 + 7) / 8 * 8; }
+
+struct ExclWs {
+  unsigned long long* cand_idx;   // n
+  uint8_t* excl;                  // n
+  PairRec* pairs;                 // P
+  int* pair_base;                 // n_later
+  unsigned int* seg_count;        // P
+  float* xs;                      // P * cap * k0p
+  unsigned int* cid;              // P * cap
+  int64_t cap;                    // rows per segment (candidates per pass)
+};
+
+// carve the exclusion scratch out of [base, base + avail); cap < 0 asks for
+// the size that holds `want_cap` candidates per pass
+static size_t excl_layout(int64_t n, int P, int n_later, int k0p, char* base,
+                          size_t avail, int64_t want_cap, ExclWs* out) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  ExclWs w;
+  w.cand_idx = (unsigned long long*)take(sizeof(unsigned long long) * n);
+  w.excl = (uint8_t*)take((size_t)n);
+  w.pairs = (PairRec*)take(sizeof(PairRec) * (size_t)(P > 0 ? P : 1));
+  w.pair_base = (int*)take(sizeof(int) * (size_t)n_later);
+  w.seg_count = (unsigned int*)take(sizeof(unsigned int) * (size_t)(P > 0 ? P : 1));
+  const size_t row = (size_t)(P > 0 ? P : 1) * ((size_t)k0p * 4 + 4);
+  int64_t cap = want_cap;
+  if (cap < 0) {
+    cap = off + 512 < avail ? (int64_t)((avail - off - 512) / row) : 0;
+    cap = cap / 128 * 128;
+    const int64_t n128 = (n + 127) / 128 * 128;
+    if (cap > n128) cap = n128;
+  }
+  w.cap = cap;
+  w.xs = (float*)take((size_t)(P > 0 ? P : 1) * (size_t)cap * k0p * 4);
+  w.cid = (unsigned int*)take((size_t)(P > 0 ? P : 1) * (size_t)cap * 4);
+  if (out) *out = w;
+  return off;
+}
+
+// can records first_later .. +n_later be handled by the grouped pass?
+// *n_pairs = (later bound, neural bound) pairs; *hdr = the tensor-core header
+// shared by every pair that has an emulator (nullptr: none has one)
+static bool excl_applicable(const int32_t* meta_h, int first_later,
+                            int n_later, int d, int* n_pairs,
+                            const int32_t** hdr) {
+  const char* e = getenv("NB200_EXCLUDE");
+  if (e && strcmp(e, "loop") == 0) return false;
+  if (d > 48) return false;
+  int P = 0;
+  const int32_t* first = nullptr;
+  for (int l = first_later; l < first_later + n_later; ++l) {
+    const Rec rec = record(meta_h, l);
+    if (rec.d() != d) return false;
+    if (rec.kind() == 0) continue;
+    for (int j = 0; j < rec.J(); ++j, ++P) {
+      const int32_t* nb = rec.nb(j);
+      if (nb[3] <= 0) continue;                     // ellipsoid only
+      if (nb[10] < 0 || nb[11] <= 0) return false;  // no tensor-core blob
+      const int32_t* h = rec.r + nb[11];
+      if ((h[0] & 0xFFFF) != 0x7F32 || (h[0] >> 16) < 1) return false;
+      if (!first) first = h;
+      else if (memcmp(first, h, 30 * sizeof(int32_t)) != 0) return false;
+    }
+  }
+  if (P > 1 << 15) return false;
+  *n_pairs = P;
+  *hdr = first;
+  return true;
+}
+
 static int check_bound(const int32_t* meta_h, int bound) {
   NB_CHECK(meta_h != nullptr, "meta_h is NULL");
   NB_CHECK(bound >= 0 && bound < meta_h[0], "bound index out of range");
@@ -925,6 +1020,21 @@ int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 size_t nb200_workspace_bytes(int64_t n, int d) {
   return workspace_layout(n < 1 ? 1 : n, d < 1 ? 1 : d, nullptr, nullptr);
+}
+
+size_t nb200_cycle_workspace_bytes(int64_t n, int d, int n_pairs) {
+  if (n < 1) n = 1;
+  if (d < 1) d = 1;
+  size_t bytes = nb200_workspace_bytes(n, d);
+  if (n_pairs > 0) {
+    int64_t chunk = EXCL_CHUNK;
+    const char* e = getenv("NB200_EXCL_CHUNK");     // tests: force more passes
+    if (e && atoll(e) >= 128) chunk = atoll(e);
+    const int64_t cap = (n < chunk ? n : chunk) + 127;
+    bytes += excl_layout(n, n_pairs, n_pairs, k0p_of(d), nullptr, 0,
+                         cap / 128 * 128, nullptr) + 1024;
+  }
+  return bytes;
 }
 
 int nb200_ell_transform(const double* points_d, int64_t n, int d,
@@ -1284,8 +1394,62 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
       rc = launch_apply(1, n, code_d, ws.cand, ws.passf, nullptr, nullptr, st);
       if (rc) return rc;
     }
-    // 3. exclusion by every later bound (no short-circuit, like the reference)
-    for (int l = first_later; l < first_later + n_later; ++l) {
+    // 3. exclusion by every later bound (sampler.py:796-801): one grouped
+    // pass over all (later bound, neural bound) pairs when the emulators run
+    // on the tensor cores and the scratch holds at least one pass ...
+    bool grouped = false;
+    int n_pairs = 0;
+    const int32_t* hdr = nullptr;
+    if (n_later > 0 && mlp_mode == NB200_MLP_TF32 &&
+        excl_applicable(meta_h, first_later, n_later, d, &n_pairs, &hdr)) {
+      const size_t base_bytes = nb200_workspace_bytes(n, d);
+      const int k0p = k0p_of(d);
+      ExclWs ew;
+      excl_layout(n, n_pairs, n_later, k0p, (char*)workspace_d + base_bytes,
+                  workspace_bytes - base_bytes, -1, &ew);
+      if (ew.cap >= 1024 || ew.cap * 1 >= (n + 127) / 128 * 128) {
+        grouped = true;
+        ProfScope prof(ST_UNION, st);
+        rc = launch_excl_pairs(meta_d, first_later, n_later, ew.pairs,
+                               ew.pair_base, st);
+        if (rc) return rc;
+        // candidates = proposals still in the shell
+        const int nblocks = (int)((n + CMP_ITEMS - 1) / CMP_ITEMS);
+        k_compact_count<<<nblocks, CMP_THREADS, 0, st>>>(code_d, n,
+                                                         ws.block_count);
+        NB_LAUNCH_OK();
+        k_compact_index<<<nblocks, CMP_THREADS, 0, st>>>(
+            nullptr, code_d, n, 0ull, ws.block_count, ew.cand_idx, nullptr,
+            ws.total);
+        NB_LAUNCH_OK();
+        NB_CUDA(cudaMemsetAsync(ew.excl, 0, (size_t)n, st));
+        const unsigned long long* n_cand =
+            (const unsigned long long*)ws.total;
+        for (int64_t lo = 0; lo < n; lo += ew.cap) {
+          // (passes beyond the candidate count return at once: the count
+          // lives on the device, the number of passes must not)
+          NB_CUDA(cudaMemsetAsync(ew.seg_count, 0,
+                                  sizeof(unsigned int) * (size_t)(n_pairs > 0 ? n_pairs : 1), st));
+          rc = launch_excl_prep(meta_d, data_d, first_later, n_later, d, k0p,
+                                points_d, ew.cand_idx, n_cand, lo, ew.cap,
+                                ew.pair_base, ew.seg_count, ew.xs, ew.cid,
+                                ew.cap, ew.excl, st);
+          if (rc) return rc;
+          if (hdr) {
+            TcGroupArgs G;
+            G.n_pairs = n_pairs; G.chunk_lo = lo; G.seg_stride = ew.cap;
+            G.pairs = ew.pairs; G.seg_count = ew.seg_count; G.n_cand = n_cand;
+            G.cid = ew.cid; G.data = data_d; G.excl = ew.excl;
+            rc = run_mlp_tf32_grouped(hdr, ew.xs, G, st);
+            if (rc) return rc;
+          }
+        }
+        rc = launch_excl_apply(ew.cand_idx, n_cand, ew.excl, code_d, n, st);
+        if (rc) return rc;
+      }
+    }
+    // ... else one bound at a time (no short-circuit, like the reference)
+    for (int l = first_later; !grouped && l < first_later + n_later; ++l) {
       if (check_bound(meta_h, l)) return 1;
       NB_CHECK(record(meta_h, l).d() == d, "later bound has another n_dim");
       rc = union_contains_launch(meta_h, meta_d, data_d, l, points_d, code_d,

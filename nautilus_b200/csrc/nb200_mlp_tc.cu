@@ -57,6 +57,14 @@ struct TcTail {
   double log_l_min;
 };
 
+// Grouped mode (later-bound exclusion, nautilus/sampler.py:796-801): instead
+// of one array of rows the kernel walks SEGMENTS, one per (later bound,
+// neural bound) pair -- rows that k_excl_prep found inside that pair's
+// ellipsoids, already whitened and standardised -- with that pair's weights
+// and threshold; a row whose score passes marks its candidate as excluded.
+// The flattened list of 128-row tiles of all segments is split evenly over
+// the CTAs; a CTA reloads the weights (TMA bulk copy out of L2) only when it
+// crosses into another segment.
 // Debug timeline: clock64 stamps of one epilogue thread (slot 0) and of the
 // MMA issuer (slot 1) of tile group 0 in CTA 0, read back with
 // nb200_debug_timeline(); compiled in only with -DNB200_TIMELINE.  The index
@@ -96,12 +104,14 @@ __device__ __forceinline__ void pair_sync(int id) {
 // the epilogue warps arrive on s0/s1/s2/sA when the operand they produced (or
 // the region they finished reading) is ready -- nobody waits at a CTA
 // barrier, a fast warp runs ahead.
+template <bool GROUPED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
-           const float* __restrict__ xs32, const uint8_t* __restrict__ mask,
-           int64_t n, double* __restrict__ score_out,
-           uint8_t* __restrict__ passf, uint8_t* __restrict__ code,
-           const TcTail tail) {
+k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
+           const float* __restrict__ xs32_arg,
+           const uint8_t* __restrict__ mask, int64_t n_arg,
+           double* __restrict__ score_out, uint8_t* __restrict__ passf,
+           uint8_t* __restrict__ code, const TcTail tail,
+           const TcGroupArgs G) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t wbar;
   __shared__ uint64_t mbar[TC_GROUPS * 3];    // MMA completion: bA, bB, bC
@@ -122,7 +132,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
                                      // handles (warps w and w+4 share lanes)
   TL_DECL;
 
-  const double thr = __hiloint2double(h.thr_hi, h.thr_lo);
+  double thr = __hiloint2double(h.thr_hi, h.thr_lo);
   // architectures that need more than 256 TMEM columns run ONE tile group per
   // CTA (group 1 idles); otherwise two groups interleave
   const int n_groups = h.magic >> 16;
@@ -153,6 +163,83 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
                  ::: "memory");
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+
+  uint64_t* bA = &mbar[g * 3 + 0];
+  uint64_t* bB = &mbar[g * 3 + 1];
+  uint64_t* bC = &mbar[g * 3 + 2];
+  uint64_t* s0 = &sbar[g * 4 + 0];   // epilogue 0 done: A of layer 1 ready
+  uint64_t* s1 = &sbar[g * 4 + 1];   // epilogue 1 done: A of layer 2 ready
+  uint64_t* s2 = &sbar[g * 4 + 2];   // last epilogue done: D2 region free
+  uint64_t* sA = &sbar[g * 4 + 3];   // input rows of a tile staged
+
+  // ---- the rows this CTA works on ------------------------------------------
+  // plain mode: ONE segment = the whole array, tiles interleaved over the
+  // CTAs.  grouped mode: this CTA's share [my_lo, my_hi) of the flattened
+  // tile list of all segments, walked segment by segment.
+  const float* blob = blob_arg;
+  const float* xs32 = xs32_arg;
+  int64_t n = n_arg;
+  int64_t n_tiles = (n + 127) / 128;
+  int64_t tile_step = (int64_t)gridDim.x * n_groups;
+  int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g : n_tiles;
+  int64_t seg_row0 = 0;              // first row of the segment in cid[]
+  long long my_lo = 0, my_hi = 0, seg_first = 0;
+  int seg = 0, seg_end = 1;
+  if (GROUPED) {
+    seg_end = 0;
+    if ((unsigned long long)G.chunk_lo < *G.n_cand) {
+      long long total = 0;
+      for (int p = 0; p < G.n_pairs; ++p)
+        total += ((long long)G.seg_count[p] + 127) >> 7;
+      my_lo = total * (long long)blockIdx.x / (long long)gridDim.x;
+      my_hi = total * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+      seg_end = my_hi > my_lo ? G.n_pairs : 0;
+    }
+  }
+  uint32_t wphase = 0;
+  bool loaded = false;
+
+  // phases of the hand-over barriers run on across segments
+  uint32_t p0 = 0, p1 = 0, p2 = 0, pA = 0;         // issuer side
+  uint32_t phA = 0, phB = 0, phC = 0;             // epilogue side
+
+  Lse lse_acc;
+  lse_acc.init();
+  int c_rej0 = 0, c_rej1 = 0, c_rej2 = 0, c_rej3 = 0, c_in = 0, c_upd = 0,
+      c_raw = 0;
+
+  for (; seg < seg_end; ++seg) {
+  if (GROUPED) {
+    // this CTA's tiles [t_lo, t_hi) of segment `seg` (warp-uniform)
+    const long long tiles_p = ((long long)G.seg_count[seg] + 127) >> 7;
+    const long long lo = my_lo > seg_first ? my_lo - seg_first : 0;
+    const long long hi = my_hi - seg_first < tiles_p ? my_hi - seg_first
+                                                     : tiles_p;
+    seg_first += tiles_p;
+    if (hi <= lo) continue;
+    const PairRec pr = G.pairs[seg];
+    blob = reinterpret_cast<const float*>(G.data + pr.blob_off);
+    thr = G.data[pr.thr_off];
+    seg_row0 = (int64_t)seg * G.seg_stride;
+    xs32 = xs32_arg + seg_row0 * (int64_t)h.k0p;
+    n = (int64_t)G.seg_count[seg];
+    n_tiles = hi;
+    tile_step = n_groups;
+    tile0 = g < n_groups ? lo + g : n_tiles;
+  }
+  // ---- weights of this segment -> shared memory (TMA bulk copy) ------------
+  if (loaded) {
+    // every MMA that read the old weights has been waited for by the epilogue
+    // warps; everyone is done with the old segment
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (tid == 32) {   // one thread of warp 1 feeds the weights by TMA bulk copy
     const uint32_t bytes = (uint32_t)h.total_floats * 4u;
     mbar_expect_tx(&wbar, bytes);
@@ -164,33 +251,12 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       done += c;
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot + (uint32_t)(g * TC_COLS_PER_GROUP);
-  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-  mbar_wait(&wbar, 0);
-
-  uint64_t* bA = &mbar[g * 3 + 0];
-  uint64_t* bB = &mbar[g * 3 + 1];
-  uint64_t* bC = &mbar[g * 3 + 2];
-  uint64_t* s0 = &sbar[g * 4 + 0];   // epilogue 0 done: A of layer 1 ready
-  uint64_t* s1 = &sbar[g * 4 + 1];   // epilogue 1 done: A of layer 2 ready
-  uint64_t* s2 = &sbar[g * 4 + 2];   // last epilogue done: D2 region free
-  uint64_t* sA = &sbar[g * 4 + 3];   // input rows of a tile staged
-
-  const int64_t n_tiles = (n + 127) / 128;
-  const int64_t tile_step = (int64_t)gridDim.x * n_groups;
-  const int64_t tile0 = g < n_groups ? (int64_t)blockIdx.x * n_groups + g
-                                     : n_tiles;
+  mbar_wait(&wbar, wphase);
+  wphase ^= 1u;
+  loaded = true;
   // tiles this group processes
   const int64_t my_tiles =
       tile0 < n_tiles ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
-
-  Lse lse_acc;
-  lse_acc.init();
-  int c_rej0 = 0, c_rej1 = 0, c_rej2 = 0, c_rej3 = 0, c_in = 0, c_upd = 0,
-      c_raw = 0;
 
   if (is_issuer) {
     // =====================================================================
@@ -218,7 +284,6 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       }
       __syncwarp();
     };
-    uint32_t p0 = 0, p1 = 0, p2 = 0, pA = 0;
     const int N = h.n_net;
     if (h.n_hid == 3) {
       // instance i = (tile, network); MMAs execute in issue order, so region
@@ -394,6 +459,12 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
                         double ll) {
       const int64_t row = tile * 128 + r;
       bool accepted = false;
+      if (GROUPED) {
+        // inside this later bound: the candidate leaves the shell
+        if (active && (double)(sum / (float)h.n_net) > thr)
+          G.excl[G.cid[seg_row0 + row]] = 1;
+        return;
+      }
       if (active) {
         const double score = (double)(sum / (float)h.n_net);
         accepted = score > thr;
@@ -421,7 +492,6 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
       }
     };
 
-    uint32_t phA = 0, phB = 0, phC = 0;
     const int N = h.n_net;
     fetch(tile0);
     if (h.n_hid == 3) {
@@ -501,6 +571,8 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob,
     }
   }
 
+  }  // segments
+
   if (tail.partial) {
     long long cnt[NB200_N_CNT];
 #pragma unroll
@@ -569,7 +641,7 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
   if (smem < 120 * 1024) smem = 120 * 1024;
-  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32,
+  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   int dev = 0, sms = 0;
@@ -582,8 +654,36 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   if (grid < 1) grid = 1;
   if (tail.partial) NB_CHECK(grid <= STAT_MAX_BLOCKS, "too many partials");
   if (grid_out) *grid_out = (int)grid;
-  k_mlp_tf32<<<(unsigned)grid, TC_THREADS, smem, st>>>(
-      h, blob, xs32, mask, n, score_out, passf, code, tail);
+  TcGroupArgs none;
+  memset(&none, 0, sizeof(none));
+  k_mlp_tf32<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(
+      h, blob, xs32, mask, n, score_out, passf, code, tail, none);
+  NB_LAUNCH_OK();
+  return 0;
+}
+
+// Grouped mode: every (later bound, neural bound) segment of one candidate
+// chunk in ONE launch.  `h` is the architecture shared by all the pairs
+// (checked by the caller); thresholds and weights come from G.pairs.
+int run_mlp_tf32_grouped(const int32_t* hdr32, const float* xs_segments,
+                         const TcGroupArgs& G, cudaStream_t st) {
+  TcHeader h;
+  memcpy(&h, hdr32, sizeof(h));
+  NB_CHECK((h.magic >> 16) >= 1, "grouped emulator needs resident weights");
+  size_t smem = (size_t)h.total_floats * 4;
+  NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  int dev = 0, sms = 0;
+  NB_CUDA(cudaGetDevice(&dev));
+  NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TcTail tail;
+  memset(&tail, 0, sizeof(tail));
+  k_mlp_tf32<true><<<(unsigned)sms, TC_THREADS, smem, st>>>(
+      h, nullptr, xs_segments, nullptr, 0, nullptr, nullptr, nullptr, tail,
+      G);
   NB_LAUNCH_OK();
   return 0;
 }

@@ -175,7 +175,11 @@ int nb200_session_create(const int32_t* meta_h, int64_t n_meta,
   NB_S(cudaMalloc(&s->points_d, sizeof(double) * n_max * d));
   NB_S(cudaMalloc(&s->log_l_d, sizeof(double) * n_max));
   NB_S(cudaMalloc(&s->code_d, (size_t)n_max));
-  s->wsb = nb200_workspace_bytes(n_max, d);
+  // room for the grouped later-bound exclusion over the whole stack
+  int pairs = 0;
+  for (int b = 0; b < meta_h[0]; ++b)
+    if (record(meta_h, b).kind() == 1) pairs += record(meta_h, b).J();
+  s->wsb = nb200_cycle_workspace_bytes(n_max, d, pairs);
   NB_S(cudaMalloc(&s->ws, s->wsb));
   for (int i = 0; i < n_slots; ++i) {
     Slot& t = s->slot[i];

@@ -97,8 +97,12 @@ class Workspace:
         self.device = device
         self.buf = None
 
-    def get(self, n, d):
-        need = int(_lib.lib().nb200_workspace_bytes(int(n), int(d)))
+    def get(self, n, d, pairs=0):
+        if pairs > 0:
+            need = int(_lib.lib().nb200_cycle_workspace_bytes(
+                int(n), int(d), int(pairs)))
+        else:
+            need = int(_lib.lib().nb200_workspace_bytes(int(n), int(d)))
         if self.buf is None or self.buf.numel() < need:
             self.buf = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self.buf, need
@@ -241,7 +245,12 @@ class DeviceStack:
                                 device=self.device),
                 counters=torch.empty(N_CNT, dtype=torch.int64,
                                      device=self.device))
-        buf, nbytes = self.ws.get(n, d)
+        # (later bound, neural bound) pairs of the exclusion: record header
+        # word 4 is J
+        pairs = sum(int(self.meta_h[self.meta_h[1 + b] + 4])
+                    for b in range(later[0], later[0] + later[1])) \
+            if later[1] > 0 and mode == MLP_TF32 else 0
+        buf, nbytes = self.ws.get(n, d, pairs)
         n_par = 0 if like_params is None else like_params.numel()
         _lib.check(_lib.lib().nb200_cycle(
             self._meta_h_ptr, _ptr(self.meta_d), _ptr(self.data_d), bound,
