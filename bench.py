@@ -619,6 +619,79 @@ def run_gpu(args):
             np_, wp = cpu_pass(1, 200000, kind='port')
             cpu['port_single_core_value'] = np_ / wp
 
+    # ---- second workload: the same cycle in the SAMPLING phase, where a
+    # proposal of shell i is also tested against every later bound
+    # (sampler.py:796-801; 70 % of the reference's time there).  47 later
+    # bounds = nested copies of the config-2 bound (radius factor 0.9885 per
+    # bound: the volume halves every two bounds), each with its own threshold.
+    later_line = None
+    if CONFIG == 2 and not args.no_later:
+        import copy
+        os.environ.pop('NB200_EXCLUDE', None)
+
+        def nested(f, dthr):
+            sp = copy.deepcopy(spec)
+            for mx in sp['mixtures']:
+                mx['ell']['B'] = mx['ell']['B'] * f
+                mx['ell']['B_inv'] = mx['ell']['B_inv'] / f
+            for nbs in sp['neural']:
+                nbs['ell']['B'] = nbs['ell']['B'] * f
+                nbs['ell']['B_inv'] = nbs['ell']['B_inv'] / f
+                nbs['score_predict_min'] += dthr
+            return sp
+
+        L = 47
+        rs = np.random.default_rng(47)
+        later = [nested(0.9885**(i + 1), 0.01 * rs.normal())
+                 for i in range(L)]
+        stack_l = ops.DeviceStack([spec] + later, device=dev)
+        out_l = stack_l.cycle(0, n, later=(1, L), seed=seed,
+                              like_id=like.like_id, like_params=like_params,
+                              log_l_min=log_l_min, mode=mode)
+
+        def later_leg(k_steps):
+            for _ in range(2):
+                stack_l.cycle(0, n, later=(1, L), seed=seed,
+                              like_id=like.like_id, like_params=like_params,
+                              log_l_min=log_l_min, mode=mode, out=out_l)
+            barrier()
+            l0 = ops.launch_count()
+            a0 = torch.cuda.Event(enable_timing=True)
+            a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for s_ in range(k_steps):
+                stack_l.cycle(0, n, later=(1, L), seed=seed,
+                              offset=(s_ * world + rank) * n,
+                              like_id=like.like_id, like_params=like_params,
+                              log_l_min=log_l_min, mode=mode, out=out_l)
+            a1.record()
+            barrier()
+            return a0.elapsed_time(a1) / k_steps, \
+                (ops.launch_count() - l0) / k_steps
+
+        ms_g, launches_g = later_leg(50)
+        cnt_l = out_l['counters'].cpu().numpy()
+        os.environ['NB200_EXCLUDE'] = 'loop'
+        ms_loop, launches_loop = later_leg(5)
+        os.environ.pop('NB200_EXCLUDE', None)
+        if world > 1:
+            t = torch.tensor([ms_g, ms_loop], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_g, ms_loop = float(t[0].item()), float(t[1].item())
+        later_line = {
+            'workload': 'cfg2 + 47 later bounds (sampling phase): every '
+                        'proposal that passes the bound is tested against 47 '
+                        'nested later bounds (47 x 4 networks)',
+            'value': world * n / (ms_g * 1e-3), 'unit': 'proposals/s',
+            'ms_per_step': ms_g, 'launches_per_step': launches_g,
+            'excluded_fraction_of_accepted': float(
+                cnt_l[ops.CNT_EXCLUDED] / max(1, cnt_l[ops.CNT_EXCLUDED] +
+                                              cnt_l[ops.CNT_IN_SHELL])),
+            'per_bound_loop': {'value': world * n / (ms_loop * 1e-3),
+                               'ms_per_step': ms_loop,
+                               'launches_per_step': launches_loop}}
+        del stack_l, out_l
+
     # |delta log Z| of BASELINE's metric: config 2 end to end through the
     # drop-in Sampler (outside every timed region), against the analytic
     # evidence of the 30-D Gaussian; N_eff >= 4e4 puts the statistical error
@@ -674,6 +747,7 @@ def run_gpu(args):
                     'api': 'nb200_session_submit/_wait: in-shell ROWS cross '
                            'PCIe (round-1 form)'}},
         'gpu_launches': launches,
+        'later_bounds': later_line,
         'delta_log_z': None if logz is None else logz['delta_log_z'],
         'log_z_run': logz,
         'clocks': clocks.summary() if clocks else None,
@@ -696,6 +770,8 @@ def main():
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--mlp', default='tf32', choices=['f64', 'tf32'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-later', action='store_true',
+                    help='skip the cfg2 + 47 later bounds workload')
     ap.add_argument('--no-logz', action='store_true',
                     help='skip the end-to-end config-2 run (delta_log_z)')
     args = ap.parse_args()

@@ -367,7 +367,33 @@ def make_emulator():
     save('emulator_d5', x=x, y=y, predict=emu.predict(x), **flat)
 
 
+def make_fit_stats():
+    """scikit-learn's fit on the emulator_d5 data, 10 seeds (the reference's
+    train_network, nautilus/neural.py:10-32, with random_state = 0..9): final
+    training loss, epochs, and the rmse of the prediction against the target
+    -- what tests/test_gpu_bounds_api.py compares the CUDA trainer with."""
+    from nautilus.neural import train_network
+    with np.load(os.path.join(HERE, 'emulator_d5.npz')) as f:
+        x, y = f['x'], f['y']
+    xs = (x - np.mean(x, axis=0)) / np.std(x, axis=0)
+    kwargs = dict(hidden_layer_sizes=(100, 50, 20), alpha=0,
+                  learning_rate_init=1e-2, max_iter=10000, tol=0,
+                  n_iter_no_change=10)
+    loss, n_iter, rmse = [], [], []
+    for seed in range(10):
+        net = train_network(xs, y, kwargs, seed)
+        loss.append(net.loss_)
+        n_iter.append(net.n_iter_)
+        rmse.append(np.sqrt(np.mean((net.predict(xs) - y)**2)))
+    save('emulator_d5_sklearn_fits', loss=np.array(loss),
+         n_iter=np.array(n_iter), rmse=np.array(rmse))
+    print(loss, n_iter, rmse)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['fits']:
+        make_fit_stats()
+        sys.exit(0)
     if sys.argv[1:] == ['cfg5']:
         make_cfg5()
         sys.exit(0)

@@ -201,6 +201,44 @@ def test_neural_network_emulator():
     assert emu.neural_networks[0].coefs_[0].shape == (5, 100)
 
 
+def test_trainer_quality_against_sklearn_fits(golden):
+    """The CUDA trainer against scikit-learn's own fits of the same data
+    (tests/golden/emulator_d5_sklearn_fits.npz: MLPRegressor with
+    random_state 0..9 through the reference's train_network,
+    nautilus/neural.py:10-32).  The fit is statistical -- other random
+    numbers, fp32 -- so the bar is on the distribution over seeds: median
+    final loss and median rmse of ten networks within 1.25x of sklearn's
+    medians, and no network worse than sklearn's worst by more than 1.5x."""
+    from nautilus_b200.neural import NeuralNetworkEmulator
+    g = golden('emulator_d5')
+    ref = golden('emulator_d5_sklearn_fits')
+    x, y = g['x'], g['y']
+    emu = NeuralNetworkEmulator.train(x, y, n_networks=10, seed=123)
+    xs = (x - emu.mean) / emu.scale
+    loss = np.array([n.loss_ for n in emu.neural_networks])
+    n_iter = np.array([n.n_iter_ for n in emu.neural_networks])
+    rmse = []
+    for net in emu.neural_networks:
+        a = xs
+        for i, (w, b) in enumerate(zip(net.coefs_, net.intercepts_)):
+            a = a @ w + b
+            if i + 1 < len(net.coefs_):
+                a = np.maximum(a, 0)
+        rmse.append(np.sqrt(np.mean((a[:, 0] - y)**2)))
+    rmse = np.array(rmse)
+    print('trainer vs sklearn over 10 seeds: median loss {:.2e} vs {:.2e}, '
+          'median rmse {:.4f} vs {:.4f}, worst rmse {:.4f} vs {:.4f}, '
+          'median epochs {:.0f} vs {:.0f}'.format(
+              np.median(loss), np.median(ref['loss']), np.median(rmse),
+              np.median(ref['rmse']), rmse.max(), ref['rmse'].max(),
+              np.median(n_iter), np.median(ref['n_iter'])))
+    assert np.median(loss) <= 1.25 * np.median(ref['loss'])
+    assert np.median(rmse) <= 1.25 * np.median(ref['rmse'])
+    assert rmse.max() <= 1.5 * ref['rmse'].max()
+    # the test of the reference itself (tests/test_neural.py:15)
+    assert np.all(rmse < 0.3 * np.std(y))
+
+
 def test_neural_bound_contains(random_points_from_hypercube):
     points = random_points_from_hypercube
     log_l = -np.linalg.norm(points - 0.5, axis=1)
@@ -334,3 +372,30 @@ def test_device_mvee_matches_host():
                                              max_updates=20000)
     assert np.allclose(c, 0, atol=1e-3) and np.allclose(a, np.eye(d),
                                                         atol=1e-2)
+
+
+@pytest.mark.parametrize('d', [3, 10, 30])
+def test_device_mvee_against_the_reference_ellipsoid(golden, d):
+    """The device enclosing ellipsoid against the REFERENCE's own
+    (tests/golden/ellipsoid_d*.npz stores c, A, log_v of
+    Ellipsoid.compute(pts, enlarge_per_dim=1.1) for a seeded point cloud that
+    is regenerated here): both enclose every point; the volumes agree to a few
+    per cent (Khachiyan's iteration is stopped by tolerance in the reference,
+    basic.py:175-241, and run to 3000 updates here: slightly tighter)."""
+    g = golden('ellipsoid_d{}'.format(d))
+    rng = np.random.default_rng(100 + d)
+    L = np.tril(rng.normal(size=(d, d))) * 0.3 + np.eye(d)
+    pts = 0.5 + 0.05 * rng.normal(size=(40 * d, d)) @ L.T / np.sqrt(d)
+    # the fixture's ellipsoid encloses the regenerated cloud (same cloud)
+    ref_quad = np.einsum('ij,jk,ik->i', pts - g['c'], g['A'], pts - g['c'])
+    assert np.max(ref_quad) <= 1.0 / 1.1**2 + 1e-9
+    ell = bounds.Ellipsoid.compute(pts, enlarge_per_dim=1.1,
+                                   rng=np.random.default_rng(0))
+    quad = np.einsum('ij,jk,ik->i', pts - ell.c, ell.A, pts - ell.c)
+    assert abs(np.max(quad) - 1.0 / 1.1**2) < 1e-8       # touches, encloses
+    assert bool(np.all(ell.contains(pts)))
+    print('d = {}: log_v device {:.5f} reference {:.5f}'.format(
+        d, ell.log_v, float(g['log_v'])))
+    assert ell.log_v <= float(g['log_v']) + 1e-3          # never looser
+    assert float(g['log_v']) - ell.log_v < 0.03 * d       # ... nor far off
+    assert np.max(np.abs(ell.c - g['c'])) < 0.02
