@@ -359,7 +359,8 @@ def run_gpu(args):
     strong = CONFIGS[CONFIG]['scaling'] == 'strong'
     # weak scaling: args.batch per GPU; strong: args.batch in total
     n = args.batch // world if strong else args.batch
-    mode = ops.MLP_TF32 if args.mlp == 'tf32' else ops.MLP_F64
+    mode = {'tf32': ops.MLP_TF32, 'f16': ops.MLP_F16,
+            'f64': ops.MLP_F64}[args.mlp]
     seed = 0
     log_l_min = _log_l_min()
 
@@ -594,11 +595,15 @@ def run_gpu(args):
     if 'mlp_predict' in stage_ms:
         fl = MLP_FLOPS_PER_POINT * evaluated
         ach = fl / (stage_ms['mlp_predict'] * 1e-3) / 1e12
+        # kind::f16 runs at the bf16 rate; kind::tf32 at half of it
+        tpeak = peaks['bf16'] * (0.5 if args.mlp == 'tf32' else 1.0)
         roofline['emulator_tensor'] = {
-            'achieved': ach, 'peak': peaks['bf16'], 'unit': 'TFLOP/s',
-            'frac': ach / peaks['bf16'], 'flops_per_launch': fl,
+            'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s',
+            'frac': ach / tpeak, 'flops_per_launch': fl,
             'arith': args.mlp,
-            'peak_source': peaks['source'] + ', dense bf16 burst'}
+            'peak_source': peaks['source'] + ', dense bf16 burst' + (
+                ' / 2 (tf32)' if args.mlp == 'tf32' else
+                ' (fp16 operands run at the bf16 rate)')}
     # whole-step figure against the 8d+9 B/proposal HBM roofline
     roofline['cycle_hbm_frac'] = (value / world * ALGO_BYTES_PER_PROPOSAL /
                                   1e9) / peaks['hbm']
@@ -768,7 +773,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=None)
-    ap.add_argument('--mlp', default='tf32', choices=['f64', 'tf32'])
+    ap.add_argument('--mlp', default='f16', choices=['f64', 'tf32', 'f16'],
+                    help='emulator arithmetic: tcgen05 kind::f16 (default), '
+                         'kind::tf32, or the fp64 parity kernels')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-later', action='store_true',
                     help='skip the cfg2 + 47 later bounds workload')

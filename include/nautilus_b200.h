@@ -57,6 +57,9 @@ extern "C" {
 /* emulator arithmetic */
 #define NB200_MLP_F64 0   /* fp64 CUDA cores, canonical summation order     */
 #define NB200_MLP_TF32 1  /* tcgen05 kind::tf32, fp32 accumulate in TMEM    */
+#define NB200_MLP_F16 2   /* tcgen05 kind::f16 (fp16 operands: the same 10
+                           * mantissa bits as tf32, half the bytes), fp32
+                           * accumulate; emulators with resident weights    */
 
 /* built-in synthetic likelihoods; params are float64        */
 #define NB200_LIKE_GAUSSIAN 0    /* {inv_sigma2, norm, mu[d]}                */

@@ -243,6 +243,89 @@ def pack_tc(emu, score_predict_min):
     return np.asarray(hdr, dtype=np.int32), blob
 
 
+TC16_MAGIC = 0x7F16
+
+
+def f16_round(a):
+    """Round to IEEE half precision (nearest even), returned as float32."""
+    return np.asarray(a, dtype=np.float64).astype(np.float16).astype(
+        np.float32)
+
+
+def _core_matrix_layout16(wt, np_, kp):
+    """K-major, no-swizzle UMMA operand layout of a [n, k] half-precision
+    matrix zero-padded to [np_, kp]: 8-row x 16-byte (8 element) core
+    matrices, K chunks 128 B apart, 8-row groups kp*16 B apart."""
+    full = np.zeros((np_, kp), dtype=np.float16)
+    full[:wt.shape[0], :wt.shape[1]] = wt
+    return full.reshape(np_ // 8, 8, kp // 8, 8).transpose(0, 2, 1, 3).ravel()
+
+
+def pack_tc16(emu, score_predict_min):
+    """Tensor-core blob of an emulator for the kind::f16 form of the emulator
+    kernel (fp16 x fp16 -> fp32: the same 10 explicit mantissa bits as tf32,
+    half the shared memory, TMEM traffic and MMA time).
+
+    Returns ``(header int32[32], blob float32[] holding the raw bytes)`` or
+    ``None`` when the architecture does not fit (resident weights only: <= 4
+    hidden layers, <= 220 KB, <= 512 TMEM columns).  Same header fields as
+    :func:`pack_tc`; offsets count 4-byte words; ``b_off[0]`` is filled by
+    the caller with the blob's offset in the data array."""
+    coefs, intercepts = emu['coefs'], emu['intercepts']
+    n_net, n_lay = len(coefs), len(coefs[0])
+    n_hid = n_lay - 1
+    if not 1 <= n_hid <= TC_MAX_HID:
+        return None
+    sizes = [coefs[0][0].shape[0]] + [w.shape[1] for w in coefs[0]]
+    d = sizes[0]
+    k0p = _round_up(d + 1, 16)
+    np_ = [_round_up(sizes[l + 1] + 1, 16) for l in range(n_hid)]
+    kp = [k0p] + np_[:-1]          # fan_in of layer l = padded fan_out of l-1
+    a0_col, col = 0, _round_up(k0p // 2, 32)
+    d_col = []
+    for l in range(n_hid):
+        d_col.append(col)
+        col += _round_up(np_[l], 32)
+    w_off, off = [], 0
+    for l in range(n_hid):
+        w_off.append(off)
+        off += np_[l] * kp[l] // 2             # 4-byte words
+    w_out_off = off
+    off += np_[-1]
+    b_out_off = off
+    off += 4
+    net_stride = _round_up(off, 4)
+    total = net_stride * n_net
+    if col > TC_COLS_SINGLE or total * 4 > TC_SMEM_LIMIT:
+        return None
+    n_groups = 2 if col <= TC_COLS else 1
+    blob = np.zeros(total, dtype=np.float32)
+    raw = blob.view(np.float16)
+    for n in range(n_net):
+        base = n * net_stride
+        for l in range(n_hid):
+            fi, fo = sizes[l], sizes[l + 1]
+            wt = np.zeros((fo + 1, fi + 1))
+            wt[:fo, :fi] = np.asarray(coefs[n][l], dtype=np.float64).T
+            wt[:fo, fi] = np.asarray(intercepts[n][l], dtype=np.float64)
+            if l + 1 < n_hid:
+                wt[fo, fi] = 1.0   # regenerate the constant-one column
+            lo = 2 * (base + w_off[l])
+            raw[lo:lo + np_[l] * kp[l]] = _core_matrix_layout16(
+                wt.astype(np.float16), np_[l], kp[l])
+        w_out = np.asarray(coefs[n][-1], dtype=np.float32).ravel()
+        blob[base + w_out_off:base + w_out_off + len(w_out)] = w_out
+        blob[base + b_out_off] = np.float32(intercepts[n][-1][0])
+    thr = np.array([float(score_predict_min) - 1e-9]).view(np.int32)
+    pad4 = lambda v: list(v) + [0] * (TC_MAX_HID - len(v))  # noqa: E731
+    hdr = [TC16_MAGIC | (n_groups << 16), n_net, n_hid, d, k0p, net_stride,
+           total, a0_col]
+    hdr += pad4(np_) + pad4(kp) + pad4(w_off) + pad4([]) + pad4(d_col)
+    hdr += [w_out_off, b_out_off, int(thr[0]), int(thr[1])]
+    assert len(hdr) == TC_HDR_WORDS
+    return np.asarray(hdr, dtype=np.int32), blob
+
+
 def _is_lower(m):
     return bool(np.all(np.triu(m, 1) == 0))
 
@@ -341,6 +424,18 @@ def pack_record(spec, data, cdf=None):
                     np.float64))
             off_tc_hdr = base_tail + sum(len(t) for t in tail)
             tail.append(tc[0])
+            # the kind::f16 form of the same weights: a second 32-int header
+            # right behind the first (all zero when the architecture does not
+            # fit), its b_off[0] = offset of the blob in the data array
+            tc16 = pack_tc16(emu, nb['score_predict_min'])
+            if tc16 is None:
+                tail.append(np.zeros(TC_HDR_WORDS, dtype=np.int32))
+            else:
+                h16 = tc16[0].copy()
+                h16[20] = data.add(np.concatenate(
+                    [tc16[1], np.zeros(len(tc16[1]) % 2, np.float32)]).view(
+                        np.float64))
+                tail.append(h16)
         nb_recs[j] = (off_c, off_binv, tri, n_net, n_lay, off_mean, off_scale,
                       off_thr, off_sizes, off_wtab, off_tc, off_tc_hdr)
     hdr[7] = HDR

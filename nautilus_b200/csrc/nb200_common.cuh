@@ -102,6 +102,11 @@ struct TcGroupArgs {
 };
 
 
+// emulator arithmetic on the tensor cores?
+inline bool mode_tc(int mode) {
+  return mode == NB200_MLP_TF32 || mode == NB200_MLP_F16;
+}
+
 // ---- small device utilities ----------------------------------------------
 __device__ __forceinline__ int row_stride(int d) { return d | 1; }
 

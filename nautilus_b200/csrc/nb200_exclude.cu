@@ -22,6 +22,7 @@
 // (same device functions, same expressions), so the result is bit-identical
 // to the per-bound loop it replaces (tests/test_gpu_exclusion.py).
 #include "nb200_device.cuh"
+#include "nb200_tc.cuh"
 
 namespace nb200 {
 
@@ -30,7 +31,8 @@ constexpr int EX_THREADS = 128;
 // pair tables: pair_base[l] = first pair of later bound l; one pair per
 // (later bound, neural bound), with or without an emulator
 __global__ void k_excl_pairs(const int32_t* __restrict__ meta, int first_later,
-                             int n_later, PairRec* __restrict__ pairs,
+                             int n_later, int f16,
+                             PairRec* __restrict__ pairs,
                              int* __restrict__ pair_base) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int p = 0;
@@ -43,16 +45,79 @@ __global__ void k_excl_pairs(const int32_t* __restrict__ meta, int first_later,
       PairRec pr;
       pr.rec_off = (int)(rec.r - meta);
       pr.j = j;
-      pr.blob_off = nb[3] > 0 ? nb[10] : -1;
+      // (the fp16 header sits 32 ints behind the tf32 one; its word 20 is
+      // the position of the fp16 blob, _pack.py:pack_record)
+      pr.blob_off = nb[3] <= 0 ? -1 : f16 ? rec.r[nb[11] + 32 + 20] : nb[10];
       pr.thr_off = nb[3] > 0 ? nb[7] : -1;
       pairs[p++] = pr;
     }
   }
 }
 
+// matvec_rows (nb200_device.cuh) for a factor staged in SHARED memory: same
+// left-to-right FMA chains, plain loads
+template <typename F>
+__device__ __forceinline__ void matvec_rows_sm(const double* M, int de,
+                                               int lower, const double* s,
+                                               F&& f) {
+  int i = 0;
+  for (; i + 4 <= de; i += 4) {
+    const double* m0 = M + (size_t)i * de;
+    const double* m1 = m0 + de;
+    const double* m2 = m1 + de;
+    const double* m3 = m2 + de;
+    const int jmax = lower ? i + 4 : de;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < jmax; ++j) {
+      const double sj = s[j];
+      a0 = fma(m0[j], sj, a0);
+      a1 = fma(m1[j], sj, a1);
+      a2 = fma(m2[j], sj, a2);
+      a3 = fma(m3[j], sj, a3);
+    }
+    f(i, a0); f(i + 1, a1); f(i + 2, a2); f(i + 3, a3);
+  }
+  for (; i < de; ++i) {
+    const double* m0 = M + (size_t)i * de;
+    const int jmax = lower ? i + 1 : de;
+    double a0 = 0.0;
+    for (int j = 0; j < jmax; ++j) a0 = fma(m0[j], s[j], a0);
+    f(i, a0);
+  }
+}
+
+// append one (candidate, pair) row to the pair's segment
+__device__ __forceinline__ void excl_append(const float* f, int d, int k0p,
+                                            int f16, int p, long long c,
+                                            unsigned int* seg_count,
+                                            float* xs, unsigned int* cid,
+                                            long long seg_stride) {
+  const unsigned int slot = atomicAdd(seg_count + p, 1u);
+  const long long row = (long long)p * seg_stride + slot;
+  if (f16) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(xs) +
+                    row * (long long)(k0p >> 1);
+    for (int q = 0; q < k0p; q += 2) {
+      const float v0 = q < d ? f[q] : (q == d ? 1.0f : 0.0f);
+      const float v1 = q + 1 < d ? f[q + 1] : (q + 1 == d ? 1.0f : 0.0f);
+      dst[q >> 1] = pack_f16x2(v0, v1);
+    }
+  } else {
+    float* dst = xs + row * (long long)k0p;
+    for (int q = 0; q < k0p; ++q) {
+      const float v = q < d ? f[q] : (q == d ? 1.0f : 0.0f);
+      uint32_t rr;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
+      dst[q] = __uint_as_float(rr);
+    }
+  }
+  cid[row] = (unsigned int)(c);
+}
+
 __global__ void __launch_bounds__(EX_THREADS)
 k_excl_prep(const int32_t* __restrict__ meta, const double* __restrict__ data,
-            int first_later, int n_later, int d, int k0p,
+            int first_later, int n_later, int d, int k0p, int f16,
             const double* __restrict__ points,
             const unsigned long long* __restrict__ cand_idx,
             const unsigned long long* __restrict__ n_cand, long long chunk_lo,
@@ -64,7 +129,13 @@ k_excl_prep(const int32_t* __restrict__ meta, const double* __restrict__ data,
   const int stride = row_stride(d);
   double* rowX = sm;                                      // the candidate
   double* rowS = rowX + (size_t)EX_THREADS * stride;      // x - c (scratch)
-  float* rowF = reinterpret_cast<float*>(rowS + (size_t)EX_THREADS * stride);
+  // parameters of the later bound at hand, staged once per block (the usual
+  // bound: one plain ellipsoid + one neural bound): the factors come out of
+  // shared memory instead of L2 (47 bounds x 2 factors do not fit L1)
+  double* stM = rowS + (size_t)EX_THREADS * stride;       // d*d  mixture B_inv
+  double* stN = stM + d * d;                              // d*d  neural B_inv
+  double* stV = stN + d * d;        // 4 d: c (mixture), c (neural), mean, 1/scale
+  float* rowF = reinterpret_cast<float*>(stV + 4 * d);
   const long long m = (long long)*n_cand;
   const long long hi = min(m, chunk_lo + chunk_cap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,58 +148,99 @@ k_excl_prep(const int32_t* __restrict__ meta, const double* __restrict__ data,
       for (int j = lane; j < d; j += 32) rowX[r * stride + j] = src[j];
     }
     __syncthreads();
-    if ((int)threadIdx.x < nrows) {
-      const long long c = t0 + threadIdx.x;
-      const double* x = rowX + threadIdx.x * stride;
-      double* s = rowS + threadIdx.x * stride;
-      float* f = rowF + threadIdx.x * k0p;
-      bool out = false;
-      for (int l = 0; l < n_later && !out; ++l) {
-        const Rec rec = record(meta, first_later + l);
-        // Union.contains (union.py:285-289); a cube record is the unit cube
-        bool in;
-        if (rec.kind() == 0) {
-          in = cube_ok(x, nullptr, d);
-        } else {
-          in = union_count(rec, data, x, s) > 0;
-          if (in && rec.unit()) in = cube_ok(x, nullptr, d);
+    const bool valid = (int)threadIdx.x < nrows;
+    const long long c = t0 + threadIdx.x;
+    const double* x = rowX + threadIdx.x * stride;
+    double* s = rowS + threadIdx.x * stride;
+    float* f = rowF + threadIdx.x * k0p;
+    bool out = false;
+    for (int l = 0; l < n_later; ++l) {
+      const Rec rec = record(meta, first_later + l);
+      const bool plain = rec.kind() == 1 && rec.K() == 1 && rec.J() == 1 &&
+                         rec.mix(0)[1] == 0 && rec.mix(0)[0] == d;
+      if (plain) {
+        // ---- staged: one ellipsoid, one neural bound (block-uniform) --------
+        const int32_t* mix = rec.mix(0);
+        const int32_t* nb = rec.nb(0);
+        const bool same = rec.r[10] - 1 == 0;    // neural ellipsoid == mixture's
+        const bool has_emu = nb[3] > 0;
+        __syncthreads();                         // the previous bound is done
+        for (int e = threadIdx.x; e < d * d; e += EX_THREADS) {
+          stM[e] = __ldg(data + mix[5] + e);
+          if (!same) stN[e] = __ldg(data + nb[1] + e);
         }
+        for (int e = threadIdx.x; e < d; e += EX_THREADS) {
+          stV[e] = __ldg(data + mix[3] + e);
+          stV[d + e] = __ldg(data + nb[0] + e);
+          if (has_emu) {
+            stV[2 * d + e] = __ldg(data + nb[5] + e);
+            stV[3 * d + e] = 1.0 / __ldg(data + nb[6] + e);
+          }
+        }
+        __syncthreads();
+        if (!valid || out) continue;
+        // Union.contains (union.py:285-289): the mixture's ellipsoid + cube
+        for (int q = 0; q < d; ++q) s[q] = x[q] - stV[q];
+        double r2 = 0.0;
+        matvec_rows_sm(stM, d, mix[6], s, [&](int i, double v) {
+          r2 = fma(v, v, r2);
+          if (same && has_emu)
+            f[i] = (float)((v - stV[2 * d + i]) * stV[3 * d + i]);
+        });
+        bool in = r2 < 1.0;
+        if (in && rec.unit()) in = cube_ok(x, nullptr, d);
         if (!in) continue;
-        const int J = rec.kind() == 1 ? rec.J() : 0;
-        if (J == 0) { out = true; break; }
-        for (int j = 0; j < J; ++j) {
-          const int32_t* nb = rec.nb(j);
-          const bool has_emu = nb[3] > 0;
-          const double* cN = data + nb[0];
-          const double* mean = data + nb[5];
-          const double* scale = data + nb[6];
-          // NeuralBound.contains (neural.py:115-119): ellipsoid test and the
-          // whitened coordinates, standardised for the emulator
-          // (nautilus/neural.py:115) exactly as k_standardise_tf32 does
-          for (int q = 0; q < d; ++q) s[q] = x[q] - __ldg(cN + q);
-          double r2 = 0.0;
-          matvec_rows(data + nb[1], d, nb[2], s, [&](int i, double v) {
+        // NeuralBound.contains (neural.py:115-119)
+        if (!same) {
+          for (int q = 0; q < d; ++q) s[q] = x[q] - stV[d + q];
+          r2 = 0.0;
+          matvec_rows_sm(stN, d, nb[2], s, [&](int i, double v) {
             r2 = fma(v, v, r2);
-            if (has_emu)
-              f[i] = (float)((v - __ldg(mean + i)) * (1.0 / __ldg(scale + i)));
+            if (has_emu) f[i] = (float)((v - stV[2 * d + i]) * stV[3 * d + i]);
           });
           if (!(r2 < 1.0)) continue;
-          if (!has_emu) { out = true; break; }
-          const int p = pair_base[l] + j;
-          const unsigned int slot = atomicAdd(seg_count + p, 1u);
-          const long long row = (long long)p * seg_stride + slot;
-          float* dst = xs + row * (long long)k0p;
-          for (int q = 0; q < k0p; ++q) {
-            const float v = q < d ? f[q] : (q == d ? 1.0f : 0.0f);
-            uint32_t rr;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
-            dst[q] = __uint_as_float(rr);
-          }
-          cid[row] = (unsigned int)(c);
         }
+        if (!has_emu) { out = true; continue; }
+        excl_append(f, d, k0p, f16, pair_base[l], c, seg_count, xs, cid,
+                    seg_stride);
+        continue;
       }
-      if (out) excl[c] = 1;
+      // ---- any other bound: parameters read through the cache --------------
+      if (!valid || out) continue;
+      // Union.contains (union.py:285-289); a cube record is the unit cube
+      bool in;
+      if (rec.kind() == 0) {
+        in = cube_ok(x, nullptr, d);
+      } else {
+        in = union_count(rec, data, x, s) > 0;
+        if (in && rec.unit()) in = cube_ok(x, nullptr, d);
+      }
+      if (!in) continue;
+      const int J = rec.kind() == 1 ? rec.J() : 0;
+      if (J == 0) { out = true; continue; }
+      for (int j = 0; j < J; ++j) {
+        const int32_t* nb = rec.nb(j);
+        const bool has_emu = nb[3] > 0;
+        const double* cN = data + nb[0];
+        const double* mean = data + nb[5];
+        const double* scale = data + nb[6];
+        // NeuralBound.contains (neural.py:115-119): ellipsoid test and the
+        // whitened coordinates, standardised for the emulator
+        // (nautilus/neural.py:115) exactly as k_standardise_tf32 does
+        for (int q = 0; q < d; ++q) s[q] = x[q] - __ldg(cN + q);
+        double r2 = 0.0;
+        matvec_rows(data + nb[1], d, nb[2], s, [&](int i, double v) {
+          r2 = fma(v, v, r2);
+          if (has_emu)
+            f[i] = (float)((v - __ldg(mean + i)) * (1.0 / __ldg(scale + i)));
+        });
+        if (!(r2 < 1.0)) continue;
+        if (!has_emu) { out = true; break; }
+        excl_append(f, d, k0p, f16, pair_base[l] + j, c, seg_count, xs, cid,
+                    seg_stride);
+      }
     }
+    if (valid && out) excl[c] = 1;
     __syncthreads();
   }
 }
@@ -146,8 +258,9 @@ __global__ void k_excl_apply(const unsigned long long* __restrict__ cand_idx,
 // ---- host wrappers ----------------------------------------------------------
 
 int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
-                      PairRec* pairs, int* pair_base, cudaStream_t st) {
-  k_excl_pairs<<<1, 32, 0, st>>>(meta_d, first_later, n_later, pairs,
+                      int f16, PairRec* pairs, int* pair_base,
+                      cudaStream_t st) {
+  k_excl_pairs<<<1, 32, 0, st>>>(meta_d, first_later, n_later, f16, pairs,
                                  pair_base);
   NB_LAUNCH_OK();
   return 0;
@@ -155,11 +268,12 @@ int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
 
 size_t excl_prep_smem(int d, int k0p) {
   return (size_t)EX_THREADS * (2 * (size_t)(d | 1) * sizeof(double) +
-                               (size_t)k0p * sizeof(float));
+                               (size_t)k0p * sizeof(float)) +
+         (2 * (size_t)d * d + 4 * (size_t)d) * sizeof(double);
 }
 
 int launch_excl_prep(const int32_t* meta_d, const double* data_d,
-                     int first_later, int n_later, int d, int k0p,
+                     int first_later, int n_later, int d, int k0p, int f16,
                      const double* points, const unsigned long long* cand_idx,
                      const unsigned long long* n_cand, long long chunk_lo,
                      long long chunk_cap, const int* pair_base,
@@ -178,8 +292,9 @@ int launch_excl_prep(const int32_t* meta_d, const double* data_d,
   if (grid > 4 * resident) grid = 4 * resident;
   if (grid < 1) grid = 1;
   k_excl_prep<<<(unsigned)grid, EX_THREADS, smem, st>>>(
-      meta_d, data_d, first_later, n_later, d, k0p, points, cand_idx, n_cand,
-      chunk_lo, chunk_cap, pair_base, seg_count, xs, cid, seg_stride, excl);
+      meta_d, data_d, first_later, n_later, d, k0p, f16, points, cand_idx,
+      n_cand, chunk_lo, chunk_cap, pair_base, seg_count, xs, cid, seg_stride,
+      excl);
   NB_LAUNCH_OK();
   return 0;
 }

@@ -21,6 +21,7 @@
 
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
+#include "nb200_tc.cuh"
 
 namespace nb200 {
 
@@ -46,6 +47,7 @@ struct FrontArgs {
   // gather mode (nb200_materialize): proposal i is the GLOBAL proposal index
   // gather[i]; only the row is written (bit-identical to the cycle's)
   const unsigned long long* gather;
+  int xs_f16;             // emulator input rows in fp16 (NB200_MLP_F16)
 };
 
 __device__ __forceinline__ unsigned long long front_index(const FrontArgs& A,
@@ -266,11 +268,13 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
     double r2_nb[FRONT_PTS] = {-1.0, -1.0};
     auto whiten_store = [&](const bool (&want)[FRONT_PTS]) {
       if (!(want[0] || want[1])) return;
-      float* xrow0 = xs32 + gi[0] * (long long)A.k0p;
-      float* xrow1 = xs32 + gi[1] * (long long)A.k0p;
+      // row pointers in 32-bit words: k0p tf32 values or k0p / 2 fp16 pairs
+      const int xw = A.xs_f16 ? A.k0p >> 1 : A.k0p;
+      uint32_t* xrow0 = reinterpret_cast<uint32_t*>(xs32) + gi[0] * (long long)xw;
+      uint32_t* xrow1 = reinterpret_cast<uint32_t*>(xs32) + gi[1] * (long long)xw;
       double r20 = 0.0, r21 = 0.0;
       for (int i0 = 0; i0 < A.k0p; i0 += 8) {
-        uint32_t pk0[8], pk1[8];
+        float f0[8], f1[8];
         if (i0 < d8) {
           double a0[8], a1[8];
           mv8x2<true, false>(nbT, d8, i0, A.lower_n ? min(i0 + 8, d) : d,
@@ -280,16 +284,31 @@ k_front(const FrontArgs A, const int32_t* __restrict__ meta,
             r20 = fma(a0[q], a0[q], r20);
             r21 = fma(a1[q], a1[q], r21);
             const double mq = meanN[i0 + q], iq = iscaleN[i0 + q];
-            float v0 = (float)((a0[q] - mq) * iq);
-            float v1 = (float)((a1[q] - mq) * iq);
-            if (i0 + q == d) { v0 = 1.0f; v1 = 1.0f; }
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk0[q]) : "f"(v0));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk1[q]) : "f"(v1));
+            f0[q] = (float)((a0[q] - mq) * iq);
+            f1[q] = (float)((a1[q] - mq) * iq);
+            if (i0 + q == d) { f0[q] = 1.0f; f1[q] = 1.0f; }
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            pk0[q] = pk1[q] = (i0 + q == d) ? 0x3F800000u : 0u;
+            f0[q] = f1[q] = (i0 + q == d) ? 1.0f : 0.0f;
+        }
+        if (A.xs_f16) {
+          if (want[0])
+            *reinterpret_cast<uint4*>(xrow0 + (i0 >> 1)) = make_uint4(
+                pack_f16x2(f0[0], f0[1]), pack_f16x2(f0[2], f0[3]),
+                pack_f16x2(f0[4], f0[5]), pack_f16x2(f0[6], f0[7]));
+          if (want[1])
+            *reinterpret_cast<uint4*>(xrow1 + (i0 >> 1)) = make_uint4(
+                pack_f16x2(f1[0], f1[1]), pack_f16x2(f1[2], f1[3]),
+                pack_f16x2(f1[4], f1[5]), pack_f16x2(f1[6], f1[7]));
+          continue;
+        }
+        uint32_t pk0[8], pk1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk0[q]) : "f"(f0[q]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk1[q]) : "f"(f1[q]));
         }
         if (want[0]) {
           *reinterpret_cast<uint4*>(xrow0 + i0) =
@@ -372,7 +391,8 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
                      uint64_t offset, uint32_t stream_id, double* points,
                      uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
                      const double* like_p, double* log_l,
-                     const unsigned long long* gather, cudaStream_t st);
+                     const unsigned long long* gather, int xs_f16,
+                     cudaStream_t st);
 
 // NB200_FRONT=dfma forces the DFMA kernel (A/B measurements, tests)
 static bool front_mma_wanted() {
@@ -423,18 +443,21 @@ int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  uint64_t offset, uint32_t stream_id, double* points,
                  uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
                  const double* like_p, double* log_l,
-                 const unsigned long long* gather, cudaStream_t st) {
+                 const unsigned long long* gather, int xs_f16,
+                 cudaStream_t st) {
   if (front_mma_wanted() &&
       front_mma_applicable(meta_h, bound, nullptr, nullptr))
     return launch_front_mma(meta_h, meta_d, data_d, bound, n, seed, offset,
                             stream_id, points, code, maskj, xs32, like_id,
-                            like_p, log_l, gather, st);
+                            like_p, log_l, gather, xs_f16, st);
   FrontArgs A;
   size_t smem = 0;
   NB_CHECK(front2_applicable(meta_h, bound, &smem, &A), "front kernel n/a");
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
   A.gather = gather;
+  A.xs_f16 = xs_f16;
+  if (xs_f16) A.k0p = (A.d + 1 + 15) / 16 * 16;
   NB_CUDA(cudaFuncSetAttribute(k_front,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));

@@ -26,6 +26,7 @@
 // other inside the loop.
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
+#include "nb200_tc.cuh"
 
 namespace nb200 {
 
@@ -48,6 +49,9 @@ struct FrontMmaArgs {
   // written -- same instructions in the same order as the cycle's launch, so
   // the regenerated row is bit-identical to the one the cycle produced
   const unsigned long long* gather;
+  // emulator input rows in fp16 (NB200_MLP_F16): k0p halves per row, two to
+  // a 32-bit word, instead of k0p tf32 words
+  int xs_f16;
 };
 
 // global proposal index (the Philox counter) of local proposal i
@@ -266,7 +270,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
       }
     }
 #pragma unroll
-    for (int I = 0; I < nI + 1; ++I) {
+    for (int I = 0; I < nI + 2; ++I) {
       if (8 * I >= A.k0p) break;
       double T[4][2];
       if (I < nI) {
@@ -290,14 +294,22 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
         float v1 = (float)((T[g][1] - m1) * s1);
         if (i0 >= d) v0 = i0 == d ? 1.0f : 0.0f;
         if (i0 + 1 >= d) v1 = i0 + 1 == d ? 1.0f : 0.0f;
-        uint32_t k0, k1;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
         const long long gi = base + 8 * g + p;
         // rows cut by the unit cube are never looked at by the emulator
-        if (gi < A.n && (!A.unit || ((cube_bits >> g) & 1u)))
-          *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
-              make_uint2(k0, k1);
+        const bool wanted =
+            gi < A.n && (!A.unit || ((cube_bits >> g) & 1u));
+        if (A.xs_f16) {
+          if (wanted)
+            reinterpret_cast<uint32_t*>(xs32)[gi * (long long)(A.k0p >> 1) +
+                                              (i0 >> 1)] = pack_f16x2(v0, v1);
+        } else {
+          uint32_t k0, k1;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
+          if (wanted)
+            *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
+                make_uint2(k0, k1);
+        }
       }
     }
 #pragma unroll
@@ -375,7 +387,8 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
                      uint64_t offset, uint32_t stream_id, double* points,
                      uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
                      const double* like_p, double* log_l,
-                     const unsigned long long* gather, cudaStream_t st) {
+                     const unsigned long long* gather, int xs_f16,
+                     cudaStream_t st) {
   FrontMmaArgs A;
   size_t smem = 0;
   NB_CHECK(front_mma_applicable(meta_h, bound, &smem, &A),
@@ -383,6 +396,8 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
   A.seed = seed; A.offset = offset; A.stream_id = stream_id; A.n = n;
   A.like_id = like_id; A.like_p = like_p; A.log_l = log_l;
   A.gather = gather;
+  A.xs_f16 = xs_f16;
+  if (xs_f16) A.k0p = (A.d + 1 + 15) / 16 * 16;
   void (*kern)(const FrontMmaArgs, const int32_t*, const double*, double*,
                uint8_t*, uint8_t*, float*) = nullptr;
   switch (A.d8) {

@@ -761,14 +761,16 @@ static int launch_apply(int mode, int64_t n, uint8_t* code, uint8_t* cand,
 int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
                     int j, const double* t_rows, const uint8_t* mask,
                     int64_t n, double* score_out, uint8_t* passf,
-                    float* xs32_ws, cudaStream_t st);
+                    float* xs32_ws, int mode, cudaStream_t st);
 
 int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
                          double log_l_min, double* log_l, void* partial,
-                         int* n_partial_out, cudaStream_t st);
-bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j);
+                         int* n_partial_out, int mode, cudaStream_t st);
+bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j, int mode);
+const int32_t* tc_header_words(const int32_t* meta_h, int bound, int j,
+                               int mode);
 bool front_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
                       struct FrontArgs* args);
 int launch_front(const int32_t* meta_h, const int32_t* meta_d,
@@ -776,7 +778,8 @@ int launch_front(const int32_t* meta_h, const int32_t* meta_d,
                  uint64_t offset, uint32_t stream_id, double* points,
                  uint8_t* code, uint8_t* maskj, float* xs32, int like_id,
                  const double* like_p, double* log_l,
-                 const unsigned long long* gather, cudaStream_t st);
+                 const unsigned long long* gather, int xs_f16,
+                 cudaStream_t st);
 
 // emulator of neural bound j on whitened rows; ORs into passf and/or writes
 // the scores.
@@ -790,9 +793,9 @@ static int launch_mlp(const int32_t* meta_h, const int32_t* meta_d,
   const int32_t* nb = rec.nb(j);
   NB_CHECK(nb[3] > 0, "neural bound has no emulator");
   ProfScope prof(ST_MLP, st);
-  if (mlp_mode == NB200_MLP_TF32)
+  if (mode_tc(mlp_mode))
     return launch_mlp_tf32(meta_h, data_d, bound, j, t_rows, mask, n,
-                           score_out, passf, xs32_ws, st);
+                           score_out, passf, xs32_ws, mlp_mode, st);
   NB_CHECK(mlp_mode == NB200_MLP_F64, "unknown mlp_mode");
   const int d = rec.d();
   const int32_t* sizes = rec.r + nb[8];
@@ -864,10 +867,11 @@ static int union_contains_launch(const int32_t* meta_h, const int32_t* meta_d,
 
 // ---- grouped later-bound exclusion (csrc/nb200_exclude.cu) ------------------
 int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
-                      PairRec* pairs, int* pair_base, cudaStream_t st);
+                      int f16, PairRec* pairs, int* pair_base,
+                      cudaStream_t st);
 size_t excl_prep_smem(int d, int k0p);
 int launch_excl_prep(const int32_t* meta_d, const double* data_d,
-                     int first_later, int n_later, int d, int k0p,
+                     int first_later, int n_later, int d, int k0p, int f16,
                      const double* points, const unsigned long long* cand_idx,
                      const unsigned long long* n_cand, long long chunk_lo,
                      long long chunk_cap, const int* pair_base,
@@ -929,7 +933,7 @@ static size_t excl_layout(int64_t n, int P, int n_later, int k0p, char* base,
 // *n_pairs = (later bound, neural bound) pairs; *hdr = the tensor-core header
 // shared by every pair that has an emulator (nullptr: none has one)
 static bool excl_applicable(const int32_t* meta_h, int first_later,
-                            int n_later, int d, int* n_pairs,
+                            int n_later, int d, int mode, int* n_pairs,
                             const int32_t** hdr) {
   const char* e = getenv("NB200_EXCLUDE");
   if (e && strcmp(e, "loop") == 0) return false;
@@ -943,11 +947,14 @@ static bool excl_applicable(const int32_t* meta_h, int first_later,
     for (int j = 0; j < rec.J(); ++j, ++P) {
       const int32_t* nb = rec.nb(j);
       if (nb[3] <= 0) continue;                     // ellipsoid only
-      if (nb[10] < 0 || nb[11] <= 0) return false;  // no tensor-core blob
-      const int32_t* h = rec.r + nb[11];
-      if ((h[0] & 0xFFFF) != 0x7F32 || (h[0] >> 16) < 1) return false;
+      const int32_t* h = tc_header_words(meta_h, l, j, mode);
+      if (!h) return false;                // no resident tensor-core blob
+      // one architecture for all pairs (words 20..23 of the fp16 header
+      // hold the blob's position, words 30, 31 the threshold)
       if (!first) first = h;
-      else if (memcmp(first, h, 30 * sizeof(int32_t)) != 0) return false;
+      else if (memcmp(first, h, 20 * sizeof(int32_t)) != 0 ||
+               memcmp(first + 24, h + 24, 6 * sizeof(int32_t)) != 0)
+        return false;
     }
   }
   if (P > 1 << 15) return false;
@@ -1303,11 +1310,10 @@ int nb200_materialize(const int32_t* meta_h, const int32_t* meta_d,
   const unsigned long long* gather = (const unsigned long long*)index_d;
   // the SAME kernel the cycle would run for this bound and emulator
   // arithmetic (their sums round differently)
-  if (mlp_mode == NB200_MLP_TF32 &&
-      front_applicable(meta_h, bound, nullptr, nullptr))
+  if (mode_tc(mlp_mode) && front_applicable(meta_h, bound, nullptr, nullptr))
     return launch_front(meta_h, meta_d, data_d, bound, k, seed, 0, stream_id,
                         points_out_d, nullptr, nullptr, nullptr, -1, nullptr,
-                        nullptr, gather, st);
+                        nullptr, gather, 0, st);
   const Rec rec = record(meta_h, bound);
   const int d = rec.d();
   const int threads = threads_for(d);
@@ -1342,8 +1348,11 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
   Workspace ws;
   workspace_layout(n < 1 ? 1 : n, d, (char*)workspace_d, &ws);
   int rc;
-  const bool fused = mlp_mode == NB200_MLP_TF32 && n > 0 &&
+  const bool fused = mode_tc(mlp_mode) && n > 0 &&
                      front_applicable(meta_h, bound, nullptr, nullptr);
+  if (fused && mlp_mode == NB200_MLP_F16)
+    NB_CHECK(mlp_tf32_resident(meta_h, bound, 0, NB200_MLP_F16),
+             "this emulator has no fp16 tensor-core blob; use NB200_MLP_TF32");
   bool fused_tail = false;
   int n_partial = 0;
   if (fused) {
@@ -1352,20 +1361,22 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
     // candidate (it holds the row on chip anyway), the emulator kernel sums
     // the survivors
     fused_tail = n_later == 0 && like_id >= 0 && lse_d && counters_d &&
-                 mlp_tf32_resident(meta_h, bound, 0);
+                 mlp_tf32_resident(meta_h, bound, 0, mlp_mode);
     // 1+2 fused: proposal, cube cut, overlap acceptance, neural-ellipsoid
     // whitening and standardisation in one fp64 kernel, then the emulator on
     // tensor cores writes NN rejects straight into the disposition bytes
     rc = launch_front(meta_h, meta_d, data_d, bound, n, seed, offset,
                       stream_id, points_d, code_d, ws.maskj, ws.xs32,
                       fused_tail ? like_id : -1, like_params_d,
-                      fused_tail ? log_l_d : nullptr, nullptr, st);
+                      fused_tail ? log_l_d : nullptr, nullptr,
+                      mlp_mode == NB200_MLP_F16, st);
     if (rc) return rc;
     {
       ProfScope prof(ST_MLP, st);
       rc = launch_mlp_tf32_rows(
           meta_h, data_d, bound, 0, ws.xs32, ws.maskj, n, code_d, log_l_min,
-          log_l_d, fused_tail ? (void*)ws.partial : nullptr, &n_partial, st);
+          log_l_d, fused_tail ? (void*)ws.partial : nullptr, &n_partial,
+          mlp_mode, st);
     }
     if (rc) return rc;
     if (fused_tail) {
@@ -1400,17 +1411,21 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
     bool grouped = false;
     int n_pairs = 0;
     const int32_t* hdr = nullptr;
-    if (n_later > 0 && mlp_mode == NB200_MLP_TF32 &&
-        excl_applicable(meta_h, first_later, n_later, d, &n_pairs, &hdr)) {
+    if (n_later > 0 && mode_tc(mlp_mode) &&
+        excl_applicable(meta_h, first_later, n_later, d, mlp_mode, &n_pairs,
+                        &hdr)) {
       const size_t base_bytes = nb200_workspace_bytes(n, d);
+      const bool f16 = mlp_mode == NB200_MLP_F16;
+      // (scratch rows are sized for the tf32 form; the fp16 rows are shorter)
       const int k0p = k0p_of(d);
+      const int k0p_rows = f16 ? (d + 1 + 15) / 16 * 16 : k0p;
       ExclWs ew;
       excl_layout(n, n_pairs, n_later, k0p, (char*)workspace_d + base_bytes,
                   workspace_bytes - base_bytes, -1, &ew);
       if (ew.cap >= 1024 || ew.cap * 1 >= (n + 127) / 128 * 128) {
         grouped = true;
         ProfScope prof(ST_UNION, st);
-        rc = launch_excl_pairs(meta_d, first_later, n_later, ew.pairs,
+        rc = launch_excl_pairs(meta_d, first_later, n_later, f16, ew.pairs,
                                ew.pair_base, st);
         if (rc) return rc;
         // candidates = proposals still in the shell
@@ -1430,8 +1445,10 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
           // lives on the device, the number of passes must not)
           NB_CUDA(cudaMemsetAsync(ew.seg_count, 0,
                                   sizeof(unsigned int) * (size_t)(n_pairs > 0 ? n_pairs : 1), st));
-          rc = launch_excl_prep(meta_d, data_d, first_later, n_later, d, k0p,
-                                points_d, ew.cand_idx, n_cand, lo, ew.cap,
+          ProfScope prof_prep(ST_PREP, st);
+          rc = launch_excl_prep(meta_d, data_d, first_later, n_later, d,
+                                k0p_rows, f16, points_d, ew.cand_idx, n_cand,
+                                lo, ew.cap,
                                 ew.pair_base, ew.seg_count, ew.xs, ew.cid,
                                 ew.cap, ew.excl, st);
           if (rc) return rc;
@@ -1440,6 +1457,7 @@ int nb200_cycle(const int32_t* meta_h, const int32_t* meta_d,
             G.n_pairs = n_pairs; G.chunk_lo = lo; G.seg_stride = ew.cap;
             G.pairs = ew.pairs; G.seg_count = ew.seg_count; G.n_cand = n_cand;
             G.cid = ew.cid; G.data = data_d; G.excl = ew.excl;
+            ProfScope prof_mlp(ST_GLUE, st);
             rc = run_mlp_tf32_grouped(hdr, ew.xs, G, st);
             if (rc) return rc;
           }

@@ -104,7 +104,19 @@ __device__ __forceinline__ void pair_sync(int id) {
 // the epilogue warps arrive on s0/s1/s2/sA when the operand they produced (or
 // the region they finished reading) is ready -- nobody waits at a CTA
 // barrier, a fast warp runs ahead.
-template <bool GROUPED>
+// F16: the kind::f16 form (fp16 operands, fp32 accumulate; header and blob of
+// _pack.py:pack_tc16).  Two fp16 values share one 32-bit TMEM column of an A
+// operand, so an epilogue thread packs PAIRS of accumulator columns: the two
+// threads of a TMEM lane own disjoint column ranges [0, h0) and [h0, N) of
+// the accumulator (h0 = split16(N)) and write their packed halves in place at
+// the start of their own range -- the A operand of the next layer therefore
+// sits in two pieces, which costs nothing because the issuer passes the A
+// address of every K step explicitly.
+__host__ __device__ __forceinline__ int split16(int n) {
+  return (n + 31) / 32 * 16;
+}
+
+template <bool GROUPED, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
            const float* __restrict__ xs32_arg,
@@ -119,6 +131,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
   __shared__ uint32_t tmem_slot;
   __shared__ float part[TC_GROUPS][128];
   __shared__ uint4 mma_tab[TC_MAX_HID];       // {d_col, a_col, idesc, k steps}
+  __shared__ int a_split[TC_MAX_HID];         // F16: K steps in A's 1st piece
   __shared__ uint64_t desc_tab[TC_MAX_HID];   // weight descriptor of network 0
 
   const int tid = threadIdx.x;
@@ -149,9 +162,13 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
     mma_tab[l] = make_uint4(
         (uint32_t)h.d_col[l],
         (uint32_t)(l == 0 ? h.a0_col : h.d_col[l - 1]),
-        idesc_tf32(h.np[l]), (uint32_t)(h.kp[l] >> 3));
+        F16 ? idesc_f16(h.np[l]) : idesc_tf32(h.np[l]),
+        (uint32_t)(h.kp[l] >> (F16 ? 4 : 3)));
+    // (an 8-row group of the K-major operand is kp * 16 B of fp16 / kp * 32 B
+    // of tf32 away from the next)
     desc_tab[l] = smem_desc(smem_u32(smem) + 4u * (uint32_t)h.w_off[l], 128u,
-                            (uint32_t)h.kp[l] * 32u);
+                            (uint32_t)h.kp[l] * (F16 ? 16u : 32u));
+    a_split[l] = l == 0 ? (1 << 20) : split16(h.np[l - 1]) >> 4;
   }
   __syncthreads();
   float* wsm = (float*)smem;
@@ -226,7 +243,9 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
     blob = reinterpret_cast<const float*>(G.data + pr.blob_off);
     thr = G.data[pr.thr_off];
     seg_row0 = (int64_t)seg * G.seg_stride;
-    xs32 = xs32_arg + seg_row0 * (int64_t)h.k0p;
+    xs32 = reinterpret_cast<const float*>(
+        reinterpret_cast<const uint32_t*>(xs32_arg) +
+        seg_row0 * (int64_t)(F16 ? h.k0p >> 1 : h.k0p));
     n = (int64_t)G.seg_count[seg];
     n_tiles = hi;
     tile_step = n_groups;
@@ -274,11 +293,23 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
         const uint32_t d_tmem = tmem_base_u + t.x;
         const uint32_t a_tmem = tmem_base_u + t.y;
         const int ks = (int)t.w;
-        for (int s = 0; s < ks; ++s) {
-          // one K-step = 2 core matrices = 256 B -> +16 in the 16-B units
-          // of the descriptor's start-address field
-          mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(s * 8),
-                      desc0 + (uint64_t)(s * 16), t.z, s > 0 ? 1u : 0u);
+        if (F16) {
+          // A's second piece starts at column h0 of the previous
+          // accumulator: K step s >= sp lives 8 (s - sp) columns behind it
+          const int sp = a_split[l];
+          for (int s = 0; s < ks; ++s) {
+            const uint32_t a_col = s < sp ? (uint32_t)(s * 8)
+                                          : (uint32_t)(sp * 16 + (s - sp) * 8);
+            mma_f16_ts(d_tmem, a_tmem + a_col, desc0 + (uint64_t)(s * 16),
+                       t.z, s > 0 ? 1u : 0u);
+          }
+        } else {
+          for (int s = 0; s < ks; ++s) {
+            // one K-step = 2 core matrices = 256 B -> +16 in the 16-B units
+            // of the descriptor's start-address field
+            mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(s * 8),
+                        desc0 + (uint64_t)(s * 16), t.z, s > 0 ? 1u : 0u);
+          }
         }
         mma_commit(bar);
       }
@@ -335,7 +366,10 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
     // (k0p <= 32: 4 x 16 B), the candidate flag, and for the fused tail the
     // disposition byte and the likelihood the front kernel already
     // evaluated.  None of the loads depends on another one.
-    const bool prefetch = h.k0p <= 32;
+    // 32-bit words of one input row: k0p tf32 values, or k0p / 2 fp16 pairs
+    const int xw = F16 ? h.k0p >> 1 : h.k0p;
+    const uint32_t* xrows = reinterpret_cast<const uint32_t*>(xs32);
+    const bool prefetch = xw <= 32;
     uint4 pre[4];
     uint32_t nx_mask = 0, nx_cd = NB200_CODE_IN_SHELL;
     double nx_ll = 0.0;
@@ -349,11 +383,10 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
           nx_ll = tail.log_l[rw];
         }
         if (prefetch) {
-          const uint4* src =
-              (const uint4*)(xs32 + rw * (int64_t)h.k0p) + hf * 4;
+          const uint4* src = (const uint4*)(xrows + rw * (int64_t)xw) + hf * 4;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (hf * 16 + q * 4 < h.k0p) pre[q] = __ldg(src + q);
+            if (hf * 16 + q * 4 < xw) pre[q] = __ldg(src + q);
         }
       }
     };
@@ -370,7 +403,7 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = hf * 16 + q * 8;
-          if (c < h.k0p) {
+          if (c < xw) {
             uint32_t v[8];
             const uint4 a = active ? pre[2 * q] : make_uint4(0, 0, 0, 0);
             const uint4 b = active ? pre[2 * q + 1] : make_uint4(0, 0, 0, 0);
@@ -381,8 +414,8 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
         }
       } else {
         const int64_t rw = t * 128 + r;
-        const uint4* src = (const uint4*)(xs32 + rw * (int64_t)h.k0p);
-        for (int c = hf * 8; c < h.k0p; c += 16) {
+        const uint4* src = (const uint4*)(xrows + rw * (int64_t)xw);
+        for (int c = hf * 8; c < xw; c += 16) {
           uint32_t v[8];
           if (active) {
             const uint4 a = __ldg(src + (c >> 2));
@@ -405,6 +438,33 @@ k_mlp_tf32(const TcHeader h, const float* __restrict__ blob_arg,
     auto epi_hidden = [&](int l, uint64_t* done) {
       tc_fence_after();
       const uint32_t d_addr = tmem_base + lane_addr + (uint32_t)h.d_col[l];
+      if (F16) {
+        // this thread's own accumulator columns [c0, c1): ReLU, round to
+        // fp16, two values per 32-bit column, written back at the start of
+        // the range (always behind what has been read)
+        const int h0 = split16(h.np[l]);
+        const int c0 = hf ? h0 : 0, c1 = hf ? h.np[l] : h0;
+        int c = c0;
+        for (; c + 32 <= c1; c += 32) {
+          uint32_t v[32], w[16];
+          tmem_ld32(d_addr + (uint32_t)c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) w[q] = relu_f16x2(v[2 * q], v[2 * q + 1]);
+          tmem_st16(d_addr + (uint32_t)(c0 + ((c - c0) >> 1)), w);
+        }
+        if (c < c1) {                      // a last group of 16 columns
+          uint32_t v[16], w[8];
+          tmem_ld16(d_addr + (uint32_t)c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) w[q] = relu_f16x2(v[2 * q], v[2 * q + 1]);
+          tmem_st8(d_addr + (uint32_t)(c0 + ((c - c0) >> 1)), w);
+        }
+        tmem_wait_st();
+        signal(done);
+        return;
+      }
       // 32 columns per TMEM load (the accumulator regions are 32-column
       // aligned; pad columns meet zero weights), halves interleaved
       for (int c = hf * 32; c < h.np[l]; c += 64) {
@@ -619,6 +679,32 @@ __global__ void k_standardise_tf32(const double* __restrict__ t_rows,
   xs32[e] = __uint_as_float(rr);
 }
 
+// ... and the fp16 form: k0p halves per row, two to a 32-bit word
+__global__ void k_standardise_f16(const double* __restrict__ t_rows,
+                                  const uint8_t* __restrict__ mask, int64_t n,
+                                  int d, int k0p,
+                                  const double* __restrict__ mean,
+                                  const double* __restrict__ scale,
+                                  uint32_t* __restrict__ xs16) {
+  const int words = k0p >> 1;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * words) return;
+  const int64_t row = e / words;
+  const int k = 2 * (int)(e - row * words);
+  float v[2] = {0.f, 0.f};
+  if (!mask || mask[row]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (k + q < d)
+        v[q] = (float)((t_rows[row * d + k + q] - __ldg(mean + k + q)) *
+                       (1.0 / __ldg(scale + k + q)));
+      else if (k + q == d)
+        v[q] = 1.0f;
+    }
+  }
+  xs16[e] = pack_f16x2(v[0], v[1]);
+}
+
 int run_mlp_tf32_streamed(const int32_t* hdr, const float* blob,
                           const float* xs32, const uint8_t* mask, int64_t n,
                           double* score_out, uint8_t* passf, uint8_t* code,
@@ -641,7 +727,10 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
   if (smem < 120 * 1024) smem = 120 * 1024;
-  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<false>,
+  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<false, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<false, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   int dev = 0, sms = 0;
@@ -656,8 +745,12 @@ static int run_mlp_tf32(const TcHeader& h, const float* blob,
   if (grid_out) *grid_out = (int)grid;
   TcGroupArgs none;
   memset(&none, 0, sizeof(none));
-  k_mlp_tf32<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(
-      h, blob, xs32, mask, n, score_out, passf, code, tail, none);
+  if ((h.magic & 0xFFFF) == 0x7F16)
+    k_mlp_tf32<false, true><<<(unsigned)grid, TC_THREADS, smem, st>>>(
+        h, blob, xs32, mask, n, score_out, passf, code, tail, none);
+  else
+    k_mlp_tf32<false, false><<<(unsigned)grid, TC_THREADS, smem, st>>>(
+        h, blob, xs32, mask, n, score_out, passf, code, tail, none);
   NB_LAUNCH_OK();
   return 0;
 }
@@ -673,63 +766,103 @@ int run_mlp_tf32_grouped(const int32_t* hdr32, const float* xs_segments,
   size_t smem = (size_t)h.total_floats * 4;
   NB_CHECK(smem <= 220 * 1024, "emulator weights exceed shared memory");
   if (smem < 120 * 1024) smem = 120 * 1024;
-  NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
+  const bool f16 = (h.magic & 0xFFFF) == 0x7F16;
+  if (f16)
+    NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<true, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  else
+    NB_CUDA(cudaFuncSetAttribute(k_mlp_tf32<true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
   int dev = 0, sms = 0;
   NB_CUDA(cudaGetDevice(&dev));
   NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TcTail tail;
   memset(&tail, 0, sizeof(tail));
-  k_mlp_tf32<true><<<(unsigned)sms, TC_THREADS, smem, st>>>(
-      h, nullptr, xs_segments, nullptr, 0, nullptr, nullptr, nullptr, tail,
-      G);
+  if (f16)
+    k_mlp_tf32<true, true><<<(unsigned)sms, TC_THREADS, smem, st>>>(
+        h, nullptr, xs_segments, nullptr, 0, nullptr, nullptr, nullptr, tail,
+        G);
+  else
+    k_mlp_tf32<true, false><<<(unsigned)sms, TC_THREADS, smem, st>>>(
+        h, nullptr, xs_segments, nullptr, 0, nullptr, nullptr, nullptr, tail,
+        G);
   NB_LAUNCH_OK();
   return 0;
 }
 
-static int tc_header(const int32_t* meta_h, int bound, int j, TcHeader* h) {
+// header and weight blob of neural bound j for the arithmetic `mode`
+// (NB200_MLP_TF32: pack_tc, NB200_MLP_F16: pack_tc16, stored right behind)
+static int tc_header(const int32_t* meta_h, const double* data_d, int bound,
+                     int j, int mode, TcHeader* h, const float** blob) {
   const Rec rec = record(meta_h, bound);
   const int32_t* nb = rec.nb(j);
   NB_CHECK(nb[10] >= 0 && nb[11] > 0,
            "this emulator has no tensor-core blob (architecture outside the "
            "NB200_MLP_TF32 envelope); use NB200_MLP_F64");
+  if (mode == NB200_MLP_F16) {
+    memcpy(h, rec.r + nb[11] + TC_HDR_WORDS, sizeof(*h));
+    NB_CHECK((h->magic & 0xFFFF) == 0x7F16 && (h->magic >> 16) >= 1 &&
+                 (h->magic >> 16) <= TC_GROUPS,
+             "this emulator has no fp16 tensor-core blob (architecture "
+             "outside the NB200_MLP_F16 envelope); use NB200_MLP_TF32");
+    if (blob) *blob = (const float*)(data_d + h->b_off[0]);
+    return 0;
+  }
   memcpy(h, rec.r + nb[11], sizeof(*h));
   NB_CHECK((h->magic & 0xFFFF) == 0x7F32 && (h->magic >> 16) >= 0 &&
                (h->magic >> 16) <= TC_GROUPS,
            "corrupt tensor-core blob header");
+  if (blob) *blob = (const float*)(data_d + nb[10]);
   return 0;
+}
+
+// the tensor-core header the grouped exclusion compares / launches with
+const int32_t* tc_header_words(const int32_t* meta_h, int bound, int j,
+                               int mode) {
+  const Rec rec = record(meta_h, bound);
+  const int32_t* nb = rec.nb(j);
+  if (nb[3] <= 0 || nb[10] < 0 || nb[11] <= 0) return nullptr;
+  const int32_t* h = rec.r + nb[11] + (mode == NB200_MLP_F16 ? TC_HDR_WORDS
+                                                             : 0);
+  const int magic = mode == NB200_MLP_F16 ? 0x7F16 : 0x7F32;
+  if ((h[0] & 0xFFFF) != magic || (h[0] >> 16) < 1) return nullptr;
+  return h;
 }
 
 // does neural bound j of `bound` run on the resident tensor-core kernel (the
 // one that can carry the fused tail)?
-bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j) {
-  const Rec rec = record(meta_h, bound);
-  const int32_t* nb = rec.nb(j);
-  if (nb[10] < 0 || nb[11] <= 0) return false;
-  TcHeader h;
-  memcpy(&h, rec.r + nb[11], sizeof(h));
-  return (h.magic & 0xFFFF) == 0x7F32 && (h.magic >> 16) >= 1;
+bool mlp_tf32_resident(const int32_t* meta_h, int bound, int j, int mode) {
+  return tc_header_words(meta_h, bound, j, mode) != nullptr;
 }
 
 // whitened fp64 rows in, scores / pass flags out
 int launch_mlp_tf32(const int32_t* meta_h, const double* data_d, int bound,
                     int j, const double* t_rows, const uint8_t* mask,
                     int64_t n, double* score_out, uint8_t* passf,
-                    float* xs32_ws, cudaStream_t st) {
+                    float* xs32_ws, int mode, cudaStream_t st) {
   TcHeader h;
-  if (tc_header(meta_h, bound, j, &h)) return 1;
+  const float* blob = nullptr;
+  if (tc_header(meta_h, data_d, bound, j, mode, &h, &blob)) return 1;
   const Rec rec = record(meta_h, bound);
   const int32_t* nb = rec.nb(j);
-  const int64_t total = n * h.k0p;
-  k_standardise_tf32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      t_rows, mask, n, rec.d(), h.k0p, data_d + nb[5], data_d + nb[6],
-      xs32_ws);
+  if (mode == NB200_MLP_F16) {
+    const int64_t total = n * (h.k0p >> 1);
+    k_standardise_f16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        t_rows, mask, n, rec.d(), h.k0p, data_d + nb[5], data_d + nb[6],
+        (uint32_t*)xs32_ws);
+  } else {
+    const int64_t total = n * h.k0p;
+    k_standardise_tf32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        t_rows, mask, n, rec.d(), h.k0p, data_d + nb[5], data_d + nb[6],
+        xs32_ws);
+  }
   NB_LAUNCH_OK();
   TcTail none;
   memset(&none, 0, sizeof(none));
-  return run_mlp_tf32(h, (const float*)(data_d + nb[10]), xs32_ws, mask, n,
-                      score_out, passf, nullptr, none, nullptr, st);
+  return run_mlp_tf32(h, blob, xs32_ws, mask, n, score_out, passf, nullptr,
+                      none, nullptr, st);
 }
 
 // standardised tf32 rows in (from k_front); rejects are written into `code`
@@ -739,17 +872,17 @@ int launch_mlp_tf32_rows(const int32_t* meta_h, const double* data_d,
                          int bound, int j, const float* xs32,
                          const uint8_t* mask, int64_t n, uint8_t* code,
                          double log_l_min, double* log_l, void* partial,
-                         int* n_partial_out, cudaStream_t st) {
+                         int* n_partial_out, int mode, cudaStream_t st) {
   TcHeader h;
-  if (tc_header(meta_h, bound, j, &h)) return 1;
-  const Rec rec = record(meta_h, bound);
+  const float* blob = nullptr;
+  if (tc_header(meta_h, data_d, bound, j, mode, &h, &blob)) return 1;
   TcTail tail;
   memset(&tail, 0, sizeof(tail));
   tail.log_l = log_l;
   tail.partial = (StatPartial*)partial; tail.log_l_min = log_l_min;
   if ((h.magic >> 16) == 0) tail.partial = nullptr;   // streamed: no tail
-  return run_mlp_tf32(h, (const float*)(data_d + rec.nb(j)[10]), xs32, mask,
-                      n, nullptr, nullptr, code, tail, n_partial_out, st);
+  return run_mlp_tf32(h, blob, xs32, mask, n, nullptr, nullptr, code, tail,
+                      n_partial_out, st);
 }
 
 #ifdef NB200_TIMELINE

@@ -56,6 +56,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with kind::f16 (fp16 x fp16 -> fp32): 16 K elements per
+// instruction, two to a 32-bit TMEM column of the A operand
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem,
+                                           uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
@@ -133,6 +145,24 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
          ((128u >> 4) << 24);
 }
 
+
+// InstrDescriptor for kind::f16: c=F32 (1<<4), a=b=F16 (format 0)
+__device__ __forceinline__ uint32_t idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// two fp32 -> packed fp16x2 with ReLU (round to nearest even, saturating to
+// the largest finite half): `lo` lands in bits 0..15
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;"
+      : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // one thread of a converged warp
 __device__ __forceinline__ bool elect_one() {

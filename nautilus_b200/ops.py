@@ -16,6 +16,7 @@ from ._pack import _Data, pack_record, pack_stack
 
 MLP_F64 = 0
 MLP_TF32 = 1
+MLP_F16 = 2
 
 LIKE_GAUSSIAN = 0
 LIKE_ROSENBROCK = 1
@@ -249,7 +250,7 @@ class DeviceStack:
         # word 4 is J
         pairs = sum(int(self.meta_h[self.meta_h[1 + b] + 4])
                     for b in range(later[0], later[0] + later[1])) \
-            if later[1] > 0 and mode == MLP_TF32 else 0
+            if later[1] > 0 and mode in (MLP_TF32, MLP_F16) else 0
         buf, nbytes = self.ws.get(n, d, pairs)
         n_par = 0 if like_params is None else like_params.numel()
         _lib.check(_lib.lib().nb200_cycle(

@@ -154,13 +154,15 @@ class Sampler:
         self.neural_network_kwargs = neural_network_kwargs
         self.vectorized = vectorized
         self.pass_dict = pass_dict
-        # 'auto': tensor cores (tf32) whenever the emulator architecture fits
-        # the tcgen05 kernel, fp64 otherwise; 'f64' is the bit-parity mode
+        # 'auto': tensor cores (fp16 operands, else tf32) whenever the emulator
+        # architecture fits the tcgen05 kernels, fp64 otherwise; 'f64' is the
+        # bit-parity mode
         self.emulator_arith = emulator_arith
         self.mlp_mode = {'f64': ops.MLP_F64, 'tf32': ops.MLP_TF32,
+                         'f16': ops.MLP_F16,
                          'auto': ops.MLP_F64}[emulator_arith]
         if emulator_arith == 'auto':
-            from ._pack import pack_tc
+            from ._pack import pack_tc, pack_tc16
             hidden = tuple(np.atleast_1d(neural_network_kwargs.get(
                 'hidden_layer_sizes', (100, 50, 20))))
             sizes = (self.n_dim, ) + tuple(int(h) for h in hidden) + (1, )
@@ -172,6 +174,10 @@ class Sampler:
             probe['intercepts'] = probe['intercepts'] * max(n_networks, 1)
             if n_networks > 0 and pack_tc(probe, 0.0) is not None:
                 self.mlp_mode = ops.MLP_TF32
+                # fp16 operands (same 10 mantissa bits, half the bytes) when
+                # the weights fit shared memory in that form
+                if pack_tc16(probe, 0.0) is not None:
+                    self.mlp_mode = ops.MLP_F16
 
         # pool = (likelihood pool, sampling pool); an int > 1 in the first
         # slot starts worker processes for a host likelihood

@@ -209,7 +209,7 @@ def test_config2_delta_log_z_and_posterior_moments():
     d = 30
     like = likelihoods.Gaussian(d, sigma=0.1)
     sampler = Sampler(lambda x: x, like, n_dim=d, n_live=2000, seed=0)
-    assert sampler.device_cycle and sampler.mlp_mode == ops.MLP_TF32
+    assert sampler.device_cycle and sampler.mlp_mode == ops.MLP_F16
     assert sampler.run(n_eff=40000, discard_exploration=True, timeout=600)
     assert sampler.n_eff >= 40000
     delta = abs(sampler.log_z - like.log_z_true)

@@ -47,7 +47,8 @@ def later_bounds(spec, L):
             for i in range(L)]
 
 
-def run(spec, later, n, like, seed, monkeypatch, which, chunk=None):
+def run(spec, later, n, like, seed, monkeypatch, which, chunk=None,
+        mode=ops.MLP_TF32):
     if which == 'loop':
         monkeypatch.setenv('NB200_EXCLUDE', 'loop')
     else:
@@ -59,13 +60,13 @@ def run(spec, later, n, like, seed, monkeypatch, which, chunk=None):
     stack = ops.DeviceStack([spec] + later)
     # warm-up call so that launch counts exclude one-time work
     stack.cycle(0, 256, later=(1, len(later)), seed=1, like_id=like.like_id,
-                like_params=like.device_params('cuda'), mode=ops.MLP_TF32)
+                like_params=like.device_params('cuda'), mode=mode)
     torch.cuda.synchronize()
     l0 = ops.launch_count()
     out = stack.cycle(0, n, later=(1, len(later)), seed=seed, offset=11,
                       stream_id=3, like_id=like.like_id,
                       like_params=like.device_params('cuda'), log_l_min=-30.0,
-                      mode=ops.MLP_TF32)
+                      mode=mode)
     torch.cuda.synchronize()
     launches = ops.launch_count() - l0
     return {k: host(v) for k, v in out.items()}, launches
@@ -123,6 +124,21 @@ def test_grouped_exclusion_launches_do_not_depend_on_L(golden, monkeypatch):
     _, loop47 = run(spec, later_bounds(spec, 47), 1 << 14, like, 2,
                     monkeypatch, 'loop')
     assert loop47 > 4 * counts[47]
+
+
+def test_grouped_exclusion_fp16_emulator(golden, monkeypatch):
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    like = likelihoods.Gaussian(30)
+    later = later_bounds(spec, 8)
+    a, la = run(spec, later, 1 << 15, like, 9, monkeypatch, 'grouped',
+                mode=ops.MLP_F16)
+    b, lb = run(spec, later, 1 << 15, like, 9, monkeypatch, 'loop',
+                mode=ops.MLP_F16)
+    assert np.array_equal(a['code'], b['code'])
+    assert np.array_equal(a['counters'], b['counters'])
+    assert a['counters'][ops.CNT_EXCLUDED] > 0 and la < lb
+    c, _ = run(spec, later, 1 << 15, like, 9, monkeypatch, 'grouped')
+    assert np.mean(a['code'] != c['code']) < 2e-3      # fp16 vs tf32
 
 
 def test_grouped_exclusion_in_several_passes(golden, monkeypatch):

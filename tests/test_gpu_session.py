@@ -144,7 +144,8 @@ def test_session_errors(golden):
 # --------------------------------------------------------------------------
 
 @pytest.mark.parametrize('mode,front', [(ops.MLP_F64, ''), (ops.MLP_TF32, ''),
-                                        (ops.MLP_TF32, 'dfma')])
+                                        (ops.MLP_TF32, 'dfma'),
+                                        (ops.MLP_F16, '')])
 def test_index_session_and_materialize_bit_identical(golden, monkeypatch,
                                                      mode, front):
     """(index, log_l) of the index-mode session == the row-mode session's

@@ -26,8 +26,13 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+TC_MODES = [ops.MLP_TF32, ops.MLP_F16]
+MODE_NAME = {ops.MLP_TF32: 'tf32', ops.MLP_F16: 'f16'}
+
+
+@pytest.mark.parametrize('mode', TC_MODES)
 @pytest.mark.parametrize('name', ['cfg2_bound_d30', 'nautilus_d4'])
-def test_tf32_scores_close_to_fp64(golden, name):
+def test_tf32_scores_close_to_fp64(golden, name, mode):
     g = golden(name)
     spec = flat_to_spec(g)
     stack = ops.DeviceStack([spec])
@@ -35,15 +40,16 @@ def test_tf32_scores_close_to_fp64(golden, name):
     in_ell, t_rows, score, ok = c_oracle.neural(meta, data, 0, 0, g['points'])
     t = dev(t_rows)
     p64 = stack.mlp_predict(0, 0, t, mode=ops.MLP_F64).cpu().numpy()
-    p32 = stack.mlp_predict(0, 0, t, mode=ops.MLP_TF32).cpu().numpy()
+    p32 = stack.mlp_predict(0, 0, t, mode=mode).cpu().numpy()
     err = np.abs(p32 - p64)[in_ell]
-    print('tf32 emulator: max |d score| = {:.2e}, mean = {:.2e}'.format(
-        err.max(), err.mean()))
+    print('{} emulator: max |d score| = {:.2e}, mean = {:.2e}'.format(
+        MODE_NAME[mode], err.max(), err.mean()))
     assert err.max() < TOL_SCORE
     assert np.max(np.abs(p32[in_ell] - g['predict'][in_ell])) < TOL_SCORE
 
 
-def test_tf32_membership_flips_only_at_threshold(golden):
+@pytest.mark.parametrize('mode', TC_MODES)
+def test_tf32_membership_flips_only_at_threshold(golden, mode):
     g = golden('cfg2_bound_d30')
     spec = flat_to_spec(g)
     stack = ops.DeviceStack([spec])
@@ -51,11 +57,11 @@ def test_tf32_membership_flips_only_at_threshold(golden):
     n = 200000
     pts, code, _ = stack.propose(0, n, seed=4)
     c64 = stack.contains(0, pts, which=2, mode=ops.MLP_F64).cpu().numpy()
-    c32 = stack.contains(0, pts, which=2, mode=ops.MLP_TF32).cpu().numpy()
+    c32 = stack.contains(0, pts, which=2, mode=mode).cpu().numpy()
     flips = c64 != c32
     rate = flips.mean()
-    print('tf32 membership flip rate = {:.3e} ({} of {})'.format(
-        rate, flips.sum(), n))
+    print('{} membership flip rate = {:.3e} ({} of {})'.format(
+        MODE_NAME[mode], rate, flips.sum(), n))
     assert rate < TOL_FLIPS
     # every flip sits within the score tolerance of the threshold
     meta, data = pack_stack([spec])
@@ -107,7 +113,8 @@ def test_tf32_cycle_self_consistent(golden):
     assert diff < TOL_FLIPS
 
 
-def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS):
+def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS,
+                     mode=ops.MLP_TF32):
     """The fused tf32 cycle (k_front -> k_mlp_tf32 with likelihood and shell
     sums in its tail) against the same decisions rebuilt from staged ops."""
     from oracle import nautilus_oracle as orc
@@ -115,7 +122,7 @@ def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS):
     out = stack.cycle(0, n, seed=seed, offset=77, stream_id=5,
                       like_id=like.like_id,
                       like_params=like.device_params('cuda'), log_l_min=-5.0,
-                      mode=ops.MLP_TF32)
+                      mode=mode)
     pts = out['points']
     code = out['code'].cpu().numpy()
     log_l = out['log_l'].cpu().numpy()
@@ -130,7 +137,7 @@ def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS):
     assert np.array_equal(code == 0, ~in_cube)
     assert np.array_equal(code == 1, in_cube & ~acc)
     # neural stage: same arithmetic as contains(which=2, tf32)
-    nn = stack.contains(0, pts, which=2, mode=ops.MLP_TF32).cpu().numpy()
+    nn = stack.contains(0, pts, which=2, mode=mode).cpu().numpy()
     assert np.array_equal(code == 4, acc & nn)
     assert np.array_equal(code == 2, acc & ~nn)
     # ... and against the fp64 ORACLE (not the same kernel): the dispositions
@@ -165,11 +172,12 @@ def _fused_vs_staged(spec, n, like, seed, flip_tol=TOL_FLIPS):
     return cnt
 
 
-def test_fused_cycle_single_ellipsoid(golden):
+@pytest.mark.parametrize('mode', TC_MODES)
+def test_fused_cycle_single_ellipsoid(golden, mode):
     from nautilus_b200 import likelihoods
     spec = flat_to_spec(golden('cfg2_bound_d30'))
     for n in (1, 200, 1 << 15):
-        _fused_vs_staged(spec, n, likelihoods.Gaussian(30), seed=n)
+        _fused_vs_staged(spec, n, likelihoods.Gaussian(30), seed=n, mode=mode)
 
 
 def test_fused_cycle_overlapping_ellipsoids(golden):
@@ -184,6 +192,9 @@ def test_fused_cycle_overlapping_ellipsoids(golden):
     cnt = _fused_vs_staged(spec, 1 << 15, likelihoods.Gaussian(4, sigma=0.3),
                            seed=3)
     assert cnt[ops.CNT_OVERLAP_REJECT] > 0 and cnt[ops.CNT_CUBE_REJECT] > 0
+    # the DFMA front kernel writing fp16 emulator rows
+    _fused_vs_staged(spec, 1 << 14, likelihoods.Gaussian(4, sigma=0.3),
+                     seed=5, mode=ops.MLP_F16)
     # and with the neural ellipsoid different from every mixture
     spec['neural'][0]['ell']['c'] = spec['neural'][0]['ell']['c'] + 1e-3
     _fused_vs_staged(spec, 1 << 14, likelihoods.Gaussian(4, sigma=0.3), seed=4)
@@ -260,6 +271,8 @@ def test_dmma_front_kernel_all_row_widths(d, monkeypatch):
     # (a 15-epoch toy network thresholded at its median score: many points
     # sit at the threshold, hence the wider flip allowance)
     cnt = _fused_vs_staged(spec, 6000, like, seed=d, flip_tol=5e-3)
+    _fused_vs_staged(spec, 3000, like, seed=d + 1, flip_tol=5e-3,
+                     mode=ops.MLP_F16)
     assert cnt[ops.CNT_IN_SHELL] > 0 and cnt[ops.CNT_NN_REJECT] > 0
     outs = []
     for which in ('mma', 'dfma'):
