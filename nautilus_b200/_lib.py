@@ -51,6 +51,53 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+TORCH_SRC = os.path.join(_HERE, 'csrc_torch', 'nb200_torch_ops.cpp')
+TORCH_LIB_PATH = os.path.join(_HERE, 'libnautilus_b200_torch.so')
+_torch_ops = None
+
+
+def build_torch_ops(force=False, verbose=False):
+    """Compile the STABLE_TORCH_LIBRARY shim (torch.ops.nautilus_b200.*,
+    csrc_torch/nb200_torch_ops.cpp) in-tree: host C++ only, linked against
+    libtorch's C shim and libnautilus_b200.so."""
+    build()
+    if (not force and os.path.exists(TORCH_LIB_PATH) and
+            os.path.getmtime(TORCH_LIB_PATH) >= max(
+                os.path.getmtime(TORCH_SRC), os.path.getmtime(LIB_PATH))):
+        return TORCH_LIB_PATH
+    import torch
+    troot = os.path.dirname(torch.__file__)
+    inc, lib = os.path.join(troot, 'include'), os.path.join(troot, 'lib')
+    cmd = [os.environ.get('CXX', 'g++'), '-O2', '-std=c++17', '-shared',
+           '-fPIC', '-DUSE_CUDA', '-DTORCH_TARGET_VERSION=0x020B000000000000',
+           '-I' + inc, '-I' + os.path.join(inc, 'torch', 'csrc', 'api',
+                                           'include'),
+           '-I/usr/local/cuda/include', '-o', TORCH_LIB_PATH, TORCH_SRC,
+           '-L' + lib, '-ltorch', '-ltorch_cpu', '-ltorch_cuda', '-lc10',
+           '-L' + _HERE, '-lnautilus_b200', '-Wl,-rpath,$ORIGIN',
+           '-Wl,-rpath,' + lib]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return TORCH_LIB_PATH
+
+
+def torch_ops():
+    """``torch.ops.nautilus_b200`` (loads the shim on first use; raises if
+    it is not built -- no fallback)."""
+    global _torch_ops
+    if _torch_ops is None:
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise NautilusB200Error(
+                'libnautilus_b200_torch.so is not built; run '
+                '`python -c "import __graft_entry__ as g; g.build()"`.')
+        import torch
+        lib()                       # the C ABI it forwards to
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _torch_ops = torch.ops.nautilus_b200
+    return _torch_ops
+
+
 _i32p = ctypes.c_void_p
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

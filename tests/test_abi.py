@@ -70,3 +70,26 @@ def test_session_fails_loudly_without_gpu(built):
     with pytest.raises(_lib.NautilusB200Error, match='n_max'):
         ops.HostSession([spec], n_max=0)
     assert np.isfinite(_lib.lib().nb200_workspace_bytes(1024, 3))
+
+
+def test_torch_ops_registered_through_the_stable_abi(built):
+    """torch.ops.nautilus_b200.* (STABLE_TORCH_LIBRARY shim over the C ABI):
+    builds, loads, registers its schemas; CUDA-only, so a CPU call raises
+    instead of computing anything on the host."""
+    torch = pytest.importorskip('torch')
+    _lib.build_torch_ops()
+    ops = _lib.torch_ops()
+    for name in ('ell_contains', 'shell_stats', 'bound_contains',
+                 'shell_cycle'):
+        assert hasattr(ops, name)
+    schema = str(torch.ops.nautilus_b200.shell_cycle.default._schema)
+    assert 'like_params' in schema and '-> (Tensor, Tensor, Tensor' in schema
+    out = subprocess.check_output(['nm', '-D', '--undefined-only',
+                                   _lib.TORCH_LIB_PATH], text=True)
+    assert 'nb200_cycle' in out and 'aoti_torch_get_current_cuda_stream' in out
+    # stable ABI only: no ATen / c10 C++ symbols are pulled in
+    assert not re.search(r' U _ZN2at|_ZN3c10[^d]', out)
+    with pytest.raises(NotImplementedError):
+        ops.ell_contains(torch.zeros((3, 2), dtype=torch.float64),
+                         torch.zeros(2, dtype=torch.float64),
+                         torch.eye(2, dtype=torch.float64))

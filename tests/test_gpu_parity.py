@@ -478,3 +478,41 @@ def test_empty_and_degenerate_inputs(golden):
     # out-of-range bound index is refused by the library
     with pytest.raises(RuntimeError):
         stack.contains(3, dev(np.zeros((3, 4))))
+
+
+def test_torch_ops_match_the_ctypes_binding(golden):
+    """torch.ops.nautilus_b200.* (stable-ABI registration) return exactly what
+    the ctypes binding of the same C entry points returns."""
+    from nautilus_b200 import _lib, likelihoods
+    tops = _lib.torch_ops()
+    g = golden('ellipsoid_d10')
+    pts = dev(g['points'])
+    got = tops.ell_contains(pts, dev(g['c']), dev(g['B_inv']))
+    assert got.dtype == torch.uint8
+    assert np.array_equal(host(got).astype(bool), g['contains'])
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    stack = ops.DeviceStack([spec])
+    like = likelihoods.Gaussian(30)
+    par = like.device_params('cuda')
+    meta_h = torch.from_numpy(stack.meta_h)
+    for mode in (ops.MLP_F64, ops.MLP_F16):
+        ref = stack.cycle(0, 5000, seed=7, offset=3, stream_id=1,
+                          like_id=like.like_id, like_params=par,
+                          log_l_min=-20.0, mode=mode)
+        p, ll, code, lse, cnt = tops.shell_cycle(
+            meta_h, stack.meta_d, stack.data_d, 0, 0, 0, 5000, 7, 3, 1,
+            like.like_id, par, -20.0, mode)
+        assert torch.equal(p, ref['points']) and torch.equal(code, ref['code'])
+        assert torch.equal(cnt, ref['counters']) and torch.equal(lse,
+                                                                 ref['lse'])
+        sel = code == ops.CODE_IN_SHELL
+        assert torch.equal(ll[sel], ref['log_l'][sel])
+        inside = tops.bound_contains(meta_h, stack.meta_d, stack.data_d, 0, 0,
+                                     p, mode)
+        assert torch.equal(inside.bool(), stack.contains(0, p, mode=mode))
+        lse2, cnt2 = tops.shell_stats(ll[sel].contiguous(), -20.0)
+        assert torch.equal(lse2[:3], lse[:3])
+        assert int(cnt2[ops.CNT_UPDATE]) == int(cnt[ops.CNT_UPDATE])
+    with pytest.raises(RuntimeError, match='bound index'):
+        tops.shell_cycle(meta_h, stack.meta_d, stack.data_d, 5, 0, 0, 10, 0,
+                         0, 0, -1, par, 0.0, 0)
