@@ -371,7 +371,9 @@ def make_fit_stats():
     """scikit-learn's fit on the emulator_d5 data, 10 seeds (the reference's
     train_network, nautilus/neural.py:10-32, with random_state = 0..9): final
     training loss, epochs, and the rmse of the prediction against the target
-    -- what tests/test_gpu_bounds_api.py compares the CUDA trainer with."""
+    -- what tests/test_gpu_bounds_api.py compares the CUDA trainer with.
+    40 seeds: the spread between seeds is a factor of 8 in the loss, ten
+    would not pin a median."""
     from nautilus.neural import train_network
     with np.load(os.path.join(HERE, 'emulator_d5.npz')) as f:
         x, y = f['x'], f['y']
@@ -380,7 +382,7 @@ def make_fit_stats():
                   learning_rate_init=1e-2, max_iter=10000, tol=0,
                   n_iter_no_change=10)
     loss, n_iter, rmse = [], [], []
-    for seed in range(10):
+    for seed in range(40):
         net = train_network(xs, y, kwargs, seed)
         loss.append(net.loss_)
         n_iter.append(net.n_iter_)

@@ -204,37 +204,41 @@ def test_neural_network_emulator():
 def test_trainer_quality_against_sklearn_fits(golden):
     """The CUDA trainer against scikit-learn's own fits of the same data
     (tests/golden/emulator_d5_sklearn_fits.npz: MLPRegressor with
-    random_state 0..9 through the reference's train_network,
+    random_state 0..39 through the reference's train_network,
     nautilus/neural.py:10-32).  The fit is statistical -- other random
-    numbers, fp32 -- so the bar is on the distribution over seeds: median
-    final loss and median rmse of ten networks within 1.25x of sklearn's
-    medians, and no network worse than sklearn's worst by more than 1.5x."""
+    numbers, fp32 -- and sklearn's own seeds spread over a factor of 10 in
+    the final loss, so the bar is on the distribution over 40 networks each:
+    median final loss, median rmse and the 90th percentile of the rmse within
+    1.25x of sklearn's."""
     from nautilus_b200.neural import NeuralNetworkEmulator
     g = golden('emulator_d5')
     ref = golden('emulator_d5_sklearn_fits')
     x, y = g['x'], g['y']
-    emu = NeuralNetworkEmulator.train(x, y, n_networks=10, seed=123)
-    xs = (x - emu.mean) / emu.scale
-    loss = np.array([n.loss_ for n in emu.neural_networks])
-    n_iter = np.array([n.n_iter_ for n in emu.neural_networks])
-    rmse = []
-    for net in emu.neural_networks:
-        a = xs
-        for i, (w, b) in enumerate(zip(net.coefs_, net.intercepts_)):
-            a = a @ w + b
-            if i + 1 < len(net.coefs_):
-                a = np.maximum(a, 0)
-        rmse.append(np.sqrt(np.mean((a[:, 0] - y)**2)))
-    rmse = np.array(rmse)
-    print('trainer vs sklearn over 10 seeds: median loss {:.2e} vs {:.2e}, '
-          'median rmse {:.4f} vs {:.4f}, worst rmse {:.4f} vs {:.4f}, '
+    loss, n_iter, rmse = [], [], []
+    for rep in range(4):
+        emu = NeuralNetworkEmulator.train(x, y, n_networks=10,
+                                          seed=1000 + rep)
+        xs = (x - emu.mean) / emu.scale
+        for net in emu.neural_networks:
+            loss.append(net.loss_)
+            n_iter.append(net.n_iter_)
+            a = xs
+            for i, (w, b) in enumerate(zip(net.coefs_, net.intercepts_)):
+                a = a @ w + b
+                if i + 1 < len(net.coefs_):
+                    a = np.maximum(a, 0)
+            rmse.append(np.sqrt(np.mean((a[:, 0] - y)**2)))
+    loss, n_iter, rmse = np.array(loss), np.array(n_iter), np.array(rmse)
+    print('trainer vs sklearn over 40 networks: median loss {:.2e} vs '
+          '{:.2e}, median rmse {:.4f} vs {:.4f}, p90 rmse {:.4f} vs {:.4f}, '
           'median epochs {:.0f} vs {:.0f}'.format(
               np.median(loss), np.median(ref['loss']), np.median(rmse),
-              np.median(ref['rmse']), rmse.max(), ref['rmse'].max(),
-              np.median(n_iter), np.median(ref['n_iter'])))
+              np.median(ref['rmse']), np.percentile(rmse, 90),
+              np.percentile(ref['rmse'], 90), np.median(n_iter),
+              np.median(ref['n_iter'])))
     assert np.median(loss) <= 1.25 * np.median(ref['loss'])
     assert np.median(rmse) <= 1.25 * np.median(ref['rmse'])
-    assert rmse.max() <= 1.5 * ref['rmse'].max()
+    assert np.percentile(rmse, 90) <= 1.25 * np.percentile(ref['rmse'], 90)
     # the test of the reference itself (tests/test_neural.py:15)
     assert np.all(rmse < 0.3 * np.std(y))
 

@@ -511,7 +511,9 @@ def test_torch_ops_match_the_ctypes_binding(golden):
                                      p, mode)
         assert torch.equal(inside.bool(), stack.contains(0, p, mode=mode))
         lse2, cnt2 = tops.shell_stats(ll[sel].contiguous(), -20.0)
-        assert torch.equal(lse2[:3], lse[:3])
+        # (another reduction shape: same maximum, sums to rounding)
+        assert float(lse2[0]) == float(lse[0])
+        assert torch.allclose(lse2[1:3], lse[1:3], rtol=1e-12, atol=0)
         assert int(cnt2[ops.CNT_UPDATE]) == int(cnt[ops.CNT_UPDATE])
     with pytest.raises(RuntimeError, match='bound index'):
         tops.shell_cycle(meta_h, stack.meta_d, stack.data_d, 5, 0, 0, 10, 0,
