@@ -34,11 +34,25 @@ __global__ void k_excl_pairs(const int32_t* __restrict__ meta, int first_later,
                              int n_later, int f16,
                              PairRec* __restrict__ pairs,
                              int* __restrict__ pair_base) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int p = 0;
-  for (int l = 0; l < n_later; ++l) {
+  // one thread per later bound; the prefix over the J's by thread 0
+  extern __shared__ int sJ[];
+  for (int l = threadIdx.x; l < n_later; l += blockDim.x) {
     const Rec rec = record(meta, first_later + l);
-    pair_base[l] = p;
+    sJ[l] = rec.kind() == 1 ? rec.J() : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int p = 0;
+    for (int l = 0; l < n_later; ++l) {
+      const int J = sJ[l];
+      sJ[l] = p;
+      pair_base[l] = p;
+      p += J;
+    }
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < n_later; l += blockDim.x) {
+    const Rec rec = record(meta, first_later + l);
     const int J = rec.kind() == 1 ? rec.J() : 0;
     for (int j = 0; j < J; ++j) {
       const int32_t* nb = rec.nb(j);
@@ -49,7 +63,7 @@ __global__ void k_excl_pairs(const int32_t* __restrict__ meta, int first_later,
       // the position of the fp16 blob, _pack.py:pack_record)
       pr.blob_off = nb[3] <= 0 ? -1 : f16 ? rec.r[nb[11] + 32 + 20] : nb[10];
       pr.thr_off = nb[3] > 0 ? nb[7] : -1;
-      pairs[p++] = pr;
+      pairs[sJ[l] + j] = pr;
     }
   }
 }
@@ -260,8 +274,8 @@ __global__ void k_excl_apply(const unsigned long long* __restrict__ cand_idx,
 int launch_excl_pairs(const int32_t* meta_d, int first_later, int n_later,
                       int f16, PairRec* pairs, int* pair_base,
                       cudaStream_t st) {
-  k_excl_pairs<<<1, 32, 0, st>>>(meta_d, first_later, n_later, f16, pairs,
-                                 pair_base);
+  k_excl_pairs<<<1, 128, sizeof(int) * (size_t)(n_later > 0 ? n_later : 1),
+                 st>>>(meta_d, first_later, n_later, f16, pairs, pair_base);
   NB_LAUNCH_OK();
   return 0;
 }
