@@ -267,6 +267,20 @@ int nb200_cycle_host(const int32_t* meta_h, int64_t n_meta,
                      double* points_out_h, double* log_l_out_h,
                      int64_t* n_out_h, double* lse_h, int64_t* counters_h);
 
+/* ---- live set (sampler.py:1007-1009, 1160-1164) -------------------------- */
+
+/* The k-th largest of values f64[n] (restricted to mask_d != 0 when mask_d is
+ * given; at least k entries must be selected): *thr_d receives it, *greater_d
+ * the number of selected values strictly greater.  The live set of the
+ * sampler is {log_l > thr} plus k - greater of the ties -- what the reference
+ * gets from a full argsort of every stored log_l on each exploration step.
+ * MSB radix select, four 16-bit passes; nothing leaves the device. */
+size_t nb200_select_workspace_bytes(void);
+int nb200_select_kth_largest(const double* values_d, const uint8_t* mask_d,
+                             int64_t n, int64_t k, double* thr_d,
+                             int64_t* greater_d, void* workspace_d,
+                             size_t workspace_bytes, void* stream);
+
 /* ---- bound construction (between shells) -------------------------------- */
 
 /* Weights u f64[n] of Khachiyan's algorithm for the minimum-volume enclosing

@@ -150,6 +150,9 @@ PROTOTYPES = {
     'nb200_cycle_host': (_int, [_i32p, _i64, _vp, _i64, _int, _int, _int,
                                 _i64, _u64, _u64, _u32, _int, _vp, _int, _dbl,
                                 _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'nb200_select_workspace_bytes': (_sz, []),
+    'nb200_select_kth_largest': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp,
+                                        _sz, _vp]),
     'nb200_mvee_workspace_bytes': (_sz, [_i64]),
     'nb200_mvee_weights': (_int, [_vp, _i64, _int, _int, _dbl, _vp, _vp, _vp,
                                   _sz, _vp]),

@@ -493,13 +493,44 @@ def loglike(points, like_id, params, code=None):
     return out
 
 
+def kth_largest(values, k, mask=None):
+    """(threshold f64[1], greater i64[1]) CUDA tensors: the k-th largest entry
+    of the CUDA float64 vector ``values`` (among ``mask != 0`` if given) and
+    how many are strictly greater (nb200_select_kth_largest: device radix
+    select, no sort, no synchronisation)."""
+    n = values.numel()
+    if not (values.is_cuda and values.dtype == torch.float64 and
+            values.is_contiguous()):
+        raise ValueError('values must be a contiguous CUDA float64 tensor')
+    mask = _chk_mask(mask, n)
+    dev = values.device
+    thr = torch.empty(1, dtype=torch.float64, device=dev)
+    greater = torch.empty(1, dtype=torch.int64, device=dev)
+    nbytes = int(_lib.lib().nb200_select_workspace_bytes())
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().nb200_select_kth_largest(
+        _ptr(values), _ptr(mask), n, int(k), _ptr(thr), _ptr(greater),
+        _ptr(buf), nbytes, _stream()))
+    return thr, greater
+
+
 def top_k(values, k):
     """Indices (int64 CUDA tensor, unordered) of the k largest entries of the
     CUDA float64 vector ``values`` -- the live set of sampler.py:1007-1009,
-    1160-1164 without a host argsort."""
-    if k >= values.numel():
-        return torch.arange(values.numel(), device=values.device)
-    return torch.topk(values, int(k), sorted=False).indices
+    1160-1164 without a host argsort: device radix select of the k-th largest
+    value, everything above it, and the first ties in index order to fill up
+    (``argsort`` picks ties arbitrarily too)."""
+    n = values.numel()
+    if k >= n:
+        return torch.arange(n, device=values.device)
+    values = values.contiguous()
+    thr, greater = kth_largest(values, k)
+    above = torch.nonzero(values > thr).squeeze(1)
+    short = int(k) - above.numel()
+    if short > 0:
+        ties = torch.nonzero(values == thr).squeeze(1)[:short]
+        above = torch.cat([above, ties])
+    return above
 
 
 def mvee_weights(q_t, max_updates=3000, tol=1e-3):

@@ -518,3 +518,36 @@ def test_torch_ops_match_the_ctypes_binding(golden):
     with pytest.raises(RuntimeError, match='bound index'):
         tops.shell_cycle(meta_h, stack.meta_d, stack.data_d, 5, 0, 0, 10, 0,
                          0, 0, -1, par, 0.0, 0)
+
+
+def test_device_radix_select_kth_largest():
+    """nb200_select_kth_largest (the live-set threshold, sampler.py:1007-1009)
+    against numpy's sort: every bit of the threshold, the count above it;
+    ties, negative values, -inf, a mask, k = 1 and k = n."""
+    rng = np.random.default_rng(0)
+    cases = [rng.normal(size=100003) * 50,
+             -np.abs(rng.normal(size=5000)) * 1e-300,
+             np.round(rng.normal(size=20000), 1),          # many ties
+             np.concatenate([np.full(100, -np.inf), rng.normal(size=900)]),
+             np.array([3.0]), np.zeros(1000)]
+    for v in cases:
+        t = dev(v)
+        srt = np.sort(v)[::-1]
+        for k in sorted({1, len(v), max(1, len(v) // 3), min(len(v), 2000)}):
+            thr, greater = ops.kth_largest(t, k)
+            assert host(thr)[0] == srt[k - 1]
+            assert int(host(greater)[0]) == np.sum(v > srt[k - 1])
+            idx = host(ops.top_k(t, k))
+            assert len(idx) == min(k, len(v)) and len(set(idx)) == len(idx)
+            assert np.array_equal(np.sort(v[idx])[::-1], srt[:k])
+    v = cases[0]
+    mask = rng.random(len(v)) < 0.3
+    thr, greater = ops.kth_largest(dev(v), 500, mask=dev(mask))
+    assert host(thr)[0] == np.sort(v[mask])[::-1][499]
+    with pytest.raises(_lib_error()):
+        ops.kth_largest(dev(v), len(v) + 1)
+
+
+def _lib_error():
+    from nautilus_b200._lib import NautilusB200Error
+    return NautilusB200Error
