@@ -14,8 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libnautilus_b200.so')
 
+# --exclude-libs,ALL: nvcc links parts of libstdc++.a / libcudart_static.a
+# into the library; their symbols must not be exported (a second, partial C++
+# runtime in the lookup scope of whoever links against us breaks exception
+# unwinding there -- seen with the torch.ops shim)
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
-              '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
+              '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-Xlinker',
+              '--exclude-libs,ALL']
 
 _lib = None
 
@@ -37,14 +42,26 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def host_cxx():
+    """The SYSTEM C++ compiler.  Deliberately not $CXX: in this image $CXX is
+    a relocated gcc that only has a static libstdc++, and a second,
+    uninitialised C++ runtime inside a dlopen'ed library crashes at the first
+    ostream / exception (seen: a failed STD_TORCH_CHECK in the torch.ops shim
+    segfaulted).  NB200_CXX overrides."""
+    cxx = os.environ.get('NB200_CXX')
+    if cxx:
+        return cxx
+    return '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+
+
 def build(force=False, verbose=False):
     """Compile the extension in-tree with nvcc for sm_100a."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     extra = os.environ.get('NB200_EXTRA_FLAGS', '').split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + ['-o', LIB_PATH] + sources() + [
-        '-lcuda']
+    cmd = [nvcc, '-ccbin', host_cxx()] + NVCC_FLAGS + extra + [
+        '-o', LIB_PATH] + sources() + ['-lcuda']
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)
@@ -59,7 +76,7 @@ _torch_ops = None
 def build_torch_ops(force=False, verbose=False):
     """Compile the STABLE_TORCH_LIBRARY shim (torch.ops.nautilus_b200.*,
     csrc_torch/nb200_torch_ops.cpp) in-tree: host C++ only, linked against
-    libtorch's C shim and libnautilus_b200.so."""
+    libtorch's C shim libnautilus_b200.so."""
     build()
     if (not force and os.path.exists(TORCH_LIB_PATH) and
             os.path.getmtime(TORCH_LIB_PATH) >= max(
@@ -68,14 +85,13 @@ def build_torch_ops(force=False, verbose=False):
     import torch
     troot = os.path.dirname(torch.__file__)
     inc, lib = os.path.join(troot, 'include'), os.path.join(troot, 'lib')
-    cmd = [os.environ.get('CXX', 'g++'), '-O2', '-std=c++17', '-shared',
+    cmd = [host_cxx(), '-O2', '-std=c++17', '-shared',
            '-fPIC', '-DUSE_CUDA', '-DTORCH_TARGET_VERSION=0x020B000000000000',
            '-I' + inc, '-I' + os.path.join(inc, 'torch', 'csrc', 'api',
                                            'include'),
            '-I/usr/local/cuda/include', '-o', TORCH_LIB_PATH, TORCH_SRC,
            '-L' + lib, '-ltorch', '-ltorch_cpu', '-ltorch_cuda', '-lc10',
-           '-L' + _HERE, '-lnautilus_b200', '-Wl,-rpath,$ORIGIN',
-           '-Wl,-rpath,' + lib]
+           '-ldl', '-Wl,-rpath,' + lib]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

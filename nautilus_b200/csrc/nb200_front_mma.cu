@@ -30,8 +30,23 @@
 
 namespace nb200 {
 
-constexpr int FM_WARPS = 8;
-constexpr int FM_THREADS = FM_WARPS * 32;
+// warps per CTA: 8 for rows up to 64 wide (two CTAs per SM); wider rows
+// (d up to 128, e.g. BASELINE config 5) keep fewer rows on chip
+__host__ __device__ constexpr int fm_warps(int d8) {
+  return d8 <= 64 ? 8 : d8 <= 112 ? 4 : 2;
+}
+// Factors wider than 64 are staged TRIANGULAR-PACKED (they must be exactly
+// lower-triangular): row block I keeps its 2 I + 2 k-blocks only, so both
+// factors of a 100-D ellipsoid take 93 KB instead of 173 KB.
+__host__ __device__ constexpr bool fm_tri(int d8) { return d8 > 64; }
+__host__ __device__ constexpr int fm_fac_doubles(int d8) {
+  return fm_tri(d8) ? (d8 / 8) * (d8 / 8 + 1) * 32 : d8 * d8;
+}
+// first fragment (in units of 32 doubles) of row block I
+template <int D8>
+__device__ __forceinline__ int fm_row_block(int I) {
+  return fm_tri(D8) ? I * (I + 1) : I * (D8 / 4);
+}
 
 struct FrontMmaArgs {
   int rec_off, d, d8, unit, k0p, S;
@@ -84,12 +99,13 @@ __device__ __forceinline__ void mma_rows(const double* __restrict__ frag_lane,
                                          const double* __restrict__ c_lane,
                                          double (&T)[4][2]) {
   constexpr int NK = D8 / 4, S = D8 + 4;
+  frag_lane += fm_row_block<D8>(I) * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
 #pragma unroll
   for (int Kb = 0; Kb < NK; ++Kb) {
     if (Kb < kb_end) {
-      const double b = frag_lane[(I * NK + Kb) * 32];
+      const double b = frag_lane[Kb * 32];
       const double cq = SUBTRACT ? c_lane[4 * Kb] : 0.0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -102,7 +118,7 @@ __device__ __forceinline__ void mma_rows(const double* __restrict__ frag_lane,
 }
 
 template <int D8>
-__global__ void __launch_bounds__(FM_THREADS, 2)
+__global__ void __launch_bounds__(fm_warps(D8) * 32, D8 <= 64 ? 2 : 1)
 k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             const double* __restrict__ data, double* __restrict__ points,
             uint8_t* __restrict__ code, uint8_t* __restrict__ maskj,
@@ -110,8 +126,10 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
   extern __shared__ __align__(16) double sm[];
   const Rec rec{meta + A.rec_off};
   constexpr int d8 = D8, S = D8 + 4, nI = D8 / 8, nK = D8 / 4;
+  constexpr int FM_WARPS = fm_warps(D8), FM_THREADS = FM_WARPS * 32;
+  constexpr bool TRI = fm_tri(D8);
   const int d = A.d;
-  const int fsz = d8 * d8;                 // doubles per staged factor
+  constexpr int fsz = fm_fac_doubles(D8);  // doubles per staged factor
   double* fB = sm;                         // B        in fragment order
   double* fBinv = fB + fsz;                // B_inv (mixture)
   double* fN = fBinv + fsz;                // B_inv (neural), if different
@@ -125,14 +143,16 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
 
   // factors -> fragment order: frag[I][Kb][lane] = M[8I + lane/4][4Kb + lane%4]
   const int n_fac = A.same ? 2 : 3;
-  for (int e = threadIdx.x; e < n_fac * fsz; e += FM_THREADS) {
-    const int which = e / fsz, rem = e - which * fsz;
+  for (int e = threadIdx.x; e < n_fac * d8 * d8; e += FM_THREADS) {
+    const int which = e / (d8 * d8), rem = e - which * (d8 * d8);
     const int blk = rem >> 5, ln = rem & 31;
     const int I = blk / nK, Kb = blk - I * nK;
+    if (TRI && Kb >= 2 * I + 2) continue;    // above the diagonal: not kept
     const int i = 8 * I + (ln >> 2), j = 4 * Kb + (ln & 3);
     const double* src = data + (which == 0 ? mix[4] : which == 1 ? mix[5]
                                                                  : nb[1]);
-    sm[e] = (i < d && j < d) ? src[(size_t)i * d + j] : 0.0;
+    sm[which * fsz + (fm_row_block<D8>(I) + Kb) * 32 + ln] =
+        (i < d && j < d) ? src[(size_t)i * d + j] : 0.0;
   }
   for (int e = threadIdx.x; e < 4 * d8; e += FM_THREADS) {
     const int which = e / d8, i = e - which * d8;
@@ -217,7 +237,9 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     bool cube[4] = {true, true, true, true};
     const double* row_lane = rows + p * S + q;
     const bool pair_ok = (d & 1) == 0;     // 16-byte stores need even offsets
-#pragma unroll
+    // (row-block loops are unrolled only for narrow rows: 13 blocks x 26
+    // k-blocks of a 100-D row would not fit the instruction cache)
+#pragma unroll(D8 <= 64 ? 8 : 1)
     for (int I = nI - 1; I >= 0; --I) {
       double T[4][2];
       mma_rows<D8, false>(fB + lane, I, 2 * I + 2, row_lane, nullptr, T);
@@ -259,7 +281,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     double r2m[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the mixture's ellipsoid
     double r2n[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the neural bound's
     if (!A.same) {
-#pragma unroll
+#pragma unroll(D8 <= 64 ? 8 : 1)
       for (int I = 0; I < nI; ++I) {
         double T[4][2];
         mma_rows<D8, true>(fBinv + lane, I, A.lower_b ? 2 * I + 2 : nK,
@@ -269,7 +291,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
           r2m[g] = fma(T[g][1], T[g][1], fma(T[g][0], T[g][0], r2m[g]));
       }
     }
-#pragma unroll
+#pragma unroll(D8 <= 64 ? 10 : 1)
     for (int I = 0; I < nI + 2; ++I) {
       if (8 * I >= A.k0p) break;
       double T[4][2];
@@ -365,12 +387,14 @@ bool front_mma_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   const int d = rec.d();
   if (rec.mix(0)[1] != 0 || rec.mix(0)[0] != d) return false;
   const int d8 = (d + 7) / 8 * 8;
-  if (d8 > 64) return false;
+  if (d8 > 128) return false;
   const int S = d8 + 4;
   const int same = rec.r[10] - 1 == 0;
-  const size_t doubles = (size_t)(same ? 2 : 3) * d8 * d8 + 4 * (size_t)d8 +
-                         (size_t)FM_WARPS * 32 * S;
-  if (doubles * 8 > 200 * 1024) return false;
+  // wide rows: triangular-packed factors, which must be exactly lower
+  if (fm_tri(d8) && !(rec.mix(0)[6] && (same || nb[2]))) return false;
+  const size_t doubles = (size_t)(same ? 2 : 3) * fm_fac_doubles(d8) +
+                         4 * (size_t)d8 + (size_t)fm_warps(d8) * 32 * S;
+  if (doubles * 8 > (d8 <= 64 ? 200 : 227) * 1024) return false;
   if (smem_out) *smem_out = doubles * 8;
   if (args) {
     args->rec_off = (int)(rec.r - meta_h);
@@ -409,8 +433,17 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
     case 48: kern = k_front_mma<48>; break;
     case 56: kern = k_front_mma<56>; break;
     case 64: kern = k_front_mma<64>; break;
-    default: NB_CHECK(false, "DMMA front kernel: n_dim > 64");
+    case 72: kern = k_front_mma<72>; break;
+    case 80: kern = k_front_mma<80>; break;
+    case 88: kern = k_front_mma<88>; break;
+    case 96: kern = k_front_mma<96>; break;
+    case 104: kern = k_front_mma<104>; break;
+    case 112: kern = k_front_mma<112>; break;
+    case 120: kern = k_front_mma<120>; break;
+    case 128: kern = k_front_mma<128>; break;
+    default: NB_CHECK(false, "DMMA front kernel: n_dim > 128");
   }
+  const int FM_WARPS = fm_warps(A.d8), FM_THREADS = FM_WARPS * 32;
   NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));

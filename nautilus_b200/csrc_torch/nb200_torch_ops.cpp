@@ -21,6 +21,9 @@
 #include <torch/csrc/stable/ops.h>
 #include <torch/csrc/stable/tensor.h>
 
+#include <dlfcn.h>
+
+#include <string>
 #include <tuple>
 
 #include "../../include/nautilus_b200.h"
@@ -30,6 +33,39 @@ using torch::stable::Tensor;
 
 namespace {
 
+// The C ABI is bound at run time (dlopen of libnautilus_b200.so next to this
+// file, dlsym per entry point) instead of at link time: the nvcc-built
+// library carries pieces of a statically linked C++ runtime, and having it
+// in this module's link-time lookup scope broke exception unwinding out of
+// the boxed kernels (a failed STD_TORCH_CHECK crashed instead of raising).
+void* core_library() {
+  static void* handle = [] {
+    Dl_info info;
+    STD_TORCH_CHECK(dladdr(reinterpret_cast<void*>(&core_library), &info) &&
+                        info.dli_fname,
+                    "cannot locate libnautilus_b200_torch.so");
+    std::string path(info.dli_fname);
+    path = path.substr(0, path.find_last_of('/') + 1) + "libnautilus_b200.so";
+    void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    STD_TORCH_CHECK(h != nullptr, "cannot load ", path, ": ", dlerror());
+    return h;
+  }();
+  return handle;
+}
+
+void* core_symbol(const char* name) {
+  void* p = dlsym(core_library(), name);
+  STD_TORCH_CHECK(p != nullptr, "libnautilus_b200.so does not export ", name);
+  return p;
+}
+
+// NB(nb200_cycle)(...) calls the entry point with the header's signature
+#define NB(fn)                                                          \
+  ([]() {                                                               \
+    static auto* p = reinterpret_cast<decltype(&fn)>(core_symbol(#fn)); \
+    return p;                                                           \
+  }())
+
 void* cuda_stream_of(const Tensor& t) {
   void* stream = nullptr;
   TORCH_ERROR_CODE_CHECK(
@@ -37,7 +73,7 @@ void* cuda_stream_of(const Tensor& t) {
   return stream;
 }
 
-void check(int rc) { STD_TORCH_CHECK(rc == 0, nb200_last_error()); }
+void check(int rc) { STD_TORCH_CHECK(rc == 0, NB(nb200_last_error)()); }
 
 void want(const Tensor& t, ScalarType dtype, bool cuda, const char* what) {
   STD_TORCH_CHECK(t.scalar_type() == dtype && t.is_contiguous() &&
@@ -55,7 +91,7 @@ Tensor ell_contains(Tensor points, Tensor c, Tensor B_inv) {
   STD_TORCH_CHECK(c.numel() == d && B_inv.numel() == d * d,
                   "ellipsoid parameters do not match the points");
   Tensor out = torch::stable::new_empty(points, {n}, ScalarType::Byte);
-  check(nb200_ell_contains(
+  check(NB(nb200_ell_contains)(
       static_cast<const double*>(points.data_ptr()), n, (int)d,
       static_cast<const double*>(c.data_ptr()),
       static_cast<const double*>(B_inv.data_ptr()),
@@ -68,9 +104,9 @@ std::tuple<Tensor, Tensor> shell_stats(Tensor log_l, double log_l_min) {
   Tensor lse = torch::stable::new_empty(log_l, {NB200_N_LSE});
   Tensor counters =
       torch::stable::new_empty(log_l, {NB200_N_CNT}, ScalarType::Long);
-  const int64_t bytes = (int64_t)nb200_workspace_bytes(1, 1);
+  const int64_t bytes = (int64_t)NB(nb200_workspace_bytes)(1, 1);
   Tensor ws = torch::stable::new_empty(log_l, {bytes}, ScalarType::Byte);
-  check(nb200_stats(static_cast<const double*>(log_l.data_ptr()), nullptr,
+  check(NB(nb200_stats)(static_cast<const double*>(log_l.data_ptr()), nullptr,
                     log_l.numel(), log_l_min,
                     static_cast<double*>(lse.data_ptr()),
                     static_cast<int64_t*>(counters.data_ptr()), ws.data_ptr(),
@@ -88,9 +124,9 @@ Tensor bound_contains(Tensor meta_h, Tensor meta, Tensor data, int64_t bound,
   STD_TORCH_CHECK(points.dim() == 2, "points must be [n, d]");
   const int64_t n = points.size(0), d = points.size(1);
   Tensor out = torch::stable::new_empty(points, {n}, ScalarType::Byte);
-  const int64_t bytes = (int64_t)nb200_workspace_bytes(n, (int)d);
+  const int64_t bytes = (int64_t)NB(nb200_workspace_bytes)(n, (int)d);
   Tensor ws = torch::stable::new_empty(points, {bytes}, ScalarType::Byte);
-  check(nb200_bound_contains(
+  check(NB(nb200_bound_contains)(
       static_cast<const int32_t*>(meta_h.data_ptr()),
       static_cast<const int32_t*>(meta.data_ptr()),
       static_cast<const double*>(data.data_ptr()), (int)bound, (int)which,
@@ -124,9 +160,9 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor> shell_cycle(
   Tensor lse = torch::stable::new_empty(data, {NB200_N_LSE});
   Tensor counters =
       torch::stable::new_empty(data, {NB200_N_CNT}, ScalarType::Long);
-  const int64_t bytes = (int64_t)nb200_cycle_workspace_bytes(rows, d, pairs);
+  const int64_t bytes = (int64_t)NB(nb200_cycle_workspace_bytes)(rows, d, pairs);
   Tensor ws = torch::stable::new_empty(data, {bytes}, ScalarType::Byte);
-  check(nb200_cycle(
+  check(NB(nb200_cycle)(
       mh, static_cast<const int32_t*>(meta.data_ptr()),
       static_cast<const double*>(data.data_ptr()), (int)bound,
       (int)first_later, (int)n_later, n, (uint64_t)seed, (uint64_t)offset,

@@ -239,9 +239,11 @@ def test_front_kernels_agree(golden, monkeypatch):
     assert np.abs(a['counters'] - b['counters']).max() <= 3
 
 
-@pytest.mark.parametrize('d', [3, 8, 17, 33, 40, 50, 64])
+@pytest.mark.parametrize('d', [3, 8, 17, 33, 40, 50, 64, 72, 81, 90, 100, 111,
+                               120, 128])
 def test_dmma_front_kernel_all_row_widths(d, monkeypatch):
-    # every instantiation of k_front_mma<D8> (D8 = 8 ... 64): a hand-built
+    # every instantiation of k_front_mma<D8> (D8 = 8 ... 128; above 64 with
+    # triangular-packed factors and fewer warps per CTA): a hand-built
     # one-ellipsoid bound with a small emulator; decisions against the oracle
     # on the kernel's own proposals, and agreement with the DFMA kernel
     from nautilus_b200 import bounds, likelihoods
@@ -285,3 +287,20 @@ def test_dmma_front_kernel_all_row_widths(d, monkeypatch):
     a, b = outs
     assert np.max(np.abs(a['points'] - b['points'])) < 1e-12
     assert np.mean(a['code'] != b['code']) < 2e-3
+
+
+def test_fused_cycle_config5_bound(golden):
+    """BASELINE config 5 (100-D, the bound the reference built): the wide DMMA
+    front end + the fp16 emulator in its one-tile-group form + fused shell
+    sums, against the oracle and the staged kernels."""
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden('cfg5_bound_d100'))
+    like = likelihoods.EquicorrelatedGaussian(100)
+    stack = ops.DeviceStack([spec])
+    l0 = ops.launch_count()
+    stack.cycle(0, 4096, seed=1, like_id=like.like_id,
+                like_params=like.device_params('cuda'), mode=ops.MLP_F16)
+    assert ops.launch_count() - l0 == 3          # front, emulator, final sums
+    cnt = _fused_vs_staged(spec, 1 << 15, like, seed=2, mode=ops.MLP_F16)
+    assert cnt[ops.CNT_NN_REJECT] > 0
+    _fused_vs_staged(spec, 3000, like, seed=3, mode=ops.MLP_TF32)
