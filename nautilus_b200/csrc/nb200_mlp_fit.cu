@@ -471,6 +471,20 @@ __global__ void k_f64_to_f32(const double* __restrict__ in, long long n,
 
 }  // namespace nb200
 
+namespace nb200 {
+// the tcgen05 trainer (nb200_mlp_fit_tc.cu)
+struct FitTcArgs;
+bool fit_tc_plan(const int32_t* sizes, int n_lay, int64_t m, int batch,
+                 FitTcArgs* out);
+int launch_fit_tc_from(const int32_t* sizes, int n_lay, int64_t m, int batch,
+                       int max_epochs, int patience, float lr, float beta1,
+                       float beta2, float eps, float tol,
+                       unsigned long long seed, const float* x32,
+                       const float* y32, float* moments, int n_net,
+                       double* weights_out, int* n_iter_out, double* loss_out,
+                       cudaStream_t st, bool* used);
+}  // namespace nb200
+
 using namespace nb200;
 
 extern "C" {
@@ -567,6 +581,16 @@ int nb200_mlp_fit(const double* x_d, const double* y_d, int64_t m, int d,
   NB_LAUNCH_OK();
   k_f64_to_f32<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(y_d, m, y32);
   NB_LAUNCH_OK();
+  {
+    // tensor-core trainer whenever the problem fits its envelope
+    bool used = false;
+    const int rc = launch_fit_tc_from(
+        sizes_h, n_lay, m, A.batch, max_epochs, patience, A.lr, A.beta1,
+        A.beta2, A.eps, A.tol, seed, x32, y32, moments, n_net, weights_out_d,
+        n_iter_out_d, loss_out_d, st, &used);
+    if (rc) return rc;
+    if (used) return 0;
+  }
   auto kern = A.big ? k_mlp_fit<true> : k_mlp_fit<false>;
   NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -117,6 +117,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
         "r"(v[5]), "r"(v[6]), "r"(v[7])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]),
+        "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(addr));
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

@@ -403,3 +403,41 @@ def test_device_mvee_against_the_reference_ellipsoid(golden, d):
     assert ell.log_v <= float(g['log_v']) + 1e-3          # never looser
     assert float(g['log_v']) - ell.log_v < 0.03 * d       # ... nor far off
     assert np.max(np.abs(ell.c - g['c'])) < 0.02
+
+
+def test_tensor_core_trainer_follows_the_simt_trainer(golden, monkeypatch):
+    """k_mlp_fit_tc (tcgen05 kind::tf32 products, fp32 accumulate) against
+    k_mlp_fit (fp32 FFMA) from the same initial networks through the same
+    minibatches: after a few epochs the weights agree to tf32 rounding noise
+    and the epoch losses to a few per cent; run to the end both meet the
+    reference's own bar."""
+    from nautilus_b200.neural import NeuralNetworkEmulator
+    g = golden('emulator_d5')
+    x, y = g['x'], g['y']
+
+    def fit(kind, **kw):
+        monkeypatch.setenv('NB200_FIT', kind)
+        return NeuralNetworkEmulator.train(x, y, n_networks=3, seed=7,
+                                           neural_network_kwargs=kw)
+
+    for epochs in (1, 4):
+        a = fit('tc', max_iter=epochs)
+        b = fit('ffma', max_iter=epochs)
+        for na, nb_ in zip(a.neural_networks, b.neural_networks):
+            assert na.n_iter_ == nb_.n_iter_ == epochs
+            assert abs(na.loss_ / nb_.loss_ - 1) < 0.05, (na.loss_, nb_.loss_)
+            for wa, wb in zip(na.coefs_ + na.intercepts_,
+                              nb_.coefs_ + nb_.intercepts_):
+                # (Adam's first steps move every weight by ~lr = 0.01 in the
+                # direction of the gradient's SIGN: a weight whose gradient is
+                # at rounding level may go the other way, hence the max bar)
+                diff = np.abs(wa - wb)
+                assert np.mean(diff) < 2e-3 * epochs, (epochs, np.mean(diff))
+                assert np.max(diff) < 0.1, (epochs, np.max(diff))
+    a, b = fit('tc'), fit('ffma')
+    for emu in (a, b):
+        rmse = np.sqrt(np.mean((emu.predict(x) - y)**2))
+        assert rmse < 0.1 * np.std(y)
+    print('final losses tc {} ffma {}'.format(
+        [round(n.loss_, 6) for n in a.neural_networks],
+        [round(n.loss_, 6) for n in b.neural_networks]))
