@@ -604,6 +604,21 @@ def run_gpu(args):
             'peak_source': peaks['source'] + ', dense bf16 burst' + (
                 ' / 2 (tf32)' if args.mlp == 'tf32' else
                 ' (fp16 operands run at the bf16 rate)')}
+        # the instruction's own ceiling in the shape the kernel issues
+        # (cta_group::1, M = 128), measured by tools/peak_umma.cu on this
+        # pool's B200 and committed under profiles/
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r2_peak_umma.json')) as f:
+                umma = json.load(f)
+            upeak = umma['tf32_ts_n128' if args.mlp == 'tf32'
+                         else 'f16_ts_n128']
+            roofline['emulator_tensor']['umma_peak'] = upeak
+            roofline['emulator_tensor']['frac_of_umma_peak'] = ach / upeak
+            roofline['emulator_tensor']['umma_peak_source'] = (
+                'profiles/r2_peak_umma.json (tools/peak_umma.cu: tcgen05.mma '
+                'cta_group::1 M=128 N=128, A from TMEM, one CTA per SM)')
+        except (OSError, KeyError, ValueError):
+            pass
     # whole-step figure against the 8d+9 B/proposal HBM roofline
     roofline['cycle_hbm_frac'] = (value / world * ALGO_BYTES_PER_PROPOSAL /
                                   1e9) / peaks['hbm']
