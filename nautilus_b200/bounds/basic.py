@@ -163,7 +163,7 @@ class UnitCubeEllipsoidMixture(_DeviceBound):
             sub_inv = a_inv[np.ix_(keep, keep)]
             sub = np.linalg.inv(sub_inv)
             diff = points[:, [cols[i] for i in keep]] - c[keep]
-            scale = np.max(np.einsum('ij,jk,ik->i', diff, sub, diff))
+            scale = np.max(np.einsum('ij,ij->i', diff @ sub, diff))
             return 0.5 * np.linalg.slogdet(sub_inv * scale)[1]
 
         # backward pass: hand dimensions to the cube while the volume shrinks

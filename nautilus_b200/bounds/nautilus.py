@@ -17,6 +17,20 @@ from .neural import NeuralBound
 from .union import Union
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the emulator fits, kept for the life of
+    the process: a new stream per bound starts with an empty allocator pool,
+    and every tensor made under it was a cudaMalloc (0.5 ms each, ~2 s per
+    config-2 run)."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class NautilusBound(_DeviceBound):
     """(nautilus/bounds/nautilus.py:13-397)."""
 
@@ -62,7 +76,7 @@ class NautilusBound(_DeviceBound):
         # which `rng` is consumed is that of the sequential code.
         bound.neural_bounds = []
         main = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side = _side_stream(main.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for ell in clusters.bounds:

@@ -216,8 +216,9 @@ k_mvee(const double* __restrict__ qT, int64_t n, int d, int max_updates,
 // own shared memory; every CTA carries its own copy of the inverse moment
 // matrix and applies the same update to it (bit-identical: the same
 // arithmetic on the same operands).  Per update the CTAs exchange, through
-// distributed shared memory, one (max g, argmax) candidate each and the
-// lifted coordinates of the winning point: two cluster barriers.
+// distributed shared memory, one candidate each -- (max g, argmax) AND that
+// point's lifted coordinates -- so one cluster barrier per update decides the
+// winner and delivers its coordinates.
 // ---------------------------------------------------------------------------
 constexpr int MVC_THREADS = 512;
 constexpr int MVC_WARPS = MVC_THREADS / 32;
@@ -226,8 +227,12 @@ constexpr int MVC_MAX_CLUSTER = 16;   // 16 needs the non-portable opt-in
 struct MvcShared {
   double red_v[MVC_WARPS];
   int red_i[MVC_WARPS];
-  double cand_v[MVC_MAX_CLUSTER];   // written by the peers
-  int cand_i[MVC_MAX_CLUSTER];
+  // written by the peers; double-buffered by the parity of the update: with
+  // ONE cluster barrier per update a fast CTA writes the candidates of
+  // update t + 1 while a slow one still reads those of update t
+  double cand_v[2][MVC_MAX_CLUSTER];
+  int cand_i[2][MVC_MAX_CLUSTER];
+  int my_i;                         // this CTA's candidate (global index)
 };
 
 __global__ void __launch_bounds__(MVC_THREADS, 1)
@@ -247,8 +252,9 @@ k_mvee_cluster(const double* __restrict__ qT, int n, int d, int n_loc_max,
   double* Vinv = smc;                     // [D][Dp]
   double* Vpart = Vinv + (size_t)D * Dp;  // [D][Dp]  this CTA's partial V
   double* w = Vpart + (size_t)D * Dp;     // [D]
-  double* qj = w + D;                     // [D]  written by the winner's CTA
-  double* g = qj + D;                     // [ld]
+  double* cq = w + D;                     // [2][MAX_CLUSTER][D] the candidates'
+                                          // lifted coordinates (by the peers)
+  double* g = cq + (size_t)2 * MVC_MAX_CLUSTER * D;   // [ld]
   double* u = g + ld;                     // [ld]
   double* q = u + ld;                     // [d][ld] coordinate-major slice
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -263,7 +269,8 @@ k_mvee_cluster(const double* __restrict__ qT, int n, int d, int n_loc_max,
 
   // (max, argmax) of this thread's candidates over the whole cluster;
   // ties go to the smaller global index (numpy.argmax)
-  auto cluster_argmax = [&](double v, int i, double& gmax, int& jmax) {
+  auto cluster_argmax = [&](double v, int i, int par, double& gmax, int& jmax,
+                            int& rwin) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ov = __shfl_down_sync(0xffffffffu, v, o);
@@ -286,14 +293,29 @@ k_mvee_cluster(const double* __restrict__ qT, int n, int d, int n_loc_max,
       i = __shfl_sync(0xffffffffu, i, 0);
       if (lane < C) {
         MvcShared* peer = cluster.map_shared_rank(&sh, lane);
-        peer->cand_v[rank] = v;
-        peer->cand_i[rank] = i;
+        peer->cand_v[par][rank] = v;
+        peer->cand_i[par][rank] = i;
+      }
+      if (lane == 0) sh.my_i = i;
+    }
+    __syncthreads();
+    {
+      // ... and the candidate's lifted coordinates, to every CTA
+      const int bi = sh.my_i;
+      if (tid < D && bi >= lo && bi < hi) {
+        const double c = lift(tid, bi - lo);
+        for (int r = 0; r < C; ++r)
+          cluster.map_shared_rank(cq, r)[(par * MVC_MAX_CLUSTER + rank) * D +
+                                         tid] = c;
       }
     }
     cluster.sync();
-    gmax = sh.cand_v[0]; jmax = sh.cand_i[0];
-    for (int r = 1; r < C; ++r) arg_better(gmax, jmax, sh.cand_v[r],
-                                           sh.cand_i[r]);
+    gmax = sh.cand_v[par][0]; jmax = sh.cand_i[par][0]; rwin = 0;
+    for (int r = 1; r < C; ++r) {
+      const int before = jmax;
+      arg_better(gmax, jmax, sh.cand_v[par][r], sh.cand_i[par][r]);
+      if (jmax != before) rwin = r;
+    }
   };
 
   // V = sum_i u_i q_i q_i^T: partial sums per CTA (one warp per entry of the
@@ -361,13 +383,12 @@ k_mvee_cluster(const double* __restrict__ qT, int n, int d, int n_loc_max,
   refresh(best_v, best_i);
   int it = 0;
   for (; it < max_updates; ++it) {
-    double gmax; int j;
-    cluster_argmax(best_v, best_i, gmax, j);
+    double gmax; int j, rwin;
+    cluster_argmax(best_v, best_i, it & 1, gmax, j, rwin);
     if (gmax <= (double)D * (1.0 + tol)) break;     // same decision everywhere
     const double step = (gmax - D) / ((double)D * (gmax - 1.0));
     const double beta = step / (1.0 - step);
     const double one_m = 1.0 - step;
-    const bool mine = j >= lo && j < hi;
     if (it % MV_REFRESH == MV_REFRESH - 1) {
       for (int i = tid; i < nl; i += MVC_THREADS)
         u[i] = u[i] * one_m + (lo + i == j ? step : 0.0);
@@ -375,16 +396,23 @@ k_mvee_cluster(const double* __restrict__ qT, int n, int d, int n_loc_max,
       refresh(best_v, best_i);
       continue;
     }
-    // the owner of point j hands its lifted coordinates to every CTA
-    if (mine && tid < D) {
-      const double v = lift(tid, j - lo);
-      for (int r = 0; r < C; ++r) cluster.map_shared_rank(qj, r)[tid] = v;
-    }
-    cluster.sync();
-    if (tid < D) {
-      double acc = 0.0;
-      for (int b = 0; b < D; ++b) acc = fma(Vinv[tid * Dp + b], qj[b], acc);
-      w[tid] = acc;
+    // w = V^-1 q_j: sixteen threads per row, then a shuffle tree (every CTA
+    // runs the same code on the same operands: bit-identical copies)
+    {
+      const double* qj = cq + ((it & 1) * MVC_MAX_CLUSTER + rwin) * D;
+      const int sub = tid & 15;
+      for (int a0 = 0; a0 < D; a0 += MVC_THREADS / 16) {
+        const int a = a0 + (tid >> 4);
+        double acc = 0.0;
+        if (a < D)
+          for (int b = sub; b < D; b += 16)
+            acc = fma(Vinv[a * Dp + b], qj[b], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (a < D && sub == 0) w[a] = acc;
+      }
     }
     __syncthreads();
     const double coef = beta / (1.0 + beta * gmax);
@@ -443,7 +471,8 @@ int nb200_mvee_weights(const double* qT_d, int64_t n, int d, int max_updates,
     if (C > n) break;
     const int ld = (int)(((n + C - 1) / C + 3) / 4 * 4);
     const size_t smc = sizeof(double) * (2 * (size_t)D * (D | 1) +
-                                         2 * (size_t)D + (size_t)(d + 2) * ld);
+                                         (size_t)(1 + 2 * MVC_MAX_CLUSTER) * D +
+                                         (size_t)(d + 2) * ld);
     if (smc > 200 * 1024) continue;
     NB_CUDA(cudaFuncSetAttribute(k_mvee_cluster,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,

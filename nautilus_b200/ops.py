@@ -92,11 +92,19 @@ def profile_collect():
 
 
 class Workspace:
-    """Grow-only scratch buffer handed to the library."""
+    """Grow-only scratch buffer handed to the library.
+
+    The buffer is shared by every stack on the same (device, stream): a call
+    of the library uses it from start to end of its own launches only, and
+    launches on one stream are ordered.  (One buffer per stack meant a
+    cudaMalloc of up to a few hundred MB for every new bound -- and a
+    device-synchronising cudaFree when the stack died: ~1 s per config-2 run.)
+    """
+
+    _shared = {}
 
     def __init__(self, device):
         self.device = device
-        self.buf = None
 
     def get(self, n, d, pairs=0):
         if pairs > 0:
@@ -104,9 +112,19 @@ class Workspace:
                 int(n), int(d), int(pairs)))
         else:
             need = int(_lib.lib().nb200_workspace_bytes(int(n), int(d)))
-        if self.buf is None or self.buf.numel() < need:
-            self.buf = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self.buf, need
+        stream = torch.cuda.current_stream(self.device)
+        key = (self.device.index, stream.cuda_stream)
+        buf = Workspace._shared.get(key)
+        if buf is None or buf.numel() < need:
+            # grow by at least half so that a slowly rising demand does not
+            # reallocate on every call
+            have = 0 if buf is None else buf.numel()
+            buf = None
+            Workspace._shared.pop(key, None)
+            buf = torch.empty(max(need, have + have // 2), dtype=torch.uint8,
+                              device=self.device)
+            Workspace._shared[key] = buf
+        return buf, need
 
 
 class DeviceStack:

@@ -56,7 +56,9 @@ def main():
     wall = time.time() - t0
     if args.profile:
         prof.disable()
-        pstats.Stats(prof).sort_stats('cumulative').print_stats(28)
+        st = pstats.Stats(prof).sort_stats('cumulative')
+        st.print_stats(28)
+        st.print_callers('is_available|torch.empty|linalg_inv')
     raw = sum(b.outer_bound.n_sample for b in sampler.bounds[1:])
     emus = [nb.emulator for b in sampler.bounds[1:] for nb in b.neural_bounds
             if nb.emulator is not None]
