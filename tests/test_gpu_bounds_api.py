@@ -442,3 +442,43 @@ def test_tensor_core_trainer_follows_the_simt_trainer(golden, monkeypatch):
     print('final losses tc {} ffma {}'.format(
         [round(n.loss_, 6) for n in a.neural_networks],
         [round(n.loss_, 6) for n in b.neural_networks]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hidden', [(32, ), (47, ), (48, ), (64, 16),
+                                    (40, 40), (24, 40, 12)])
+def test_tensor_core_trainer_other_network_shapes(golden, monkeypatch,
+                                                  hidden):
+    """The other instantiations of k_mlp_fit_tc (1 and 2 hidden layers), a
+    fan-out whose padded width grows by the spare constant-one row (47 -> 48,
+    48 -> 64 columns) and a last hidden layer wider than 31 units (the
+    4-chunk output stage): one epoch from the same initial networks through
+    the same minibatches as the SIMT trainer, then a full fit."""
+    from nautilus_b200.neural import NeuralNetworkEmulator
+    g = golden('emulator_d5')
+    x, y = g['x'], g['y']
+
+    def fit(kind, **kw):
+        monkeypatch.setenv('NB200_FIT', kind)
+        return NeuralNetworkEmulator.train(
+            x, y, n_networks=2, seed=11,
+            neural_network_kwargs=dict(hidden_layer_sizes=hidden, **kw))
+
+    a, b = fit('tc', max_iter=1), fit('ffma', max_iter=1)
+    largest = 0.0
+    for na, nb_ in zip(a.neural_networks, b.neural_networks):
+        assert na.n_iter_ == nb_.n_iter_ == 1
+        assert abs(na.loss_ / nb_.loss_ - 1) < 0.05, (na.loss_, nb_.loss_)
+        for wa, wb in zip(na.coefs_ + na.intercepts_,
+                          nb_.coefs_ + nb_.intercepts_):
+            assert wa.shape == wb.shape
+            diff = np.abs(wa - wb)
+            assert np.mean(diff) < 2e-3, np.mean(diff)
+            assert np.max(diff) < 0.1, np.max(diff)
+            largest = max(largest, float(np.max(diff)))
+    # tf32 products leave a trace: bit-identical weights would mean that the
+    # shape fell outside the tensor-core envelope and both fits were SIMT
+    assert largest > 0.0
+    a = fit('tc')
+    rmse = np.sqrt(np.mean((a.predict(x) - y)**2))
+    assert rmse < 0.25 * np.std(y), rmse
