@@ -20,12 +20,11 @@ from .union import Union
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    """One side stream per device for the emulator fits, kept for the life of
+def _side_stream(device, which=0):
+    """Side streams of a device for the emulator fits, kept for the life of
     the process: a new stream per bound starts with an empty allocator pool,
-    and every tensor made under it was a cudaMalloc (0.5 ms each, ~2 s per
-    config-2 run)."""
-    key = (device.type, device.index)
+    and every tensor made under it is a cudaMalloc."""
+    key = (device.type, device.index, which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -68,24 +67,46 @@ class NautilusBound(_DeviceBound):
         clusters = Union.compute(
             live, enlarge_per_dim=enlarge_per_dim, n_points_min=n_points_min,
             bound_class=Ellipsoid, rng=rng)
+        # The emulator fits (32 SMs, ~0.1 s each) run on a side stream while
+        # the host goes on building bounds on the main stream.  The fit of the
+        # UNSPLIT live-point ellipsoid is started speculatively, before the
+        # split attempt (mixture EM + two enclosing ellipsoids, ~60 ms of
+        # host-driven work): most bounds of a unimodal problem keep the single
+        # ellipsoid, and the fit then overlaps the split attempt AND the outer
+        # bound instead of the outer bound alone.  If the split succeeds the
+        # speculative fit is dropped (it finishes in the background on its own
+        # stream) and one fit per cluster is enqueued as before.
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device, 0)
+        spec_stream = _side_stream(main.device, 1)
+        nb_kwargs = dict(enlarge_per_dim=enlarge_per_dim,
+                         n_networks=n_networks,
+                         neural_network_kwargs=neural_network_kwargs,
+                         pool=pool, rng=rng, mode=bound.mode, defer=True)
+        first = clusters.bounds[0]
+        spec_stream.wait_stream(main)
+        with torch.cuda.stream(spec_stream):
+            member = first.contains(points)
+            speculative = NeuralBound.compute(points[member], log_l[member],
+                                              log_l_min, **nb_kwargs)
+        # (device copies made under that stream stay with that stream)
+        first._invalidate()
+        first._dev_params = None
         while clusters.split(allow_overlap=False):
             pass
-        # The emulator fits (32 SMs, ~0.1-0.3 s each) are enqueued on a side
-        # stream and collected after the outer union has been built on the
-        # main stream: the two do not depend on each other, and the order in
-        # which `rng` is consumed is that of the sequential code.
-        bound.neural_bounds = []
-        main = torch.cuda.current_stream()
-        side = _side_stream(main.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            for ell in clusters.bounds:
-                member = ell.contains(points)
-                bound.neural_bounds.append(NeuralBound.compute(
-                    points[member], log_l[member], log_l_min,
-                    enlarge_per_dim=enlarge_per_dim, n_networks=n_networks,
-                    neural_network_kwargs=neural_network_kwargs, pool=pool,
-                    rng=rng, mode=bound.mode, defer=True))
+        if len(clusters.bounds) == 1 and clusters.bounds[0] is first:
+            bound.neural_bounds = [speculative]
+            side = spec_stream
+        else:
+            del speculative
+            bound.neural_bounds = []
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for ell in clusters.bounds:
+                    member = ell.contains(points)
+                    bound.neural_bounds.append(NeuralBound.compute(
+                        points[member], log_l[member], log_l_min,
+                        **nb_kwargs))
 
         # outer sampling bound, refined until close enough to the target volume
         bound.outer_bound = Union.compute(

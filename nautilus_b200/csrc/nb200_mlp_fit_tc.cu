@@ -988,8 +988,10 @@ bool fit_tc_plan(const int32_t* sizes, int n_lay, int64_t m, int batch,
   A.scr_off = fl; fl += 4 * FT_ROWS + 12 + 2 * FT_ROWS;
   fl = (fl + 31) / 32 * 32;
   A.smem_bytes = fl * 4;
-  // (the over-reads of the gradient operands must stay inside)
-  if (A.et_off[H] + 16 * FT_SBO > A.smem_bytes) return false;
+  // (the over-reads of the gradient operands must stay inside: small
+  // networks get the slack as padding)
+  if (A.et_off[H] + 16 * FT_SBO > A.smem_bytes)
+    A.smem_bytes = (A.et_off[H] + 16 * FT_SBO + 127) / 128 * 128;
   if (A.smem_bytes > 200 * 1024) return false;
   A.a_col[0] = col; col += r32(A.KP[0]);
   for (int l = 0; l < H; ++l) {
