@@ -722,7 +722,9 @@ def run_gpu(args):
         t0 = time.perf_counter()
         smp = Sampler(lambda x: x, like, n_dim=D, n_live=2000, seed=0,
                       emulator_arith=args.mlp)
-        ok = smp.run(n_eff=40000, discard_exploration=True, timeout=600)
+        # N_eff = 1e5: statistical error 1 / sqrt(N_eff) = 0.0032, so that the
+        # 0.01 bar is a 3-sigma statement about the method, not a coin flip
+        ok = smp.run(n_eff=100000, discard_exploration=True, timeout=600)
         raw_total = sum(b.outer_bound.n_sample for b in smp.bounds[1:])
         logz = {'log_z': float(smp.log_z), 'log_z_true': like.log_z_true,
                 'delta_log_z': abs(float(smp.log_z) - like.log_z_true),
@@ -732,7 +734,7 @@ def run_gpu(args):
                 'n_like': int(smp.n_like), 'n_bounds': len(smp.bounds),
                 'raw_proposals': int(raw_total),
                 'run': 'Sampler(prior=identity, Gaussian(30, sigma=0.1), '
-                       'n_live=2000, seed=0).run(n_eff=40000, '
+                       'n_live=2000, seed=0).run(n_eff=100000, '
                        'discard_exploration=True)'}
 
     line = {

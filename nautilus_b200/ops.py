@@ -551,7 +551,7 @@ def top_k(values, k):
     return above
 
 
-def mvee_weights(q_t, max_updates=3000, tol=1e-3):
+def mvee_weights(q_t, max_updates=1500, tol=1e-3):
     """Khachiyan weights of the MVEE of the points ``q_t`` f64[d, n] (CUDA,
     coordinate-major, ideally whitened) -- basic.py:175-241.  Returns
     (u f64[n] CUDA, iterations int32[1] CUDA)."""

@@ -201,7 +201,8 @@ def test_config3_like_wide_network_training():
 def test_config2_delta_log_z_and_posterior_moments():
     """BASELINE config 2 end to end through the drop-in Sampler: 30-D
     N(0.5, 0.1^2 I), n_live = 2000, tensor-core emulator, device cycle.  Run to
-    N_eff >= 4e4 (statistical error 1/sqrt(N_eff) = 0.005) and
+    N_eff >= 1e5 (statistical error 1/sqrt(N_eff) = 0.0032: SURVEY.md 8d asks
+    for >= 4e4, where the 0.01 bar is only two sigma) and
     assert north_star's |delta log Z| <= 0.01 against the analytic evidence,
     plus the posterior mean and covariance (the reference's own tolerances,
     tests/test_sampler.py:167-215: 0.01 on the mean, 0.001 on the
@@ -210,8 +211,8 @@ def test_config2_delta_log_z_and_posterior_moments():
     like = likelihoods.Gaussian(d, sigma=0.1)
     sampler = Sampler(lambda x: x, like, n_dim=d, n_live=2000, seed=0)
     assert sampler.device_cycle and sampler.mlp_mode == ops.MLP_F16
-    assert sampler.run(n_eff=40000, discard_exploration=True, timeout=600)
-    assert sampler.n_eff >= 40000
+    assert sampler.run(n_eff=100000, discard_exploration=True, timeout=600)
+    assert sampler.n_eff >= 100000
     delta = abs(sampler.log_z - like.log_z_true)
     print('config 2: log Z = {:+.5f} (truth {:+.1e}), |delta| = {:.5f}, '
           'N_eff = {:.0f}, {} bounds, {} likelihood calls'.format(
