@@ -72,3 +72,23 @@ class PhiloxStream:
         start = self.offset
         self.offset += int(n)
         return start
+
+    # -- checkpoints: the stream is three integers -------------------------
+    def write(self, group):
+        """Stands in for the PCG64 state the reference stores
+        (nautilus/sampler.py:1325-1329)."""
+        group.attrs['philox_seed'] = np.int64(self.seed)
+        group.attrs['philox_stream_id'] = np.int64(self.stream_id)
+        group.attrs['philox_offset'] = np.int64(self.offset)
+
+    @classmethod
+    def read(cls, group, rng=None):
+        """The stored stream, or a fresh one drawn from ``rng`` when the
+        group was written by the reference (no Philox attributes)."""
+        if 'philox_seed' not in group.attrs:
+            return cls(rng)
+        stream = cls.__new__(cls)
+        stream.seed = int(group.attrs['philox_seed'])
+        stream.stream_id = int(group.attrs['philox_stream_id'])
+        stream.offset = int(group.attrs['philox_offset'])
+        return stream

@@ -71,6 +71,20 @@ class UnitCube(_DeviceBound):
     def log_v(self):
         return 0
 
+    def write(self, group):
+        """(basic.py:100-110)."""
+        group.attrs['type'] = 'UnitCube'
+        group.attrs['n_dim'] = self.n_dim
+        self.stream.write(group)
+
+    @classmethod
+    def read(cls, group, rng=None):
+        """(basic.py:112-137)."""
+        bound = cls()
+        bound.n_dim = int(group.attrs['n_dim'])
+        bound.stream = PhiloxStream.read(group, rng)
+        return bound
+
 
 class Ellipsoid(_DeviceBound):
     r"""Ellipsoid (x - c)^T A (x - c) <= 1 (nautilus/bounds/basic.py:244-449).
@@ -144,6 +158,25 @@ class Ellipsoid(_DeviceBound):
         return (np.sum(np.log(np.diag(self.B))) +
                 0.5 * self.n_dim * np.log(np.pi) -
                 gammaln(self.n_dim / 2.0 + 1))
+
+    def write(self, group):
+        """(basic.py:396-407)."""
+        group.attrs['type'] = 'Ellipsoid'
+        for key in ['n_dim', 'c', 'A', 'B', 'B_inv']:
+            group.attrs[key] = getattr(self, key)
+        self.stream.write(group)
+
+    @classmethod
+    def read(cls, group, rng=None):
+        """(basic.py:409-437).  The matrices are taken as stored (a file
+        written by the reference holds a dense ``B_inv``; the kernels accept
+        both forms)."""
+        bound = cls()
+        bound.n_dim = int(group.attrs['n_dim'])
+        for key in ['c', 'A', 'B', 'B_inv']:
+            setattr(bound, key, np.array(group.attrs[key], dtype=float))
+        bound.stream = PhiloxStream.read(group, rng)
+        return bound
 
 
 class UnitCubeEllipsoidMixture(_DeviceBound):
@@ -244,6 +277,30 @@ class UnitCubeEllipsoidMixture(_DeviceBound):
     @property
     def log_v(self):
         return 0 if self.ellipsoid is None else self.ellipsoid.log_v
+
+    def write(self, group):
+        """(basic.py:657-673)."""
+        group.attrs['type'] = 'UnitCubeEllipsoidMixture'
+        group.attrs['n_dim'] = self.n_dim
+        group.create_dataset('dim_cube', data=self.dim_cube)
+        if self.cube is not None:
+            self.cube.write(group.create_group('cube'))
+        if self.ellipsoid is not None:
+            self.ellipsoid.write(group.create_group('ellipsoid'))
+        self.stream.write(group)
+
+    @classmethod
+    def read(cls, group, rng=None):
+        """(basic.py:675-712)."""
+        bound = cls()
+        bound.n_dim = int(group.attrs['n_dim'])
+        bound.dim_cube = np.array(group['dim_cube'], dtype=bool)
+        bound.cube = (UnitCube.read(group['cube'], rng=rng)
+                      if np.any(bound.dim_cube) else None)
+        bound.ellipsoid = (Ellipsoid.read(group['ellipsoid'], rng=rng)
+                           if not np.all(bound.dim_cube) else None)
+        bound.stream = PhiloxStream.read(group, rng)
+        return bound
 
     def reset(self, rng=None):
         if rng is not None:

@@ -271,6 +271,67 @@ class NautilusBound(_DeviceBound):
             return 0
         return len(self.neural_bounds) * len(emu.neural_networks)
 
+    # -- checkpoints --------------------------------------------------------
+    def _fifo_host(self):
+        if self._buffer is None:
+            return np.zeros((0, self.n_dim))
+        return self._buffer.cpu().numpy()
+
+    def write(self, group):
+        """Layout of nautilus/bounds/nautilus.py:292-317 plus the Philox
+        stream of the bound."""
+        group.attrs['type'] = 'NautilusBound'
+        group.attrs['n_dim'] = self.n_dim
+        group.attrs['n_neural_bounds'] = len(self.neural_bounds)
+        for i, neural_bound in enumerate(self.neural_bounds):
+            neural_bound.write(group.create_group('neural_bound_{}'.format(i)))
+        self.outer_bound.write(group.create_group('outer_bound'))
+        group.create_dataset('points', data=self._fifo_host(),
+                             maxshape=(None, self.n_dim))
+        group.attrs['n_sample'] = self.n_sample
+        group.attrs['n_reject'] = self.n_reject
+        self.stream.write(group)
+
+    def update(self, group):
+        """(nautilus.py:319-333)."""
+        group.attrs['n_sample'] = self.n_sample
+        group.attrs['n_reject'] = self.n_reject
+        self.outer_bound.update(group['outer_bound'])
+        fifo = self._fifo_host()
+        group['points'].resize(fifo.shape)
+        group['points'][...] = fifo
+        self.stream.write(group)
+
+    @classmethod
+    def read(cls, group, rng=None, mode=None):
+        """(nautilus.py:335-380).  ``mode``: emulator arithmetic of the bound
+        (as in ``compute``).  A group written by the reference has no Philox
+        attributes: the streams are then drawn from ``rng``."""
+        if 'shift' in group:
+            raise NotImplementedError(
+                'periodic parameters (PhaseShift) are outside the scope of '
+                'nautilus_b200.')
+        bound = cls()
+        bound.rng = np.random.default_rng() if rng is None else rng
+        bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
+        bound.n_dim = int(group.attrs['n_dim'])
+        bound.shift = None
+        bound.neural_bounds = []
+        while 'neural_bound_{}'.format(len(bound.neural_bounds)) in group:
+            bound.neural_bounds.append(NeuralBound.read(
+                group['neural_bound_{}'.format(len(bound.neural_bounds))],
+                rng=bound.rng, mode=bound.mode))
+        bound.outer_bound = Union.read(group['outer_bound'], rng=bound.rng)
+        bound.stream = PhiloxStream.read(group, bound.rng)
+        bound._clear()
+        bound.n_sample = int(group.attrs['n_sample'])
+        bound.n_reject = int(group.attrs['n_reject'])
+        fifo = np.array(group['points'], dtype=float)
+        if len(fifo) > 0:
+            bound._buffer = torch.from_numpy(
+                np.ascontiguousarray(fifo)).to(default_device())
+        return bound
+
     def reset(self, rng=None):
         """Forget sampling progress; optionally reseed (nautilus.py:382-397)."""
         self._buffer = None

@@ -81,6 +81,27 @@ class NeuralBound(_DeviceBound):
             np.polyfit(score, predicted, 3), np.amin(score[live])))
         return self
 
+    def write(self, group):
+        """(nautilus/bounds/neural.py:128-141)."""
+        group.attrs['n_dim'] = self.n_dim
+        group.attrs['score_predict_min'] = self.score_predict_min
+        self.outer_bound.write(group.create_group('outer_bound'))
+        if self.emulator is not None:
+            self.emulator.write(group.create_group('emulator'))
+
+    @classmethod
+    def read(cls, group, rng=None, mode=None):
+        """(nautilus/bounds/neural.py:143-173).  ``mode``: emulator
+        arithmetic of ``contains`` (as in ``compute``)."""
+        bound = cls()
+        bound.mode = NeuralNetworkEmulator.mode if mode is None else mode
+        bound.n_dim = int(group.attrs['n_dim'])
+        bound.score_predict_min = float(group.attrs['score_predict_min'])
+        bound.outer_bound = Ellipsoid.read(group['outer_bound'], rng=rng)
+        bound.emulator = (NeuralNetworkEmulator.read(group['emulator'])
+                          if 'emulator' in group else None)
+        return bound
+
     def nb_spec(self):
         return dict(ell=self.outer_bound.ell_spec(),
                     emulator=None if self.emulator is None

@@ -180,6 +180,76 @@ class Union(_DeviceBound):
         return logsumexp(self.log_v_all) + np.log(
             1.0 - self.n_reject / self.n_sample)
 
+    # -- checkpoints --------------------------------------------------------
+    def _fifo_host(self):
+        """The FIFO of accepted points the reference stores as ``points``."""
+        if self._buffer is None:
+            return np.zeros((0, self.n_dim))
+        return self._buffer.cpu().numpy()
+
+    def write(self, group):
+        """Layout of nautilus/bounds/union.py:345-370 (type 'MultiEllipsoid'
+        is the reference's name for it), plus the split bookkeeping and the
+        Philox stream."""
+        group.attrs['type'] = 'MultiEllipsoid'
+        for key in ['n_dim', 'log_v_all', 'enlarge_per_dim', 'n_points_min',
+                    'n_sample', 'n_reject']:
+            group.attrs[key] = getattr(self, key)
+        group.attrs['unit'] = self.cube is not None
+        if self.cube is not None:
+            self.cube.write(group.create_group('cube'))
+        group.attrs['bound_class'] = self.bounds[0].__class__.__name__
+        group.attrs['block'] = np.asarray(self.block, dtype=bool)
+        for i, bound in enumerate(self.bounds):
+            bound.write(group.create_group('bound_{}'.format(i)))
+        for i, points in enumerate(self.points_bounds):
+            group.create_dataset('points_bound_{}'.format(i), data=points)
+        group.create_dataset('points', data=self._fifo_host(),
+                             maxshape=(None, self.n_dim))
+        self.stream.write(group)
+
+    def update(self, group):
+        """(union.py:372-384)."""
+        group.attrs['n_sample'] = self.n_sample
+        group.attrs['n_reject'] = self.n_reject
+        fifo = self._fifo_host()
+        group['points'].resize(fifo.shape)
+        group['points'][...] = fifo
+        self.stream.write(group)
+
+    @classmethod
+    def read(cls, group, rng=None):
+        """(union.py:386-429)."""
+        bound = cls()
+        bound.rng = np.random.default_rng() if rng is None else rng
+        bound.n_dim = int(group.attrs['n_dim'])
+        bound.log_v_all = np.atleast_1d(np.array(group.attrs['log_v_all'],
+                                                 dtype=float))
+        bound.enlarge_per_dim = float(group.attrs['enlarge_per_dim'])
+        bound.n_points_min = int(group.attrs['n_points_min'])
+        bound.cube = (UnitCube.read(group['cube'], rng=bound.rng)
+                      if group.attrs['unit'] else None)
+        bound.bound_class = (Ellipsoid if group.attrs['bound_class'] ==
+                             'Ellipsoid' else UnitCubeEllipsoidMixture)
+        n = len(bound.log_v_all)
+        bound.bounds = [bound.bound_class.read(
+            group['bound_{}'.format(i)], rng=bound.rng) for i in range(n)]
+        bound.points_bounds = [np.array(group['points_bound_{}'.format(i)])
+                               for i in range(n)]
+        bound.block = (np.array(group.attrs['block'], dtype=bool)
+                       if 'block' in group.attrs else np.array(
+                           [len(p) < 2 * bound.n_points_min
+                            for p in bound.points_bounds]))
+        bound.stream = PhiloxStream.read(group, bound.rng)
+        bound._clear()
+        bound.n_sample = int(group.attrs['n_sample'])
+        bound.n_reject = int(group.attrs['n_reject'])
+        fifo = np.array(group['points'], dtype=float)
+        if len(fifo) > 0:
+            bound._buffer = torch.from_numpy(
+                np.ascontiguousarray(fifo)).to(default_device())
+        return bound
+
     def reset(self, rng=None):
         """Forget sampling progress; optionally reseed (union.py:431-450)."""
         self._buffer = None

@@ -136,6 +136,52 @@ class NeuralNetworkEmulator:
         emulator._stack = None
         return emulator
 
+    def write(self, group):
+        """Layout of nautilus/neural.py:118-146: per network i the scalar
+        attributes as '<name>_<i>' and the layers as 'coefs_<k>_<i>' /
+        'intercepts_<k>_<i>'.  The few extra attributes scikit-learn's
+        ``predict`` needs are written too, so that the reference can load the
+        emulator into an ``MLPRegressor``."""
+        self.wait()
+        group.attrs['n_networks'] = len(self.neural_networks)
+        for i, network in enumerate(self.neural_networks):
+            attrs = dict(n_layers_=network.n_layers_, n_iter_=network.n_iter_,
+                         loss_=network.loss_, activation='relu',
+                         out_activation_='identity', n_outputs_=1,
+                         n_features_in_=network.coefs_[0].shape[0])
+            for key, value in attrs.items():
+                group.attrs['{}_{}'.format(key, i)] = value
+            for k in range(network.n_layers_ - 1):
+                group.create_dataset('coefs_{}_{}'.format(k, i),
+                                     data=network.coefs_[k])
+                group.create_dataset('intercepts_{}_{}'.format(k, i),
+                                     data=network.intercepts_[k])
+        group.create_dataset('mean', data=self.mean)
+        group.create_dataset('scale', data=self.scale)
+
+    @classmethod
+    def read(cls, group):
+        """(nautilus/neural.py:148-187)."""
+        emulator = cls()
+        emulator.mean = np.array(group['mean'], dtype=float)
+        emulator.scale = np.array(group['scale'], dtype=float)
+        emulator.neural_networks = []
+        for i in range(int(group.attrs['n_networks'])):
+            coefs, intercepts = [], []
+            while 'coefs_{}_{}'.format(len(coefs), i) in group:
+                k = len(coefs)
+                coefs.append(np.array(group['coefs_{}_{}'.format(k, i)],
+                                      dtype=float))
+                intercepts.append(np.array(
+                    group['intercepts_{}_{}'.format(k, i)], dtype=float))
+            stored = {key: group.attrs['{}_{}'.format(key, i)]
+                      if '{}_{}'.format(key, i) in group.attrs else default
+                      for key, default in (('n_iter_', 0), ('loss_', np.nan))}
+            emulator.neural_networks.append(FittedNetwork(
+                coefs, intercepts, stored['n_iter_'], stored['loss_']))
+        emulator._stack = None
+        return emulator
+
     def emu_spec(self):
         return dict(mean=self.mean, scale=self.scale,
                     coefs=[n.coefs_ for n in self.neural_networks],

@@ -27,10 +27,18 @@ Differences that are deliberate and documented in DESIGN.md:
     consumes WHOLE raw batches: ``n_batch`` is the least number of likelihood
     evaluations of a step, not the exact number (the bookkeeping --
     ``shell_n``, ``shell_n_sample``, the bound counters -- is exact);
-  * HDF5 checkpointing and periodic parameters are out of scope and raise.
+  * checkpoints (``filepath=`` / ``resume=``, ``write``,
+    ``write_shell_update``) keep the reference's layout; they go to HDF5 when
+    h5py is installed and to the built-in '.npz' container (``_store.py``)
+    otherwise.  A batch takes well under a millisecond here, so ``run``
+    rewrites the file at structural events (new bound, end of exploration,
+    end of the run) and otherwise at most every ``checkpoint_interval``
+    seconds, not after every batch;
+  * periodic parameters are out of scope and raise.
 """
 
 from functools import partial
+from pathlib import Path
 from shutil import get_terminal_size
 from time import time
 
@@ -39,6 +47,7 @@ import torch
 from scipy.special import logsumexp
 
 from . import ops
+from ._store import check_suffix, open_store, require_backend
 from .bounds import NautilusBound, UnitCube
 from ._device import default_device
 from .likelihoods import DeviceLikelihood
@@ -108,10 +117,10 @@ class Sampler:
                  likelihood_args=[], likelihood_kwargs={}, n_batch=None,
                  n_like_new_bound=None, vectorized=False, pass_dict=None,
                  pool=None, seed=None, blobs_dtype=None, filepath=None,
-                 resume=True, emulator_arith='auto', device_cycle=True):
+                 resume=True, emulator_arith='auto', device_cycle=True,
+                 checkpoint_interval=30.0):
         if filepath is not None:
-            raise NotImplementedError(
-                'HDF5 checkpointing is outside the scope of nautilus_b200.')
+            require_backend(filepath)
         if periodic is not None:
             raise NotImplementedError(
                 'periodic parameters are outside the scope of nautilus_b200.')
@@ -231,7 +240,10 @@ class Sampler:
         self.shell_log_v = np.zeros(0, dtype=float)
         self.shell_n_sample_exp = np.zeros(0, dtype=int)
         self.shell_end_exp = np.zeros(0, dtype=int)
-        self.filepath = None
+        self.filepath = filepath
+        self.checkpoint_interval = float(checkpoint_interval)
+        self._t_checkpoint = -np.inf    # time of the last write of the file
+        self._dirty = False             # state newer than the file
         self._arena = None          # created with the first bound
         self._blobs_all = None      # host, aligned with arena positions
         self._host_cache = (None, None)
@@ -245,6 +257,8 @@ class Sampler:
         self._like_params = None
         self._cycle_buf = None
         self.cycle_stats = dict(calls=0, raw=0, d2h_bytes=0)
+        if resume and filepath is not None and Path(filepath).exists():
+            self._resume(filepath)
 
     # ------------------------------------------------------------------
     # scheduler (sampler.py:373-505)
@@ -278,21 +292,30 @@ class Sampler:
                     self.add_bound(verbose=verbose)
                     self.n_update_iter = 0
                     self.n_like_iter = 0
+                    self._checkpoint(force=True)
                 n_like_before = self.n_like
                 self.n_update_iter += self.add_samples(-1, verbose=verbose)
                 self.n_like_iter += self.n_like - n_like_before
+                self._checkpoint()
                 if self.f_live <= f_live:
                     self._finish_exploration(discard_exploration)
+                    self._checkpoint(force=True)
             elif np.any(self.shell_n < n_shell):
                 self.add_samples(int(np.flatnonzero(
                     self.shell_n < n_shell)[0]), verbose=verbose)
+                self._checkpoint()
             elif self.n_eff < n_eff:
                 gain = (self.shell_log_l + self.shell_log_v -
                         0.5 * np.log(self.shell_n) -
                         0.5 * np.log(self.shell_n_eff))
                 self.add_samples(int(np.argmax(gain)), verbose=verbose)
+                self._checkpoint()
             success = done()
 
+        # whatever happened since the last write (the reference's file is
+        # current after every batch, sampler.py:449-494)
+        if self._dirty:
+            self._checkpoint(force=True)
         if verbose:
             self.print_status('Finished' if success else 'Stopped')
         return success
@@ -1028,6 +1051,240 @@ class Sampler:
                     self._sums[shell] = None
                     self.update_shell_info(shell)
         return True
+
+    # ------------------------------------------------------------------
+    # checkpoints (sampler.py:329-371, 1253-1377)
+    # ------------------------------------------------------------------
+    _ATTRS_CONFIG = ['n_dim', 'n_live', 'n_update', 'n_like_new_bound',
+                     'enlarge_per_dim', 'n_points_min', 'split_threshold',
+                     'n_networks', 'n_batch', 'vectorized', 'pass_dict']
+    _ATTRS_STATE = ['n_like', 'explored', '_discard_exploration', 'shell_n',
+                    'shell_n_sample', 'shell_n_eff', 'shell_log_l_min',
+                    'shell_log_l', 'shell_log_v', 'shell_n_sample_exp',
+                    'shell_end_exp', 'n_update_iter', 'n_like_iter']
+
+    def _checkpoint(self, force=False):
+        """``run``'s hook: rewrite the file now (``force``) or if the last
+        write is older than ``checkpoint_interval`` seconds."""
+        if self.filepath is None:
+            return
+        self._dirty = True
+        if force or time() - self._t_checkpoint >= self.checkpoint_interval:
+            self.write(self.filepath, overwrite=True)
+
+    def _write_rng(self, group):
+        state = self.rng.bit_generator.state
+        group.attrs['rng_state'] = str(state['state']['state'])
+        group.attrs['rng_inc'] = str(state['state']['inc'])
+        group.attrs['rng_has_uint32'] = state['has_uint32']
+        group.attrs['rng_uinteger'] = state['uinteger']
+
+    def _shell_arrays(self):
+        """Per shell (points, log_l, blobs) and the transfer candidates, as
+        the reference stores them."""
+        pts, ll, tag = self._host()
+        shells = []
+        for i in range(len(self.bounds)):
+            sel = tag == i
+            shells.append((pts[sel], ll[sel], None if self._blobs_all is None
+                           else self._blobs_all[:len(tag)][sel]))
+        blobs_t = (None if self._blobs_all is None
+                   else self._blobs_all[self._t_pos])
+        return shells, (pts[self._t_pos], ll[self._t_pos], blobs_t)
+
+    def write(self, filepath, overwrite=False):
+        """Write the sampler to disk in the reference's layout
+        (sampler.py:1253-1332): group 'sampler' with the settings and shell
+        bookkeeping as attributes and 'points_<i>' / 'log_l_<i>'
+        [/ 'blobs_<i>'] per shell plus the transfer candidates, and one group
+        'bound_<i>' per bound.  '.h5' / '.hdf5' need h5py; '.npz' is the
+        built-in container.
+
+        Raises ValueError for another file extension and RuntimeError if the
+        file exists and ``overwrite`` is False."""
+        filepath = Path(filepath)
+        check_suffix(filepath)
+        if filepath.exists() and not overwrite:
+            raise RuntimeError(
+                'File {} already exists.'.format(str(filepath)))
+        filepath.parent.mkdir(parents=True, exist_ok=True)
+        # ('w': the '.npz' container replaces the old file atomically when it
+        # is closed, HDF5 truncates)
+        fstream = open_store(filepath, 'w')
+        group = fstream.create_group('sampler')
+        if len(self.bounds) > 0 and not hasattr(self, 'n_update_iter'):
+            self.n_update_iter, self.n_like_iter = -self.n_live, 0
+        for key in self._ATTRS_CONFIG + self._ATTRS_STATE:
+            if hasattr(self, key):
+                group.attrs[key] = getattr(self, key)
+        for key, value in self.neural_network_kwargs.items():
+            group.attrs['neural_network_{}'.format(key)] = value
+        # not in the reference: where the exploration phase ended, per shell,
+        # is 'shell_end_exp'; the emulator arithmetic of the bounds
+        group.attrs['emulator_arith'] = self.emulator_arith
+        # acceptance seen per shell so far (sizes the next raw batch)
+        group.attrs['p_shell'] = np.array(
+            [[i, got, raw] for i, (got, raw) in sorted(self._p_shell.items())],
+            dtype=np.int64).reshape(-1, 3)
+
+        shells, (points_t, log_l_t, blobs_t) = self._shell_arrays()
+        for shell, (points, log_l, blobs) in enumerate(shells):
+            group.create_dataset('points_{}'.format(shell), data=points,
+                                 maxshape=(None, self.n_dim))
+            group.create_dataset('log_l_{}'.format(shell), data=log_l,
+                                 maxshape=(None, ))
+            if blobs is not None:
+                group.create_dataset(
+                    'blobs_{}'.format(shell), data=blobs,
+                    maxshape=(None, ) + tuple(blobs.shape[1:]))
+        group.create_dataset('points_t', data=points_t,
+                             maxshape=(None, self.n_dim))
+        group.create_dataset('shell_t', data=self._t_shell,
+                             maxshape=(None, ))
+        group.create_dataset('log_l_t', data=log_l_t, maxshape=(None, ))
+        if blobs_t is not None:
+            group.create_dataset('blobs_t', data=blobs_t,
+                                 maxshape=(None, ) + tuple(blobs_t.shape[1:]))
+
+        for i, bound in enumerate(self.bounds):
+            bound.write(fstream.create_group('bound_{}'.format(i)))
+        self._write_rng(group)
+        fstream.close()
+        self._t_checkpoint = time()
+        self._dirty = False
+
+    def write_shell_update(self, filepath, shell):
+        """Update the data of one shell in an existing file
+        (sampler.py:1334-1377)."""
+        if shell < 0:
+            shell = len(self.bounds) + shell
+        fstream = open_store(Path(filepath), 'r+')
+        group = fstream['sampler']
+        for key in ['n_like', 'shell_n', 'shell_n_sample', 'shell_n_eff',
+                    'shell_log_l_min', 'shell_log_l', 'shell_log_v',
+                    'n_update_iter', 'n_like_iter']:
+            group.attrs[key] = getattr(self, key)
+
+        def store(name, data):
+            if data is None:
+                return
+            if name not in group:
+                group.create_dataset(
+                    name, data=data,
+                    maxshape=(None, ) + tuple(data.shape[1:]))
+                return
+            group[name].resize(data.shape)
+            group[name][...] = data
+
+        shells, (points_t, log_l_t, blobs_t) = self._shell_arrays()
+        points, log_l, blobs = shells[shell]
+        store('points_{}'.format(shell), points)
+        store('log_l_{}'.format(shell), log_l)
+        store('blobs_{}'.format(shell), blobs)
+        store('points_t', points_t)
+        store('shell_t', self._t_shell)
+        store('log_l_t', log_l_t)
+        store('blobs_t', blobs_t)
+        if isinstance(self.bounds[shell], NautilusBound):
+            self.bounds[shell].update(fstream['bound_{}'.format(shell)])
+        self._write_rng(group)
+        fstream.close()
+        self._t_checkpoint = time()
+
+    def _resume(self, filepath):
+        """Continue from a checkpoint (sampler.py:330-371).  The stored
+        points go back into the device arena: first what every shell held
+        when the exploration phase ended ('shell_end_exp'), then the rest, so
+        that ``discard_exploration`` remains a test on arena positions;
+        chronology inside a shell is kept."""
+        with open_store(filepath, 'r') as fstream:
+            group = fstream['sampler']
+            self.rng.bit_generator.state = dict(
+                bit_generator='PCG64',
+                state=dict(state=int(group.attrs['rng_state']),
+                           inc=int(group.attrs['rng_inc'])),
+                has_uint32=int(group.attrs['rng_has_uint32']),
+                uinteger=int(group.attrs['rng_uinteger']))
+            for key in self._ATTRS_STATE:
+                if key not in group.attrs:      # written before run()
+                    continue
+                value = group.attrs[key]
+                if np.ndim(value) == 0:
+                    value = value.item() if hasattr(value, 'item') else value
+                else:
+                    value = np.array(value)
+                setattr(self, key, value)
+            self.explored = bool(self.explored)
+            self._discard_exploration = bool(self._discard_exploration)
+            if 'p_shell' in group.attrs:
+                self._p_shell = {int(i): (int(got), int(raw)) for i, got, raw
+                                 in np.array(group.attrs['p_shell']).reshape(
+                                     -1, 3)}
+            self.shell_n = self.shell_n.astype(int)
+            self.shell_n_sample = self.shell_n_sample.astype(int)
+            n_shells = len(self.shell_n)
+
+            points = [np.array(group['points_{}'.format(i)], dtype=float)
+                      .reshape(-1, self.n_dim) for i in range(n_shells)]
+            log_l = [np.array(group['log_l_{}'.format(i)], dtype=float)
+                     for i in range(n_shells)]
+            blobs = None
+            if 'blobs_0' in group:
+                blobs = [np.array(group['blobs_{}'.format(i)])
+                         for i in range(n_shells)]
+                self.blobs_dtype = blobs[0].dtype
+            points_t = np.array(group['points_t'], dtype=float).reshape(
+                -1, self.n_dim)
+            log_l_t = np.array(group['log_l_t'], dtype=float)
+            shell_t = np.array(group['shell_t']).astype(int)
+            blobs_t = np.array(group['blobs_t']) if 'blobs_t' in group \
+                else None
+
+            self.bounds = [UnitCube.read(fstream['bound_0'], rng=self.rng)]
+            for i in range(1, n_shells):
+                self.bounds.append(NautilusBound.read(
+                    fstream['bound_{}'.format(i)], rng=self.rng,
+                    mode=self.mlp_mode))
+
+        self._arena = _Arena(self.n_dim, default_device())
+        if self.explored:
+            end = np.minimum(np.asarray(self.shell_end_exp, dtype=int),
+                             [len(p) for p in points])
+        else:
+            end = np.array([len(p) for p in points], dtype=int)
+        parts = [(i, slice(0, end[i])) for i in range(n_shells)] + \
+                [(i, slice(end[i], None)) for i in range(n_shells)]
+        blob_parts = []
+        for n_part, (i, part) in enumerate(parts):
+            if n_part == n_shells:
+                self._explore_end = self._arena.n if self.explored else 0
+            if len(points[i][part]) == 0:
+                continue
+            self._arena.append(points[i][part], log_l[i][part], i)
+            if blobs is not None:
+                blob_parts.append(blobs[i][part])
+        if not self.explored:
+            self._explore_end = 0
+        # transfer candidates: stored in the arena, tagged with their donor
+        self._t_pos = self._arena.n + np.arange(len(points_t), dtype=np.int64)
+        self._t_shell = shell_t
+        for s in np.unique(shell_t):
+            sel = shell_t == s
+            self._arena.append(points_t[sel], log_l_t[sel], -2 - int(s))
+            if blobs is not None and blobs_t is not None:
+                blob_parts.append(blobs_t[sel])
+        if len(shell_t):
+            # (appended donor by donor: positions follow that order)
+            order = np.argsort(shell_t, kind='stable')
+            inverse = np.empty_like(order)
+            inverse[order] = np.arange(len(order))
+            self._t_pos = self._t_pos[0] + inverse.astype(np.int64)
+        if blobs is not None:
+            self._blobs_all = (np.concatenate(blob_parts) if blob_parts
+                               else np.zeros(0, dtype=self.blobs_dtype))
+        self._sums = [None] * n_shells
+        self._stack = None
+        self._t_checkpoint = time()
 
     # ------------------------------------------------------------------
     def print_status(self, status='', header=False, end='\n'):

@@ -244,8 +244,8 @@ def test_sampler_errors():
         Sampler(lambda x: x, lambda x: 0.0)                  # n_dim missing
     with pytest.raises(ValueError):
         Sampler(lambda x: x, lambda x: 0.0, n_dim=1)
-    with pytest.raises(NotImplementedError):
-        Sampler(lambda x: x, lambda x: 0.0, n_dim=2, filepath='x.hdf5')
+    with pytest.raises(ValueError):                          # file ending
+        Sampler(lambda x: x, lambda x: 0.0, n_dim=2, filepath='x.txt')
     s = Sampler(lambda x: x, lambda x: 0.0, n_dim=2)
     with pytest.raises(ValueError):
         s.discard_exploration = 1
