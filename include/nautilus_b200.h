@@ -297,6 +297,24 @@ int nb200_mvee_weights(const double* qT_d, int64_t n, int d, int max_updates,
                        void* workspace_d, size_t workspace_bytes,
                        void* stream);
 
+/* Two-component Gaussian mixture by EM, n_init restarts in one launch: the
+ * GaussianMixture(n_components=2, n_init=10) call of Union.split
+ * (bounds/union.py:185-187).  x_d f64[n, d] row-major (the whitened points of
+ * the bound to split); label_d u8[n_init, n] the initial hard assignment of
+ * every restart (k-means++ seeding, drawn by the caller's generator).  Every
+ * restart runs EM until its mean log likelihood moves by less than tol, at
+ * most max_iter steps; reg is added to the diagonal of the covariances.
+ * Outputs: log_p_d f64[n_init, 2, n] = log(w_k N(x | mu_k, C_k)) of the last
+ * accepted step, score_d f64[n_init] = the restart's mean log likelihood
+ * (-inf: abandoned), iters_d i32[n_init].  nb200_gmm2_applicable: 1 if the
+ * shape fits the kernel (d up to ~55: both packed moment sets, the factors and a CTA's share of the points or at least
+ * their responsibilities in shared memory). */
+int nb200_gmm2_applicable(int64_t n, int d);
+int nb200_gmm2_em(const double* x_d, int64_t n, int d,
+                  const uint8_t* label_d, int n_init, int max_iter, double tol,
+                  double reg, double* log_p_d, double* score_d,
+                  int32_t* iters_d, void* stream);
+
 /* ---- host-buffer session: the loop around add_samples ------------------- */
 
 /* A session owns the device buffers, two streams and pinned host buffers for

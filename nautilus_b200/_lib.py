@@ -172,6 +172,9 @@ PROTOTYPES = {
     'nb200_mvee_workspace_bytes': (_sz, [_i64]),
     'nb200_mvee_weights': (_int, [_vp, _i64, _int, _int, _dbl, _vp, _vp, _vp,
                                   _sz, _vp]),
+    'nb200_gmm2_applicable': (_int, [_i64, _int]),
+    'nb200_gmm2_em': (_int, [_vp, _i64, _int, _vp, _int, _int, _dbl, _dbl,
+                             _vp, _vp, _vp, _vp]),
     'nb200_session_create': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int,
                                     _int, _vp]),
     'nb200_session_destroy': (_int, [_vp]),

@@ -208,8 +208,16 @@ def two_gaussians(x, rng, n_init=10, max_iter=100, tol=1e-3, reg=1e-6):
     return best
 
 
+def _median_split(x):
+    """Degenerate data: split along the widest direction."""
+    axis = np.argmax(np.var(x, axis=0))
+    side = x[:, axis] > np.median(x[:, axis])
+    return np.stack([np.where(side, -1.0, 0.0),
+                     np.where(side, 0.0, -1.0)], axis=1)
+
+
 def two_gaussians_batched(x, rng, n_init=10, max_iter=100, tol=1e-3,
-                          reg=1e-6, device='cuda'):
+                          reg=1e-6, device='cuda', fused=None):
     """``two_gaussians`` with the EM of all ``n_init`` restarts advanced
     together as batched fp64 tensor operations on ``device``.
 
@@ -218,6 +226,10 @@ def two_gaussians_batched(x, rng, n_init=10, max_iter=100, tol=1e-3,
     is ~25 launches whatever N, d and n_init are, instead of ~40 NumPy calls
     per restart (0.8 s -> ~15 ms for 2000 x 30-D, 30 s -> ~50 ms for
     10000 x 100-D).  Returns the [N, 2] log joint densities as NumPy.
+
+    ``fused`` (default: on a CUDA device, when the shape fits): the whole EM
+    of all restarts is ONE kernel launch (``ops.gmm2_em``, a thread-block
+    cluster per restart) instead of ~25 launches per iteration.
     """
     import torch
     x_h = np.ascontiguousarray(x, dtype=float)
@@ -231,6 +243,26 @@ def two_gaussians_batched(x, rng, n_init=10, max_iter=100, tol=1e-3,
         resp0[r, 0], resp0[r, 1] = 1 - near, near
     dev = torch.device(device)
     xt = torch.from_numpy(x_h).to(dev)
+    if fused is None:
+        fused = dev.type == 'cuda'
+    if fused:
+        from .. import ops
+        fused = ops.gmm2_applicable(n, d)
+    if fused:
+        # one launch: a thread-block cluster per restart runs its EM start to
+        # finish (csrc/nb200_gmm.cu); the host reads R scores and the winner
+        labels = torch.from_numpy(
+            np.ascontiguousarray(resp0[:, 1, :]).astype(np.uint8)).to(dev)
+        log_p, score, _ = ops.gmm2_em(xt.contiguous(), labels,
+                                      max_iter=max_iter, tol=tol, reg=reg)
+        score_h = score.cpu().numpy()
+        best, best_ll = None, -np.inf
+        for r in range(n_init):
+            if score_h[r] > best_ll:
+                best, best_ll = r, score_h[r]
+        if best is None:
+            return _median_split(x_h)
+        return log_p[best].transpose(0, 1).contiguous().cpu().numpy()
     resp = torch.from_numpy(resp0).to(dev)                      # [R, 2, N]
     eye = torch.eye(d, dtype=torch.float64, device=dev) * reg
     done = torch.zeros(n_init, dtype=torch.bool, device=dev)
@@ -291,8 +323,101 @@ def two_gaussians_batched(x, rng, n_init=10, max_iter=100, tol=1e-3,
 
 # --------------------------------------------------------------------------
 
-def ellipsoids_overlap(ellipsoids):
+def projection_scan(points, c, a):
+    """Dimension search of ``UnitCubeEllipsoidMixture.compute``
+    (nautilus/bounds/basic.py:497-512): for EVERY dimension i of the ellipsoid
+    ``(x - c)^T A (x - c) <= 1``, the log volume factor of its projection
+    along i, rescaled so that it still encloses the projected points.
+
+    The reference inverts an (m-1) x (m-1) matrix and evaluates a quadratic
+    form over all points for each candidate: O(m) inversions and O(n m^3)
+    flops per step of the search.  With y = x - c, G = y A and Q = rowsum(G y)
+    the Schur complement gives all candidates at once,
+
+        y_k^T A_proj,i y_k = Q - G_i^2 / A_ii,
+        log det (A^-1)_kk  = log A_ii - log det A,
+
+    i.e. ONE [n, m] x [m, m] product: O(n m^2) per step.  ``points`` [n, m]
+    and ``c``, ``a`` are tensors of one device (fp64); returns the tensor
+    ``0.5 * log det(scale_i (A^-1)_kk)`` [m] -- what the reference calls
+    ``log_v`` up to the constant 1/2, which does not move its argmin.
+    """
+    import torch
+    y = points - c
+    g = y @ a
+    q = (g * y).sum(dim=1)
+    diag = torch.diagonal(a)
+    scale = (q[:, None] - g * g / diag).amax(dim=0)
+    m = a.shape[0]
+    return 0.5 * ((m - 1) * torch.log(scale) + torch.log(diag) -
+                  torch.linalg.slogdet(a)[1])
+
+
+def overlap_k_min(c, a_inv, pairs, levels=4, grid=1024):
+    """min over s in (0, 1) of
+        K(s) = 1 - d^T (A_1^-1 / (1 - s) + A_2^-1 / s)^-1 d,  d = c_1 - c_2,
+    for all ``pairs`` of ellipsoids at once.  ``c`` [K, m] and ``a_inv``
+    [K, m, m] are tensors of one device.
+
+    One generalised eigen-decomposition per pair turns K into a scalar
+    rational function: with A_1^-1 = L L^T, L^-1 A_2^-1 L^-T = U diag(lam) U^T
+    and v = U^T L^-1 d,
+
+        K(s) = 1 - sum_i v_i^2 s (1 - s) / (s + lam_i (1 - s)),
+
+    which is evaluated on a grid of s for all pairs in one tensor expression
+    and refined ``levels`` times around the minimum (K is convex in s): four
+    levels of 1024 points bracket the minimiser to 1e-11, a few launches in
+    total instead of a d x d solve per function evaluation.
+    """
+    import torch
+    i1 = torch.as_tensor([p[0] for p in pairs], device=c.device)
+    i2 = torch.as_tensor([p[1] for p in pairs], device=c.device)
+    d = c[i1] - c[i2]                                          # [P, m]
+    chol = torch.linalg.cholesky(a_inv[i1])
+    w = torch.linalg.solve_triangular(chol, a_inv[i2], upper=False)
+    w = torch.linalg.solve_triangular(chol, w.transpose(-1, -2), upper=False)
+    lam, u = torch.linalg.eigh(0.5 * (w + w.transpose(-1, -2)))
+    ld = torch.linalg.solve_triangular(chol, d[..., None], upper=False)
+    v2 = (u.transpose(-1, -2) @ ld)[..., 0]**2                 # [P, m]
+    lo = torch.full((len(pairs), ), 1e-9, dtype=c.dtype, device=c.device)
+    hi = 1 - lo
+    t = torch.linspace(0, 1, grid, dtype=c.dtype, device=c.device)
+    k_min = None
+    for _ in range(levels):
+        s = lo[:, None] + (hi - lo)[:, None] * t               # [P, G]
+        k = 1 - (v2[:, None, :] * (s * (1 - s))[..., None] /
+                 (s[..., None] + lam[:, None, :] * (1 - s)[..., None])
+                 ).sum(dim=-1)
+        best = k.argmin(dim=1)
+        k_min = k.gather(1, best[:, None])[:, 0]
+        lo = s.gather(1, (best - 1).clamp(min=0)[:, None])[:, 0]
+        hi = s.gather(1, (best + 1).clamp(max=grid - 1)[:, None])[:, 0]
+    return k_min
+
+
+def ellipsoids_overlap(ellipsoids, device=None):
     """True if any two ellipsoids intersect (nautilus/bounds/union.py:14-40).
+
+    With ``device`` all pairs are tested at once on that device
+    (``overlap_k_min``); the host form below is kept for
+    ``NB200_CONSTRUCT=host`` and as the cross-check of the tests.
+    """
+    if device is not None and len(ellipsoids) > 1:
+        import torch
+        c = torch.as_tensor(np.stack([np.asarray(e.c) for e in ellipsoids]),
+                            device=device)
+        a = torch.as_tensor(np.stack([np.asarray(e.A) for e in ellipsoids]),
+                            device=device)
+        pairs = [(i, j) for i in range(len(ellipsoids))
+                 for j in range(i + 1, len(ellipsoids))]
+        k_min = overlap_k_min(c, torch.linalg.inv(a), pairs)
+        return bool((k_min > 0).any().item())
+    return _ellipsoids_overlap_host(ellipsoids)
+
+
+def _ellipsoids_overlap_host(ellipsoids):
+    """Golden-section form of the same test, NumPy.
 
     Two ellipsoids {(x-c_i)^T A_i (x-c_i) <= 1} are disjoint iff
     K(s) = 1 - d^T (A_1^{-1}/(1-s) + A_2^{-1}/s)^{-1} d  < 0 for some s in

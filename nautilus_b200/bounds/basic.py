@@ -189,25 +189,28 @@ class UnitCubeEllipsoidMixture(_DeviceBound):
         n_dim = points.shape[1]
         kwargs = dict(enlarge_per_dim=enlarge_per_dim, rng=rng)
 
-        def projected_log_v(a_inv, c, cols, drop):
-            # volume of the ellipsoid's projection without column `drop`,
-            # rescaled to still enclose the projected points
-            keep = [i for i in range(len(cols)) if i != drop]
-            sub_inv = a_inv[np.ix_(keep, keep)]
-            sub = np.linalg.inv(sub_inv)
-            diff = points[:, [cols[i] for i in keep]] - c[keep]
-            scale = np.max(np.einsum('ij,ij->i', diff @ sub, diff))
-            return 0.5 * np.linalg.slogdet(sub_inv * scale)[1]
+        # dimension search (basic.py:497-512): one [n, m] x [m, m] product on
+        # the construction device gives the projected volume of EVERY
+        # candidate (_construct.projection_scan); the host only reads the
+        # argmin
+        dev = _construct.construction_device()
+        pts_t = torch.from_numpy(np.ascontiguousarray(points))
+        if dev is not None:
+            pts_t = pts_t.to(dev)
+
+        def best_drop(ell, cols):
+            trial = _construct.projection_scan(
+                pts_t[:, cols],
+                torch.from_numpy(ell.c).to(pts_t.device),
+                torch.from_numpy(ell.A).to(pts_t.device))
+            return int(torch.argmin(trial).item())
 
         # backward pass: hand dimensions to the cube while the volume shrinks
         in_cube = np.zeros(n_dim, dtype=bool)
         ell = Ellipsoid.compute(points, **kwargs)
         while np.sum(~in_cube) > 1:
             cols = list(np.flatnonzero(~in_cube))
-            a_inv = np.linalg.inv(ell.A)
-            trial = [projected_log_v(a_inv, ell.c, cols, i)
-                     for i in range(len(cols))]
-            cand = cols[int(np.argmin(trial))]
+            cand = cols[best_drop(ell, cols)]
             in_cube[cand] = True
             smaller = Ellipsoid.compute(points[:, ~in_cube], **kwargs)
             if smaller.log_v < ell.log_v:

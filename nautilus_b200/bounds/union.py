@@ -108,7 +108,8 @@ class Union(_DeviceBound):
                 self.block[index] = True
                 continue
             others = self.bounds[:index] + self.bounds[index + 1:]
-            if not allow_overlap and ellipsoids_overlap(others + new):
+            if not allow_overlap and ellipsoids_overlap(
+                    others + new, device=_construct.construction_device()):
                 return False
             if logsumexp([new[0].log_v, new[1].log_v]) > \
                     self.bounds[index].log_v:

@@ -569,6 +569,33 @@ def mvee_weights(q_t, max_updates=1500, tol=1e-3):
     return u, iters
 
 
+def gmm2_applicable(n, d):
+    """Does ``gmm2_em`` take an [n, d] problem?"""
+    return bool(_lib.lib().nb200_gmm2_applicable(int(n), int(d)))
+
+
+def gmm2_em(x, labels, max_iter=100, tol=1e-3, reg=1e-6):
+    """EM of a 2-component Gaussian mixture for all restarts in one launch
+    (the GaussianMixture call of Union.split, union.py:185-187).  ``x``
+    f64[n, d] CUDA, ``labels`` uint8[R, n] CUDA initial assignments.  Returns
+    CUDA tensors (log_p f64[R, 2, n], score f64[R], iters int32[R])."""
+    _chk_points(x)
+    n, d = x.shape
+    if not (labels.is_cuda and labels.dtype == torch.uint8 and
+            labels.dim() == 2 and labels.shape[1] == n and
+            labels.is_contiguous()):
+        raise ValueError('labels must be a contiguous CUDA uint8 [R, n] '
+                         'tensor')
+    r = labels.shape[0]
+    log_p = torch.empty((r, 2, n), dtype=torch.float64, device=x.device)
+    score = torch.empty(r, dtype=torch.float64, device=x.device)
+    iters = torch.empty(r, dtype=torch.int32, device=x.device)
+    _lib.check(_lib.lib().nb200_gmm2_em(
+        _ptr(x), n, d, _ptr(labels), r, int(max_iter), float(tol), float(reg),
+        _ptr(log_p), _ptr(score), _ptr(iters), _stream()))
+    return log_p, score, iters
+
+
 def mlp_fit(x, y, sizes, n_networks, seed=0, lr=1e-2, beta1=0.9, beta2=0.999,
             eps=1e-8, batch_size=200, max_epochs=10000, tol=0.0, patience=10):
     """Train an ensemble on standardised inputs (neural.py:50-98).

@@ -273,3 +273,70 @@ def test_prior_device_transforms_match_scipy():
     with pytest.raises(NotImplementedError):
         other.unit_to_physical_device(torch.zeros((3, 1),
                                                   dtype=torch.float64))
+
+
+def test_projection_scan_matches_the_per_candidate_form():
+    """The dimension search of UnitCubeEllipsoidMixture.compute
+    (nautilus/bounds/basic.py:497-512) restated per candidate -- delete the
+    column, invert the projected shape matrix, rescale to the farthest point,
+    log det -- against the one-product closed form the device path uses."""
+    import torch
+    rng = np.random.default_rng(3)
+    for n, m in ((400, 2), (600, 7), (2000, 30)):
+        pts = rng.normal(size=(n, m)) @ rng.normal(size=(m, m))
+        c = pts.mean(axis=0) + 0.05 * rng.normal(size=m)
+        a = np.linalg.inv(np.cov(pts.T)) / 25.0
+        a_inv = np.linalg.inv(a)
+        ref = np.zeros(m)
+        for i in range(m):
+            pts_proj = np.delete(pts, i, axis=1)
+            c_proj = np.delete(c, i)
+            a_proj = np.linalg.inv(
+                np.delete(np.delete(a_inv, i, axis=0), i, axis=1))
+            diff = pts_proj - c_proj
+            a_proj = a_proj / np.amax(np.einsum('...i,ij,...j', diff, a_proj,
+                                                diff))
+            ref[i] = np.linalg.slogdet(np.linalg.inv(a_proj))[1]
+        got = _construct.projection_scan(
+            torch.from_numpy(pts), torch.from_numpy(c),
+            torch.from_numpy(a)).numpy()
+        assert np.allclose(2 * got, ref, rtol=0, atol=1e-10 * m)
+        assert np.argmin(got) == np.argmin(ref)
+
+
+def test_batched_overlap_test_matches_golden_section():
+    """All pairs at once through the generalised eigen-decomposition vs the
+    d x d solve per evaluation; also the value of min K itself."""
+    import torch
+
+    class Ell:
+        pass
+
+    rng = np.random.default_rng(5)
+    m = 6
+    decided = 0
+    for trial in range(120):
+        ells = []
+        for k in range(3):
+            e = Ell()
+            mat = rng.normal(size=(m, m))
+            e.A = (mat @ mat.T + m * np.eye(m)) / 4.0
+            e.c = rng.normal(size=m) * rng.uniform(0.05, 0.8)
+            ells.append(e)
+        host = _construct._ellipsoids_overlap_host(ells)
+        dev = _construct.ellipsoids_overlap(ells, device='cpu')
+        assert host == dev
+        decided += host
+        # min K of one pair against a dense scan of the definition
+        a_inv = [np.linalg.inv(e.A) for e in ells[:2]]
+        d = ells[0].c - ells[1].c
+        s = np.linspace(1e-6, 1 - 1e-6, 20001)
+        k_def = np.array([1 - d @ np.linalg.solve(
+            a_inv[0] / (1 - x) + a_inv[1] / x, d) for x in s[::50]])
+        k_min = _construct.overlap_k_min(
+            torch.from_numpy(np.stack([e.c for e in ells])),
+            torch.from_numpy(np.stack([np.linalg.inv(e.A) for e in ells])),
+            [(0, 1)])[0].item()
+        assert k_min <= k_def.min() + 1e-12
+        assert k_min >= k_def.min() - 1e-2 * max(1.0, abs(k_def.min()))
+    assert 10 < decided < 110          # both outcomes exercised
