@@ -24,7 +24,12 @@
  * Blob layout (mirrored by nautilus_b200/csrc/nb200_common.cuh)
  *   meta[0] = L (#bounds); meta[1+i] = start of record i.
  *   record header (16 ints): len, kind(0 cube,1 nautilus), d, K, J, unit,
- *       off_cdf(data), off_mix(rel), off_neural(rel), max_width, 0...
+ *       off_cdf(data), off_mix(rel), off_neural(rel), max_width,
+ *       same_k (1 + index of the mixture whose ellipsoid IS neural bound 0's,
+ *       0: none), amp_log2 (with same_k: ceil(log2(|B_inv|_2 (|B|_2 +
+ *       max|c|))) of that ellipsoid -- how much the round trip x = c + B z ->
+ *       B_inv (x - c) can amplify rounding; bounds the guard band of the
+ *       fused front end's whitening shortcut), 0...
  *   mixture record (8 ints): de, nc, off_idx(rel; d ints: ellipsoid dims then
  *       cube dims), off_c, off_B, off_Binv (data; -1 if de==0), binv_is_lower, 0
  *   neural record (12 ints): off_c, off_Binv, binv_is_lower, n_net, n_lay,

@@ -451,6 +451,14 @@ def pack_record(spec, data, cdf=None):
                     np.array_equal(e['c'], nbe['c']) and
                     np.array_equal(e['B_inv'], nbe['B_inv'])):
                 hdr[10] = k + 1
+                # rounding amplification of x = c + B z -> B_inv (x - c):
+                # the fused front end takes t = s z for the whitened point
+                # unless the squared radius is within a guard band of 1
+                # whose width follows from this number (nb200_front_mma.cu)
+                amp = np.linalg.norm(e['B_inv'], 2) * (
+                    np.linalg.norm(e['B'], 2) + np.max(np.abs(e['c'])))
+                hdr[11] = int(np.clip(np.ceil(np.log2(max(amp, 1.0))), 0, 62)
+                              ) if np.isfinite(amp) else 62
                 break
     rec = np.concatenate([hdr, mix_recs.ravel(), nb_recs.ravel()] + tail)
     rec = rec.astype(np.int32)

@@ -24,6 +24,9 @@
 // proposal 8q + p for everything scalar (acceptance uniform, radial factor,
 // disposition, likelihood).  The warps of a CTA never synchronise with each
 // other inside the loop.
+#include <math.h>
+#include <stdlib.h>
+
 #include "nb200_device.cuh"
 #include "nb200_rng.cuh"
 #include "nb200_tc.cuh"
@@ -67,6 +70,10 @@ struct FrontMmaArgs {
   // emulator input rows in fp16 (NB200_MLP_F16): k0p halves per row, two to
   // a 32-bit word, instead of k0p tf32 words
   int xs_f16;
+  // whitening shortcut (FAST kernels; the neural bound's ellipsoid is the
+  // mixture's): half-width of the guard band around r^2 = 1 inside which the
+  // exact whitening is redone (see k_front_mma)
+  double fast_tau;
 };
 
 // global proposal index (the Philox counter) of local proposal i
@@ -117,7 +124,70 @@ __device__ __forceinline__ void mma_rows(const double* __restrict__ frag_lane,
   }
 }
 
-template <int D8>
+// Columns i0, i0 + 1 of the emulator's input row of proposal gi from the
+// whitened coordinates t0, t1: standardised, rounded, the constant-one bias
+// column at index d (pack_tc), zeros behind it.
+__device__ __forceinline__ void emit_xs(const FrontMmaArgs& A, float* xs32,
+                                        long long gi, int i0, int d, double t0,
+                                        double t1, double m0, double m1,
+                                        double s0, double s1, bool wanted) {
+  float v0 = (float)((t0 - m0) * s0);
+  float v1 = (float)((t1 - m1) * s1);
+  if (i0 >= d) v0 = i0 == d ? 1.0f : 0.0f;
+  if (i0 + 1 >= d) v1 = i0 + 1 == d ? 1.0f : 0.0f;
+  if (A.xs_f16) {
+    if (wanted)
+      reinterpret_cast<uint32_t*>(xs32)[gi * (long long)(A.k0p >> 1) +
+                                        (i0 >> 1)] = pack_f16x2(v0, v1);
+  } else {
+    uint32_t k0, k1;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
+    if (wanted)
+      *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
+          make_uint2(k0, k1);
+  }
+}
+
+// The same from z and the radial factor (FAST kernels): (s z - mean) / scale
+// as one multiply and one FMA, the padding selects only where the row ends.
+__device__ __forceinline__ void emit_xs_fast(const FrontMmaArgs& A,
+                                             float* xs32, long long gi, int i0,
+                                             int d, bool tail, double t0,
+                                             double t1, double s0, double s1,
+                                             double nms0, double nms1,
+                                             bool wanted) {
+  float v0 = (float)fma(t0, s0, nms0);
+  float v1 = (float)fma(t1, s1, nms1);
+  if (tail) {
+    if (i0 >= d) v0 = i0 == d ? 1.0f : 0.0f;
+    if (i0 + 1 >= d) v1 = i0 + 1 == d ? 1.0f : 0.0f;
+  }
+  if (!wanted) return;
+  if (A.xs_f16) {
+    reinterpret_cast<uint32_t*>(xs32)[gi * (long long)(A.k0p >> 1) +
+                                      (i0 >> 1)] = pack_f16x2(v0, v1);
+  } else {
+    uint32_t k0, k1;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
+    *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
+        make_uint2(k0, k1);
+  }
+}
+
+// FAST (the neural bound's ellipsoid IS the mixture's, the usual unimodal
+// bound): the whitened point t = B_inv (x - c) of x = c + s B z is s z up to
+// the rounding of the round trip, and its squared radius is s^2 |z|^2.  The
+// emulator's input row -- rounded to fp16 / tf32 anyway -- is taken from s z
+// while z is still in shared memory, and the second pass of DMMAs (half of
+// the kernel's tensor work) is skipped UNLESS some proposal of the tile has
+// s^2 |z|^2 within fast_tau of 1: then the exact whitening decides, for the
+// whole tile, as in the other kernels.  fast_tau is 256 d eps times the
+// rounding amplification of the round trip (amp_log2 in the record header),
+// at least 1e-9, so the membership decisions stay those of the exact
+// arithmetic; a tile takes the exact path with probability ~16 d fast_tau.
+template <int D8, bool FAST>
 __global__ void __launch_bounds__(fm_warps(D8) * 32, D8 <= 64 ? 2 : 1)
 k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             const double* __restrict__ data, double* __restrict__ points,
@@ -137,7 +207,9 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
   double* cN = cM + d8;                    // d8: centre of the neural bound
   double* meanN = cN + d8;                 // d8
   double* iscaleN = meanN + d8;            // d8: 1 / scale
-  double* rows_all = iscaleN + d8;         // FM_WARPS x 32 x S
+  double* nmsN = iscaleN + d8;             // d8: -mean / scale
+  double* muL = nmsN + d8;                 // d8: centre of a Gaussian likelihood
+  double* rows_all = muL + d8;             // FM_WARPS x 32 x S
   const int32_t* nb = rec.nb(0);
   const int32_t* mix = rec.mix(0);
 
@@ -154,14 +226,20 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     sm[which * fsz + (fm_row_block<D8>(I) + Kb) * 32 + ln] =
         (i < d && j < d) ? src[(size_t)i * d + j] : 0.0;
   }
-  for (int e = threadIdx.x; e < 4 * d8; e += FM_THREADS) {
+  // a Gaussian likelihood is summed in the fragment layout, next to the
+  // unit-cube test (four lanes share a proposal's row); the others walk the
+  // finished row
+  const bool gauss = A.log_l != nullptr && A.like_id == NB200_LIKE_GAUSSIAN;
+  for (int e = threadIdx.x; e < 6 * d8; e += FM_THREADS) {
     const int which = e / d8, i = e - which * d8;
     double v = 0.0;
     if (i < d) {
       if (which == 0) v = data[mix[3] + i];
       else if (which == 1) v = data[nb[0] + i];
       else if (which == 2) v = data[nb[5] + i];
-      else v = 1.0 / data[nb[6] + i];
+      else if (which == 3) v = 1.0 / data[nb[6] + i];
+      else if (which == 4) v = -data[nb[5] + i] * (1.0 / data[nb[6] + i]);
+      else if (gauss) v = A.like_p[2 + i];
     }
     cM[e] = v;
   }
@@ -228,6 +306,8 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     for (int g = 0; g < 4; ++g)
       sg[g] = __shfl_sync(0xffffffffu, s_own, 4 * p + g);
     __syncwarp();
+    const bool emit = FAST && !A.gather;
+    const double r2_fast = s_own * s_own * n2_own;
 
     // ---- x = s (B z) + c in place, highest row block first (B is lower
     // triangular: block I needs z[k < 8I + 8], which the blocks below have
@@ -235,6 +315,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     // The coordinates also leave for global memory straight from the
     // fragments: the four lanes of a proposal cover 64 contiguous bytes.
     bool cube[4] = {true, true, true, true};
+    double ll2[4] = {0.0, 0.0, 0.0, 0.0};  // sum (x - mu)^2, this lane's columns
     const double* row_lane = rows + p * S + q;
     const bool pair_ok = (d & 1) == 0;     // 16-byte stores need even offsets
     // (row-block loops are unrolled only for narrow rows: 13 blocks x 26
@@ -243,9 +324,24 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     for (int I = nI - 1; I >= 0; --I) {
       double T[4][2];
       mma_rows<D8, false>(fB + lane, I, 2 * I + 2, row_lane, nullptr, T);
-      __syncwarp();              // every lane has read this block's columns
       const int i0 = 8 * I + 2 * q;
+      if (emit) {
+        // this lane's columns of z, before x takes their place
+        const double2 sc = *reinterpret_cast<const double2*>(iscaleN + i0);
+        const double2 nm = *reinterpret_cast<const double2*>(nmsN + i0);
+        const bool tail = 8 * I + 8 > d;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const double2 zz = *reinterpret_cast<const double2*>(
+              rows + (8 * g + p) * S + i0);
+          const long long gi = base + 8 * g + p;
+          emit_xs_fast(A, xs32, gi, i0, d, tail, sg[g] * zz.x, sg[g] * zz.y,
+                       sc.x, sc.y, nm.x, nm.y, gi < A.n);
+        }
+      }
+      __syncwarp();              // every lane has read this block's columns
       const double c0 = cM[i0], c1 = cM[i0 + 1];
+      const double mu0 = muL[i0], mu1 = muL[i0 + 1];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const double x0 = fma(sg[g], T[g][0], c0);
@@ -254,6 +350,11 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             make_double2(x0, x1);
         if (i0 < d) cube[g] = cube[g] && (x0 >= 0.0) && (x0 < 1.0);
         if (i0 + 1 < d) cube[g] = cube[g] && (x1 >= 0.0) && (x1 < 1.0);
+        if (gauss) {
+          // (padding columns: x = 0 and mu = 0)
+          const double e0 = x0 - mu0, e1 = x1 - mu1;
+          ll2[g] = fma(e1, e1, fma(e0, e0, ll2[g]));
+        }
         const long long gi = base + 8 * g + p;
         if (gi < A.n) {
           double* dst = points + gi * (long long)d + i0;
@@ -274,9 +375,35 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
       ok &= __shfl_xor_sync(0xffffffffu, ok, 2);
       cube_bits |= ok << g;
     }
+    double ll2_own = 0.0;
+    if (gauss) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        ll2[g] += __shfl_xor_sync(0xffffffffu, ll2[g], 1);
+        ll2[g] += __shfl_xor_sync(0xffffffffu, ll2[g], 2);
+      }
+      ll2_own = q == 0 ? ll2[0] : q == 1 ? ll2[1] : q == 2 ? ll2[2] : ll2[3];
+    }
     __syncwarp();
     if (A.gather) continue;      // materialize: the row is all that is wanted
 
+    double r2m_own, r2n_own;
+    bool exact = true;
+    if (FAST) {
+      // input columns behind the padded row width (bias / zeros)
+      for (int I = nI; 8 * I < A.k0p; ++I) {
+        const int i0 = 8 * I + 2 * q;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const long long gi = base + 8 * g + p;
+          emit_xs(A, xs32, gi, i0, d, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                  gi < A.n);
+        }
+      }
+      exact = __any_sync(0xffffffffu, fabs(r2_fast - 1.0) < A.fast_tau);
+      r2m_own = r2n_own = r2_fast;
+    }
+    if (exact) {
     // ---- whitening(s): squared radii, emulator input rows -------------------
     double r2m[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the mixture's ellipsoid
     double r2n[4] = {0.0, 0.0, 0.0, 0.0};   // w.r.t. the neural bound's
@@ -310,28 +437,12 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         r2n[g] = fma(T[g][1], T[g][1], fma(T[g][0], T[g][0], r2n[g]));
-        // standardised, tf32-rounded input row with the constant-one bias
-        // column at index d (pack_tc)
-        float v0 = (float)((T[g][0] - m0) * s0);
-        float v1 = (float)((T[g][1] - m1) * s1);
-        if (i0 >= d) v0 = i0 == d ? 1.0f : 0.0f;
-        if (i0 + 1 >= d) v1 = i0 + 1 == d ? 1.0f : 0.0f;
         const long long gi = base + 8 * g + p;
         // rows cut by the unit cube are never looked at by the emulator
         const bool wanted =
             gi < A.n && (!A.unit || ((cube_bits >> g) & 1u));
-        if (A.xs_f16) {
-          if (wanted)
-            reinterpret_cast<uint32_t*>(xs32)[gi * (long long)(A.k0p >> 1) +
-                                              (i0 >> 1)] = pack_f16x2(v0, v1);
-        } else {
-          uint32_t k0, k1;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k0) : "f"(v0));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(k1) : "f"(v1));
-          if (wanted)
-            *reinterpret_cast<uint2*>(xs32 + gi * (long long)A.k0p + i0) =
-                make_uint2(k0, k1);
-        }
+        emit_xs(A, xs32, gi, i0, d, T[g][0], T[g][1], m0, m1, s0, s1,
+                wanted || (FAST && gi < A.n));
       }
     }
 #pragma unroll
@@ -345,11 +456,10 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
         r2m[g] = r2n[g];
       }
     }
+    r2m_own = q == 0 ? r2m[0] : q == 1 ? r2m[1] : q == 2 ? r2m[2] : r2m[3];
+    r2n_own = q == 0 ? r2n[0] : q == 1 ? r2n[1] : q == 2 ? r2n[2] : r2n[3];
+    }
     // ---- disposition of this lane's own proposal (8q + p) -------------------
-    const double r2m_own = q == 0 ? r2m[0] : q == 1 ? r2m[1]
-                                                    : q == 2 ? r2m[2] : r2m[3];
-    const double r2n_own = q == 0 ? r2n[0] : q == 1 ? r2n[1]
-                                                    : q == 2 ? r2n[2] : r2n[3];
     if (gi_own < A.n) {
       uint8_t cd = NB200_CODE_IN_SHELL;
       bool in_ell = false;
@@ -368,10 +478,10 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
       maskj[gi_own] = in_ell ? 1 : 0;
       if (A.log_l)
         A.log_l[gi_own] =
-            cd == NB200_CODE_IN_SHELL
-                ? front_mma_loglike(A.like_id, A.like_p,
-                                    rows + (8 * q + p) * S, d)
-                : nan("");
+            cd != NB200_CODE_IN_SHELL ? nan("")
+            : gauss ? -0.5 * __ldg(A.like_p) * ll2_own + __ldg(A.like_p + 1)
+                    : front_mma_loglike(A.like_id, A.like_p,
+                                        rows + (8 * q + p) * S, d);
     }
     __syncwarp();
   }
@@ -393,7 +503,7 @@ bool front_mma_applicable(const int32_t* meta_h, int bound, size_t* smem_out,
   // wide rows: triangular-packed factors, which must be exactly lower
   if (fm_tri(d8) && !(rec.mix(0)[6] && (same || nb[2]))) return false;
   const size_t doubles = (size_t)(same ? 2 : 3) * fm_fac_doubles(d8) +
-                         4 * (size_t)d8 + (size_t)fm_warps(d8) * 32 * S;
+                         6 * (size_t)d8 + (size_t)fm_warps(d8) * 32 * S;
   if (doubles * 8 > (d8 <= 64 ? 200 : 227) * 1024) return false;
   if (smem_out) *smem_out = doubles * 8;
   if (args) {
@@ -422,27 +532,30 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
   A.gather = gather;
   A.xs_f16 = xs_f16;
   if (xs_f16) A.k0p = (A.d + 1 + 15) / 16 * 16;
+  // whitening shortcut: only when one whitening serves both ellipsoids and
+  // the guard band that keeps the decisions exact is narrow
+  A.fast_tau = 0.0;
+  if (A.same) {
+    const Rec rec = record(meta_h, bound);
+    double tau = ldexp(256.0 * A.d, -53 + rec.r[11]);
+    if (tau < 1e-9) tau = 1e-9;
+    if (const char* env = getenv("NB200_FRONT_TAU")) tau = atof(env);
+    if (tau > 0.0 && (tau <= 1e-4 || getenv("NB200_FRONT_TAU")))
+      A.fast_tau = tau;
+  }
+  const bool fast = A.fast_tau > 0.0;
   void (*kern)(const FrontMmaArgs, const int32_t*, const double*, double*,
                uint8_t*, uint8_t*, float*) = nullptr;
+#define NB_FM_CASE(W) \
+  case W: kern = fast ? k_front_mma<W, true> : k_front_mma<W, false>; break;
   switch (A.d8) {
-    case 8: kern = k_front_mma<8>; break;
-    case 16: kern = k_front_mma<16>; break;
-    case 24: kern = k_front_mma<24>; break;
-    case 32: kern = k_front_mma<32>; break;
-    case 40: kern = k_front_mma<40>; break;
-    case 48: kern = k_front_mma<48>; break;
-    case 56: kern = k_front_mma<56>; break;
-    case 64: kern = k_front_mma<64>; break;
-    case 72: kern = k_front_mma<72>; break;
-    case 80: kern = k_front_mma<80>; break;
-    case 88: kern = k_front_mma<88>; break;
-    case 96: kern = k_front_mma<96>; break;
-    case 104: kern = k_front_mma<104>; break;
-    case 112: kern = k_front_mma<112>; break;
-    case 120: kern = k_front_mma<120>; break;
-    case 128: kern = k_front_mma<128>; break;
+    NB_FM_CASE(8) NB_FM_CASE(16) NB_FM_CASE(24) NB_FM_CASE(32)
+    NB_FM_CASE(40) NB_FM_CASE(48) NB_FM_CASE(56) NB_FM_CASE(64)
+    NB_FM_CASE(72) NB_FM_CASE(80) NB_FM_CASE(88) NB_FM_CASE(96)
+    NB_FM_CASE(104) NB_FM_CASE(112) NB_FM_CASE(120) NB_FM_CASE(128)
     default: NB_CHECK(false, "DMMA front kernel: n_dim > 128");
   }
+#undef NB_FM_CASE
   const int FM_WARPS = fm_warps(A.d8), FM_THREADS = FM_WARPS * 32;
   NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,

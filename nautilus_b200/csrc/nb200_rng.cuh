@@ -54,7 +54,10 @@ __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0,
   const float u1 = ((float)(a >> 9) + 0.5f) * 1.1920928955078125e-7f;
   const float ang =
       ((float)(b >> 8) * 5.9604644775390625e-8f - 0.5f) * 6.283185307179586f;
-  const float rr = sqrtf(-2.0f * __logf(u1));
+  // (sqrt.approx: one MUFU op, ~1 ulp; sqrtf is a MUFU.RSQ plus a Newton
+  // step and a range fix-up)
+  float rr;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(-2.0f * __logf(u1)));
   n0 = rr * __cosf(ang);
   n1 = rr * __sinf(ang);
 }

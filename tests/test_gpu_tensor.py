@@ -304,3 +304,44 @@ def test_fused_cycle_config5_bound(golden):
     cnt = _fused_vs_staged(spec, 1 << 15, like, seed=2, mode=ops.MLP_F16)
     assert cnt[ops.CNT_NN_REJECT] > 0
     _fused_vs_staged(spec, 3000, like, seed=3, mode=ops.MLP_TF32)
+
+
+@pytest.mark.parametrize('name,n', [('cfg2_bound_d30', 1 << 17),
+                                    ('nautilus_d4', 1 << 15),
+                                    ('cfg5_bound_d100', 1 << 14)])
+def test_front_whitening_shortcut_decides_like_the_exact_whitening(
+        golden, monkeypatch, name, n):
+    """k_front_mma<.., FAST>: when the neural bound's ellipsoid is the
+    mixture's, the whitened point of x = c + s B z is taken as s z and the
+    second DMMA pass is skipped unless r^2 is within a guard band of 1.
+    NB200_FRONT_TAU overrides the band: 2 sends EVERY tile through the exact
+    whitening (the kernel of the previous round), 1e-3 about half of them.
+    Dispositions, likelihoods, sums and counters must not depend on it."""
+    from nautilus_b200 import likelihoods
+    spec = flat_to_spec(golden(name))
+    d = int(spec['n_dim'])
+    like = likelihoods.Gaussian(d, sigma=0.3)
+    stack = ops.DeviceStack([spec])
+    for mode in (ops.MLP_F16, ops.MLP_TF32):
+        runs = []
+        for tau in ('2', '1e-3', None):
+            if tau is None:
+                monkeypatch.delenv('NB200_FRONT_TAU', raising=False)
+            else:
+                monkeypatch.setenv('NB200_FRONT_TAU', tau)
+            out = stack.cycle(0, n, seed=11, offset=123, stream_id=2,
+                              like_id=like.like_id,
+                              like_params=like.device_params('cuda'),
+                              log_l_min=-5.0, mode=mode)
+            runs.append({k: out[k].clone() for k in
+                         ('points', 'code', 'log_l', 'counters', 'lse')})
+        exact = runs[0]
+        assert int((exact['code'] == ops.CODE_IN_SHELL).sum()) > 0
+        for other in runs[1:]:
+            assert torch.equal(exact['points'], other['points'])
+            assert torch.equal(exact['code'], other['code'])
+            assert torch.equal(exact['counters'], other['counters'])
+            assert torch.equal(exact['log_l'].nan_to_num(nan=-7e77),
+                               other['log_l'].nan_to_num(nan=-7e77))
+            assert torch.allclose(exact['lse'], other['lse'], rtol=1e-13,
+                                  atol=0)
