@@ -550,11 +550,12 @@ def run_gpu(args):
     total_stage = sum(stage_ms.values()) or 1.0
     top = max(stage_ms, key=stage_ms.get)
     evaluated = result['raw'] / world - 0   # ~all proposals reach the MLP
-    traffic = None
+    traffic, traffic_all = None, None
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top)
+            traffic_all = json.load(f)
+        traffic = traffic_all.get(top)
     if top == 'mlp_predict':
         flops = MLP_FLOPS_PER_POINT * evaluated
         achieved = flops / (stage_ms[top] * 1e-3) / 1e12
@@ -586,12 +587,27 @@ def run_gpu(args):
         with open(ppath) as f:
             fp64_peak = float(json.load(f)['dmma_tflops_w8_16warps'])
     if 'fused_cycle' in stage_ms:
-        fl = 2.0 * 2 * (D * (D + 1) / 2) * n      # x = Bz + c, t = Binv(x - c)
+        # x = B z + c on the FP64 tensor cores.  The second product,
+        # t = B_inv (x - c), is skipped by the whitening shortcut whenever the
+        # neural bound's ellipsoid is the mixture's (this workload; it is
+        # redone only inside the guard band around r^2 = 1), so one
+        # triangular product per proposal is what the kernel executes
+        fl = 2.0 * (D * (D + 1) / 2) * n
         ach = fl / (stage_ms['fused_cycle'] * 1e-3) / 1e12
         roofline['front_fp64'] = {
             'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s',
             'frac': ach / fp64_peak, 'flops_per_launch': fl,
             'peak_source': 'measured DMMA m8n8k4 (profiles/r1_peak_dmma.json)'}
+        # the front kernel writes every algorithmic byte of the step
+        # (row + log_l + disposition): its own HBM figure, whichever kernel
+        # is the longest of the step
+        nbytes = ALGO_BYTES_PER_PROPOSAL * n
+        ach = nbytes / (stage_ms['fused_cycle'] * 1e-3) / 1e9
+        roofline['front_hbm'] = {
+            'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s',
+            'frac': ach / peaks['hbm'], 'bytes_per_launch': nbytes,
+            'ms_per_launch': stage_ms['fused_cycle'],
+            'traffic': (traffic_all or {}).get('fused_cycle')}
     if 'mlp_predict' in stage_ms:
         fl = MLP_FLOPS_PER_POINT * evaluated
         ach = fl / (stage_ms['mlp_predict'] * 1e-3) / 1e12

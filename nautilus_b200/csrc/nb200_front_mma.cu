@@ -215,16 +215,30 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
 
   // factors -> fragment order: frag[I][Kb][lane] = M[8I + lane/4][4Kb + lane%4]
   const int n_fac = A.same ? 2 : 3;
-  for (int e = threadIdx.x; e < n_fac * d8 * d8; e += FM_THREADS) {
-    const int which = e / (d8 * d8), rem = e - which * (d8 * d8);
-    const int blk = rem >> 5, ln = rem & 31;
-    const int I = blk / nK, Kb = blk - I * nK;
-    if (TRI && Kb >= 2 * I + 2) continue;    // above the diagonal: not kept
-    const int i = 8 * I + (ln >> 2), j = 4 * Kb + (ln & 3);
-    const double* src = data + (which == 0 ? mix[4] : which == 1 ? mix[5]
-                                                                 : nb[1]);
-    sm[which * fsz + (fm_row_block<D8>(I) + Kb) * 32 + ln] =
-        (i < d && j < d) ? src[(size_t)i * d + j] : 0.0;
+  // (four independent loads in flight per thread: the staging is a chain of
+  // L2 round trips otherwise, ~5 % of the kernel at 2^20 proposals)
+  for (int e0 = threadIdx.x; e0 < n_fac * d8 * d8; e0 += 4 * FM_THREADS) {
+    double val[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * FM_THREADS;
+      dst[u] = -1;
+      val[u] = 0.0;
+      if (e >= n_fac * d8 * d8) continue;
+      const int which = e / (d8 * d8), rem = e - which * (d8 * d8);
+      const int blk = rem >> 5, ln = rem & 31;
+      const int I = blk / nK, Kb = blk - I * nK;
+      if (TRI && Kb >= 2 * I + 2) continue;  // above the diagonal: not kept
+      const int i = 8 * I + (ln >> 2), j = 4 * Kb + (ln & 3);
+      const double* src = data + (which == 0 ? mix[4] : which == 1 ? mix[5]
+                                                                   : nb[1]);
+      dst[u] = which * fsz + (fm_row_block<D8>(I) + Kb) * 32 + ln;
+      if (i < d && j < d) val[u] = __ldg(src + (size_t)i * d + j);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u] >= 0) sm[dst[u]] = val[u];
   }
   // a Gaussian likelihood is summed in the fragment layout, next to the
   // unit-cube test (four lanes share a proposal's row); the others walk the
@@ -251,6 +265,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
   const int p = lane >> 2, q = lane & 3;
   double* rows = rows_all + (size_t)warp * 32 * S;
   const int nblk = (d + 3) >> 2;           // Philox blocks of 4 normals
+  const double inv_d = 1.0 / (double)d;
   const long long n_tiles = (A.n + 31) / 32;
   const long long tile_step = (long long)gridDim.x * FM_WARPS;
 
@@ -300,7 +315,9 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
     const double n2_own = q == 0 ? n2g[0] : q == 1 ? n2g[1]
                                                    : q == 2 ? n2g[2] : n2g[3];
     // radial factor of the uniform ball draw (basic.py:377-379)
-    const double s_own = pow(u_own, 1.0 / (double)d) / sqrt(n2_own);
+    // (u^(1/d) as exp(log(u) / d): ~2e-16 relative, half of pow()'s
+    // instructions; u = 0 gives 0 either way)
+    const double s_own = exp(log(u_own) * inv_d) * rsqrt(n2_own);
     double sg[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g)

@@ -345,3 +345,66 @@ def test_front_whitening_shortcut_decides_like_the_exact_whitening(
                                other['log_l'].nan_to_num(nan=-7e77))
             assert torch.allclose(exact['lse'], other['lse'], rtol=1e-13,
                                   atol=0)
+
+
+def _synthetic_spec(d, rng, hidden=(24, 12)):
+    """One ellipsoid shared by the mixture and the neural bound, two small
+    random networks."""
+    m = rng.normal(size=(d, d))
+    cov = 0.004 * (m @ m.T / d + np.eye(d))
+    B = np.linalg.cholesky(cov)
+    ell = dict(c=0.5 + 0.01 * rng.normal(size=d), B=B,
+               B_inv=np.tril(np.linalg.solve(B, np.eye(d))))
+    sizes = (d, ) + hidden + (1, )
+    coefs = [[rng.normal(size=(a, b)) / np.sqrt(a)
+              for a, b in zip(sizes[:-1], sizes[1:])] for _ in range(2)]
+    intercepts = [[0.1 * rng.normal(size=b) for b in sizes[1:]]
+                  for _ in range(2)]
+    emu = dict(mean=0.05 * rng.normal(size=d),
+               scale=0.5 + rng.uniform(size=d), coefs=coefs,
+               intercepts=intercepts)
+    return dict(kind='nautilus', n_dim=d, unit=True, log_v_all=np.zeros(1),
+                mixtures=[dict(dim_cube=np.zeros(d, bool), ell=ell)],
+                neural=[dict(ell={k: v.copy() for k, v in ell.items()},
+                             emulator=emu, score_predict_min=0.0)])
+
+
+@pytest.mark.parametrize('d', [8, 16, 32, 47, 64])
+def test_front_whitening_shortcut_row_widths(monkeypatch, d):
+    """Row widths at and around multiples of 8 / 16: the bias column and the
+    zero padding of the emulator's input row lie behind the padded row of the
+    proposal (d = 16, 32, 64) or inside it; the shortcut must hand the
+    emulator what the exact whitening hands it."""
+    from nautilus_b200 import likelihoods
+    spec = _synthetic_spec(d, np.random.default_rng(d))
+    meta, _ = pack_stack([spec])
+    rec = meta[meta[1]:]
+    assert rec[10] == 1 and 0 <= rec[11] < 30
+    like = likelihoods.Gaussian(d, sigma=0.2)
+    stack = ops.DeviceStack([spec])
+    n = 1 << 14
+    for mode in (ops.MLP_F16, ops.MLP_TF32):
+        runs = []
+        for tau in ('2', None):
+            if tau is None:
+                monkeypatch.delenv('NB200_FRONT_TAU', raising=False)
+            else:
+                monkeypatch.setenv('NB200_FRONT_TAU', tau)
+            out = stack.cycle(0, n, seed=d, offset=5, stream_id=1,
+                              like_id=like.like_id,
+                              like_params=like.device_params('cuda'),
+                              log_l_min=-5.0, mode=mode)
+            runs.append({k: out[k].clone() for k in
+                         ('points', 'code', 'log_l', 'counters')})
+        exact, fast = runs
+        frac = float((exact['code'] == ops.CODE_IN_SHELL).float().mean())
+        assert 1e-3 < frac < 0.999, frac
+        assert torch.equal(exact['points'], fast['points'])
+        assert torch.equal(exact['code'], fast['code'])
+        assert torch.equal(exact['counters'], fast['counters'])
+        assert torch.equal(exact['log_l'].nan_to_num(nan=-7e77),
+                           fast['log_l'].nan_to_num(nan=-7e77))
+        # the fused decisions are those of contains() on the finished rows
+        monkeypatch.delenv('NB200_FRONT_TAU', raising=False)
+        inside = stack.contains(0, fast['points'], mode=mode)
+        assert torch.equal(inside, fast['code'] == ops.CODE_IN_SHELL)
