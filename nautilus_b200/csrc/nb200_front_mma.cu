@@ -45,6 +45,21 @@ __host__ __device__ constexpr bool fm_tri(int d8) { return d8 > 64; }
 __host__ __device__ constexpr int fm_fac_doubles(int d8) {
   return fm_tri(d8) ? (d8 / 8) * (d8 / 8 + 1) * 32 : d8 * d8;
 }
+// FAST kernels of wide rows stage ONE factor (B): the exact whitening runs
+// for one tile in a million and fetches B_inv from global memory, so the
+// shared memory of the second factor holds more rows instead -- 6 warps
+// instead of 4 at d = 100.  Shared memory of such a CTA in doubles, and the
+// largest warp count that fits 220 KB:
+__host__ __device__ constexpr size_t fm_fast_wide_doubles(int d8, int warps) {
+  return (size_t)fm_fac_doubles(d8) + 6 * (size_t)d8 +
+         (size_t)warps * 32 * (d8 + 4);
+}
+__host__ __device__ constexpr int fm_warps(int d8, bool fast) {
+  if (!(fast && fm_tri(d8))) return fm_warps(d8);
+  for (int w = 8; w > 2; w -= 2)
+    if (fm_fast_wide_doubles(d8, w) * 8 <= 220 * 1024) return w;
+  return 2;
+}
 // first fragment (in units of 32 doubles) of row block I
 template <int D8>
 __device__ __forceinline__ int fm_row_block(int I) {
@@ -99,20 +114,33 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // trip counts and strides are compile-time, so the loop unrolls into
 // LDS / DMMA with immediate offsets (the first version spent more issue
 // slots on address arithmetic than on DMMAs)
-template <int D8, bool SUBTRACT>
+// GLOBAL_B: the B fragments come straight from the row-major matrix in global
+// memory (frag_lane = M, this lane's element of fragment (I, Kb) is
+// M[8 I + lane / 4][4 Kb + lane % 4]) -- the rarely taken exact whitening of
+// the wide FAST kernels; same values, same DMMA sequence as the staged form.
+template <int D8, bool SUBTRACT, bool GLOBAL_B = false>
 __device__ __forceinline__ void mma_rows(const double* __restrict__ frag_lane,
                                          int I, int kb_end,
                                          const double* row_lane,
                                          const double* __restrict__ c_lane,
-                                         double (&T)[4][2]) {
+                                         double (&T)[4][2], int d = 0) {
   constexpr int NK = D8 / 4, S = D8 + 4;
-  frag_lane += fm_row_block<D8>(I) * 32;
+  const int gl = threadIdx.x & 31;
+  const int gi_row = 8 * I + (gl >> 2);
+  if (!GLOBAL_B) frag_lane += fm_row_block<D8>(I) * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
 #pragma unroll
   for (int Kb = 0; Kb < NK; ++Kb) {
     if (Kb < kb_end) {
-      const double b = frag_lane[Kb * 32];
+      double b;
+      if (GLOBAL_B) {
+        const int j = 4 * Kb + (gl & 3);
+        b = (gi_row < d && j < d) ? __ldg(frag_lane + (size_t)gi_row * d + j)
+                                  : 0.0;
+      } else {
+        b = frag_lane[Kb * 32];
+      }
       const double cq = SUBTRACT ? c_lane[4 * Kb] : 0.0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -188,7 +216,7 @@ __device__ __forceinline__ void emit_xs_fast(const FrontMmaArgs& A,
 // at least 1e-9, so the membership decisions stay those of the exact
 // arithmetic; a tile takes the exact path with probability ~16 d fast_tau.
 template <int D8, bool FAST>
-__global__ void __launch_bounds__(fm_warps(D8) * 32, D8 <= 64 ? 2 : 1)
+__global__ void __launch_bounds__(fm_warps(D8, FAST) * 32, D8 <= 64 ? 2 : 1)
 k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
             const double* __restrict__ data, double* __restrict__ points,
             uint8_t* __restrict__ code, uint8_t* __restrict__ maskj,
@@ -196,12 +224,15 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
   extern __shared__ __align__(16) double sm[];
   const Rec rec{meta + A.rec_off};
   constexpr int d8 = D8, S = D8 + 4, nI = D8 / 8, nK = D8 / 4;
-  constexpr int FM_WARPS = fm_warps(D8), FM_THREADS = FM_WARPS * 32;
+  constexpr int FM_WARPS = fm_warps(D8, FAST), FM_THREADS = FM_WARPS * 32;
   constexpr bool TRI = fm_tri(D8);
+  // wide FAST kernels keep B only; B_inv is read from global memory by the
+  // (rare) exact whitening
+  constexpr bool ONE_FAC = FAST && TRI;
   const int d = A.d;
   constexpr int fsz = fm_fac_doubles(D8);  // doubles per staged factor
   double* fB = sm;                         // B        in fragment order
-  double* fBinv = fB + fsz;                // B_inv (mixture)
+  double* fBinv = fB + (ONE_FAC ? 0 : fsz); // B_inv (mixture)
   double* fN = fBinv + fsz;                // B_inv (neural), if different
   double* cM = fN + (A.same ? 0 : fsz);    // d8: centre of the mixture
   double* cN = cM + d8;                    // d8: centre of the neural bound
@@ -214,7 +245,7 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
   const int32_t* mix = rec.mix(0);
 
   // factors -> fragment order: frag[I][Kb][lane] = M[8I + lane/4][4Kb + lane%4]
-  const int n_fac = A.same ? 2 : 3;
+  const int n_fac = ONE_FAC ? 1 : A.same ? 2 : 3;
   // (four independent loads in flight per thread: the staging is a chain of
   // L2 round trips otherwise, ~5 % of the kernel at 2^20 proposals)
   for (int e0 = threadIdx.x; e0 < n_fac * d8 * d8; e0 += 4 * FM_THREADS) {
@@ -440,8 +471,12 @@ k_front_mma(const FrontMmaArgs A, const int32_t* __restrict__ meta,
       if (8 * I >= A.k0p) break;
       double T[4][2];
       if (I < nI) {
-        mma_rows<D8, true>(fNeural + lane, I, lower_n ? 2 * I + 2 : nK,
-                           row_lane, cN + q, T);
+        if (ONE_FAC)
+          mma_rows<D8, true, true>(data + nb[1], I, 2 * I + 2, row_lane,
+                                   cN + q, T, d);
+        else
+          mma_rows<D8, true>(fNeural + lane, I, lower_n ? 2 * I + 2 : nK,
+                             row_lane, cN + q, T);
       } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g) { T[g][0] = 0.0; T[g][1] = 0.0; }
@@ -573,7 +608,9 @@ int launch_front_mma(const int32_t* meta_h, const int32_t* meta_d,
     default: NB_CHECK(false, "DMMA front kernel: n_dim > 128");
   }
 #undef NB_FM_CASE
-  const int FM_WARPS = fm_warps(A.d8), FM_THREADS = FM_WARPS * 32;
+  const int FM_WARPS = fm_warps(A.d8, fast), FM_THREADS = FM_WARPS * 32;
+  if (fast && fm_tri(A.d8))     // one staged factor, more rows on chip
+    smem = fm_fast_wide_doubles(A.d8, FM_WARPS) * 8;
   NB_CUDA(cudaFuncSetAttribute(kern,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
