@@ -31,9 +31,9 @@ Differences that are deliberate and documented in DESIGN.md:
     ``write_shell_update``) keep the reference's layout; they go to HDF5 when
     h5py is installed and to the built-in '.npz' container (``_store.py``)
     otherwise.  A batch takes well under a millisecond here, so ``run``
-    rewrites the file at structural events (new bound, end of exploration,
-    end of the run) and otherwise at most every ``checkpoint_interval``
-    seconds, not after every batch;
+    rewrites the file at most every ``checkpoint_interval`` seconds (30 by
+    default; 0 = after every step, like the reference) and when it returns,
+    not after every batch;
   * periodic parameters are out of scope and raise.
 """
 
@@ -292,14 +292,14 @@ class Sampler:
                     self.add_bound(verbose=verbose)
                     self.n_update_iter = 0
                     self.n_like_iter = 0
-                    self._checkpoint(force=True)
+                    self._checkpoint()
                 n_like_before = self.n_like
                 self.n_update_iter += self.add_samples(-1, verbose=verbose)
                 self.n_like_iter += self.n_like - n_like_before
                 self._checkpoint()
                 if self.f_live <= f_live:
                     self._finish_exploration(discard_exploration)
-                    self._checkpoint(force=True)
+                    self._checkpoint()
             elif np.any(self.shell_n < n_shell):
                 self.add_samples(int(np.flatnonzero(
                     self.shell_n < n_shell)[0]), verbose=verbose)
@@ -313,7 +313,10 @@ class Sampler:
             success = done()
 
         # whatever happened since the last write (the reference's file is
-        # current after every batch, sampler.py:449-494)
+        # current after every batch, sampler.py:449-494; here a write moves
+        # every stored point to the host and a whole run takes seconds, so
+        # the file is at most `checkpoint_interval` seconds old while the run
+        # lasts and current when it returns)
         if self._dirty:
             self._checkpoint(force=True)
         if verbose:
