@@ -1,21 +1,29 @@
-"""Host-side construction helpers: enclosing ellipsoids, 2-cluster mixtures,
-ellipsoid overlap.
+"""Construction helpers: enclosing ellipsoids, 2-cluster mixtures, the
+dimension search of the cube-ellipsoid mixture, ellipsoid overlap.
 
 Bound *construction* happens between shells (SURVEY.md section 8, row a23 /
-"next" f-1), on a few thousand live points; it is scheduled after the cycle
-kernels and is plain NumPy here.  The algorithms are written from their
-published descriptions, not from the reference's code:
+"next" f-1), on a few thousand live points.  Every piece has a device form
+(the default) and a host NumPy form (``NB200_CONSTRUCT=host``; also the
+cross-check of the tests).  The algorithms are written from their published
+descriptions, not from the reference's code:
 
 * minimum-volume enclosing ellipsoid: Khachiyan's first-order algorithm in
   the lifted space (Todd & Yildirim 2007) with Sherman-Morrison rank-one
-  updates of the inverse and O(N d) updates of the Mahalanobis distances;
-  the reference (nautilus/bounds/basic.py:175-241) runs a batched variant
-  with a full re-inversion per update.
+  updates of the inverse and O(N d) updates of the Mahalanobis distances
+  (device: the persistent cluster kernel behind ``ops.mvee_weights``); the
+  reference (nautilus/bounds/basic.py:175-241) runs a batched variant with a
+  full re-inversion per update.
 * two-component Gaussian mixture by EM with k-means++ restarts (the reference
   calls scikit-learn's GaussianMixture(n_components=2, n_init=10),
-  nautilus/bounds/union.py:185-187).
+  nautilus/bounds/union.py:185-187); device: all restarts in ONE launch,
+  ``ops.gmm2_em`` (csrc/nb200_gmm.cu), or batched tensor operations for
+  shapes outside that kernel's envelope.
+* dimension search (nautilus/bounds/basic.py:497-512): the projected volume of
+  every candidate dimension from one matrix product (``projection_scan``).
 * ellipsoid overlap: Gilitschenski & Hanebeck 2012 (the test cited at
-  nautilus/bounds/union.py:17), minimised by golden-section search.
+  nautilus/bounds/union.py:17); device: all pairs at once through a
+  generalised eigen-decomposition (``overlap_k_min``); host: golden-section
+  search.
 """
 
 import hashlib
