@@ -251,3 +251,39 @@ def test_resume_host_likelihood_with_blobs(tmp_path):
         n_last = len(np.array(f['sampler']['log_l_{}'.format(
             len(c.bounds) - 1)]))
     assert n_last == len(c.log_l[-1])
+
+
+def test_sampler_group_keys_are_the_references():
+    """The attribute names Sampler.write stores in the 'sampler' group are
+    the ones the reference's write() stores (parsed from its source), plus
+    the documented extras; the dataset names follow the same patterns."""
+    import ast
+    import inspect
+    from oracle import ref_arm
+    if not ref_arm.available():
+        pytest.skip('oracle/_ref missing (run oracle/make_ref.sh)')
+    ref_arm._import_reference()
+    import nautilus
+    tree = ast.parse(inspect.getsource(nautilus.Sampler))
+    keys = {}
+    for fn in (n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)
+               and n.name in ('write', 'write_shell_update')):
+        found = []
+        for node in ast.walk(fn):
+            # `for key in [...]: group.attrs[key] = getattr(self, key)`
+            if isinstance(node, ast.For) and isinstance(node.iter, ast.List):
+                found += [e.value for e in node.iter.elts
+                          if isinstance(e, ast.Constant)]
+        keys[fn.name] = found
+    mine = Sampler._ATTRS_CONFIG + Sampler._ATTRS_STATE
+    assert set(keys['write']) - {'points_t', 'shell_t', 'log_l_t',
+                                 'blobs_t'} == set(mine)
+    src = inspect.getsource(Sampler.write_shell_update)
+    for key in keys['write_shell_update']:
+        assert "'{}'".format(key) in src, key
+    src = inspect.getsource(Sampler.write) + inspect.getsource(
+        Sampler._write_rng)
+    for name in ('points_{}', 'log_l_{}', 'blobs_{}', 'points_t', 'shell_t',
+                 'log_l_t', 'blobs_t', 'bound_{}', 'rng_state', 'rng_inc',
+                 'rng_has_uint32', 'rng_uinteger', 'neural_network_{}'):
+        assert name in src, name

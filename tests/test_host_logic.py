@@ -340,3 +340,35 @@ def test_batched_overlap_test_matches_golden_section():
         assert k_min <= k_def.min() + 1e-12
         assert k_min >= k_def.min() - 1e-2 * max(1.0, abs(k_def.min()))
     assert 10 < decided < 110          # both outcomes exercised
+
+
+def test_record_header_same_k_and_rounding_amplification(golden):
+    """Record header words 10 / 11 (include/nautilus_b200.h): which mixture's
+    ellipsoid is the neural bound's, and ceil(log2(|B_inv|_2 (|B|_2 +
+    max|c|))) of it -- the number the front kernel's whitening shortcut
+    derives its guard band from."""
+    spec = flat_to_spec(golden('cfg2_bound_d30'))
+    meta, _ = pack_stack([spec])
+    rec = meta[meta[1]:]
+    ell = spec['mixtures'][0]['ell']
+    amp = np.linalg.norm(ell['B_inv'], 2) * (
+        np.linalg.norm(ell['B'], 2) + np.max(np.abs(ell['c'])))
+    assert rec[10] == 1 and rec[11] == int(np.ceil(np.log2(amp)))
+    # a distinct neural ellipsoid: no shortcut
+    spec['neural'][0]['ell']['c'] = spec['neural'][0]['ell']['c'] + 1e-3
+    meta, _ = pack_stack([spec])
+    rec = meta[meta[1]:]
+    assert rec[10] == 0 and rec[11] == 0
+    # an ill-conditioned shared ellipsoid: the band would be wide, the
+    # launcher turns the shortcut off above 1e-4 (256 d eps 2^amp_log2)
+    d = 6
+    B = np.diag(np.logspace(0, -12, d)) * 0.3
+    ell = dict(c=np.full(d, 0.5), B=B, B_inv=np.diag(1 / np.diag(B)))
+    spec = dict(kind='nautilus', n_dim=d, unit=True, log_v_all=np.zeros(1),
+                mixtures=[dict(dim_cube=np.zeros(d, bool), ell=ell)],
+                neural=[dict(ell={k: v.copy() for k, v in ell.items()},
+                             emulator=None, score_predict_min=0.0)])
+    meta, _ = pack_stack([spec])
+    rec = meta[meta[1]:]
+    assert rec[10] == 1 and rec[11] >= 40
+    assert 256 * d * 2.0**-53 * 2.0**rec[11] > 1e-4
